@@ -1,0 +1,63 @@
+// Shared helpers for libb200gan (sm_100a).  Internal -- the public surface is include/b200gan.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200gan.h"
+
+namespace b200gan {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);   // cudaGetLastError -> return code (+ message)
+int sm_count();
+
+#define B200_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            b200gan::set_error(__VA_ARGS__);    \
+            return B200GAN_EINVAL;              \
+        }                                       \
+    } while (0)
+
+template <typename T> struct io;
+template <> struct io<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct io<__nv_bfloat16> {
+    static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// VEC consecutive elements moved as one (up to 128-bit) access
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) Pack {
+    T v[VEC];
+};
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// floor division / modulo for possibly negative numerators (device)
+__device__ __forceinline__ int floordiv(int a, int b) {
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+}  // namespace b200gan
+
+// dtype dispatch: binds `T` inside the lambda body
+#define B200_DISPATCH(dtype, ...)                                   \
+    [&]() -> int {                                                  \
+        if ((dtype) == B200GAN_F32) {                               \
+            using T = float;                                        \
+            return __VA_ARGS__();                                   \
+        } else if ((dtype) == B200GAN_BF16) {                       \
+            using T = __nv_bfloat16;                                \
+            return __VA_ARGS__();                                   \
+        }                                                           \
+        b200gan::set_error("unsupported dtype %d", (int)(dtype));   \
+        return B200GAN_EINVAL;                                      \
+    }()

@@ -1,0 +1,18 @@
+// Geometry shared by the convolution engines (conv_simt.cu, conv_umma.cu) and their C API.
+#pragma once
+#include "common.cuh"
+
+namespace b200gan {
+
+// y[b][oy][ox][o] = sum_{ky,kx,i} z[b][oy*down+ky-pad0][ox*down+kx-pad0][i] * w[wb][ky][kx][o][i]
+// z = x zero-upsampled by `up`; see include/b200gan.h.
+struct ConvGeom {
+    int b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample;
+};
+
+int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
+                  const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
+                  cudaStream_t st);
+int conv_wgrad_simt(const void* x, const void* gy, float* gw, int dtype, const ConvGeom& g, cudaStream_t st);
+
+}  // namespace b200gan

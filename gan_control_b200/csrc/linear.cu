@@ -1,0 +1,163 @@
+// Dense layers: EqualLinear forward (gan_model.py:189-197) and the small fp32 GEMMs its backward
+// passes need.  These are skinny (M = batch <= 64) and weight-read bound; one tiled CUDA-core
+// kernel with split-K covers them.  The whole-mapping-network persistent kernel lives in
+// mapping.cu.
+#include "common.cuh"
+
+namespace b200gan {
+
+constexpr int LM = 32, LN = 64, LK = 16;
+
+template <typename TA, typename TC>
+__global__ void __launch_bounds__(256) gemm_kernel(const TA* __restrict__ a, const float* __restrict__ b,
+                                                   TC* __restrict__ c, int m, int n, int k, int lda,
+                                                   int ldb, int ldc, int trans_a, int trans_b,
+                                                   float alpha, float beta, const float* __restrict__ bias,
+                                                   float bias_mul, int act, int k_chunk, int use_atomic) {
+    __shared__ float As[LK][LM + 1];
+    __shared__ float Bs[LK][LN + 1];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.y * LM, n0 = blockIdx.x * LN;
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = min(k, k_begin + k_chunk);
+    const int tn = t & 31, tm = t >> 5;   // thread: rows tm*4..+3, cols tn*2..+1
+    float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    for (int k0 = k_begin; k0 < k_end; k0 += LK) {
+        // A tile: LM x LK = 512 elements, 2 per thread
+        for (int e = t; e < LM * LK; e += 256) {
+            int mi, ki;
+            if (trans_a) { mi = e % LM; ki = e / LM; } else { ki = e % LK; mi = e / LK; }
+            int gm = m0 + mi, gk = k0 + ki;
+            float v = 0.f;
+            if (gm < m && gk < k_end) v = io<TA>::ld(trans_a ? a + (int64_t)gk * lda + gm : a + (int64_t)gm * lda + gk);
+            As[ki][mi] = v;
+        }
+        // B tile: LK x LN = 1024 elements, 4 per thread
+        for (int e = t; e < LK * LN; e += 256) {
+            int ni, ki;
+            if (trans_b) { ki = e % LK; ni = e / LK; } else { ni = e % LN; ki = e / LN; }
+            int gn = n0 + ni, gk = k0 + ki;
+            float v = 0.f;
+            if (gn < n && gk < k_end) v = trans_b ? b[(int64_t)gn * ldb + gk] : b[(int64_t)gk * ldb + gn];
+            Bs[ki][ni] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < LK; ++kk) {
+            float b0 = Bs[kk][tn * 2], b1 = Bs[kk][tn * 2 + 1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float av = As[kk][tm * 4 + i];
+                acc[i][0] = fmaf(av, b0, acc[i][0]);
+                acc[i][1] = fmaf(av, b1, acc[i][1]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + tm * 4 + i;
+        if (gm >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            int gn = n0 + tn * 2 + j;
+            if (gn >= n) continue;
+            TC* dst = c + (int64_t)gm * ldc + gn;
+            float v = alpha * acc[i][j];
+            if (use_atomic) {
+                if constexpr (sizeof(TC) == 4) atomicAdd(dst, v);   // split-K: fp32 output only
+            } else {
+                if (beta != 0.f) v += beta * io<TC>::ld(dst);
+                if (bias) v += bias[gn] * bias_mul;
+                if (act) v = 1.4142135623730951f * (v > 0.f ? v : 0.2f * v);
+                io<TC>::st(dst, v);
+            }
+        }
+    }
+}
+
+template <typename TA, typename TC>
+static int launch_gemm(const TA* a, const float* b, TC* c, int m, int n, int k, int lda, int ldb, int ldc,
+                       int trans_a, int trans_b, float alpha, float beta, const float* bias, float bias_mul,
+                       int act, cudaStream_t st) {
+    if (m == 0 || n == 0) return 0;
+    int tiles = (int)(cdiv(m, LM) * cdiv(n, LN));
+    int splits = 1;
+    const bool can_split = sizeof(TC) == 4 && bias == nullptr && act == 0 && (beta == 0.f || beta == 1.f);
+    if (can_split && k >= 1024 && tiles < sm_count()) {
+        splits = (int)cdiv(2 * sm_count(), tiles);
+        int max_splits = k / 256;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    int k_chunk = (int)(cdiv(cdiv(k, splits), LK) * LK);
+    splits = (int)cdiv(k, k_chunk);
+    if (splits > 1 && beta == 0.f) {
+        if (ldc == n) {
+            cudaMemsetAsync(c, 0, sizeof(float) * (size_t)m * n, st);
+        } else {
+            splits = 1;
+            k_chunk = k;
+        }
+    }
+    dim3 grid((unsigned)cdiv(n, LN), (unsigned)cdiv(m, LM), (unsigned)splits);
+    gemm_kernel<TA, TC><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, trans_a, trans_b, alpha, beta,
+                                              bias, bias_mul, act, k_chunk, splits > 1 ? 1 : 0);
+    count_launch();
+    return check_launch("gemm");
+}
+
+// ---- Adam (+ EMA) -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v,
+                                                       float* __restrict__ ema, int64_t numel, float lr,
+                                                       float beta1, float beta2, float eps, float bias_c1,
+                                                       float bias_c2, float ema_decay, float grad_scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        // torch.optim.Adam: denom = sqrt(v)/sqrt(bias_c2) + eps ; p -= lr/bias_c1 * m/denom
+        float denom = sqrtf(vi) / sqrtf(bias_c2) + eps;
+        float pi = p[i] - (lr / bias_c1) * (mi / denom);
+        p[i] = pi;
+        if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
+    }
+}
+
+}  // namespace b200gan
+
+extern "C" int b200gan_linear_fwd(const void* x, const float* w, const float* bias, void* y, int dtype, int m,
+                                  int n, int k, float scale, float bias_mul, int act, void* stream) {
+    using namespace b200gan;
+    B200_REQUIRE(m >= 0 && n >= 1 && k >= 1, "linear_fwd: bad shape");
+    return B200_DISPATCH(dtype, [&] {
+        return launch_gemm<T, T>((const T*)x, w, (T*)y, m, n, k, k, k, n, 0, 1, scale, 0.f, bias, bias_mul, act,
+                                 (cudaStream_t)stream);
+    });
+}
+
+extern "C" int b200gan_gemm_f32(const float* a, const float* b, float* c, int m, int n, int k, int lda, int ldb,
+                                int ldc, int trans_a, int trans_b, float alpha, float beta, void* stream) {
+    using namespace b200gan;
+    B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_f32: bad shape");
+    return launch_gemm<float, float>(a, b, c, m, n, k, lda, ldb, ldc, trans_a, trans_b, alpha, beta, nullptr, 0.f,
+                                     0, (cudaStream_t)stream);
+}
+
+extern "C" int b200gan_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t numel, float lr,
+                                float beta1, float beta2, float eps, float bias_c1, float bias_c2,
+                                float ema_decay, float grad_scale, void* stream) {
+    using namespace b200gan;
+    if (numel <= 0) return 0;
+    int64_t blocks = cdiv(numel, 256);
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    adam_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, numel, lr, beta1, beta2,
+                                                                        eps, bias_c1, bias_c2, ema_decay, grad_scale);
+    count_launch();
+    return check_launch("adam_ema");
+}

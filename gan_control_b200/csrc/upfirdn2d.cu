@@ -1,0 +1,99 @@
+// upfirdn2d: zero-insert upsample -> pad/crop -> FIR (true convolution) -> decimate, NHWC.
+// Replaces gan_model.py:45-50 / pytorch_upfirdn2d.py:9-51 (a six-pass composition of F.pad,
+// F.conv2d with one channel and strided slicing) with one bandwidth-bound pass:
+// 16-byte vectorised along the contiguous channel axis, taps broadcast from shared memory.
+// The same kernel serves the adjoint (flip_kernel = 0, up <-> down), so it is closed under
+// differentiation.
+#include "common.cuh"
+
+namespace b200gan {
+
+constexpr int kMaxTaps = 16;
+
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(
+    const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ kernel, int n, int in_h,
+    int in_w, int c, int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y, int pad0_x,
+    int flip, float gain, int64_t total_vec) {
+    __shared__ float taps[kMaxTaps * kMaxTaps];
+    for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) {
+        int ky = i / kw, kx = i % kw;
+        int sy = flip ? kh - 1 - ky : ky, sx = flip ? kw - 1 - kx : kx;
+        taps[i] = kernel[sy * kw + sx] * gain;
+    }
+    __syncthreads();
+    const int cv = c / VEC;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total_vec;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int ci = (int)(idx % cv);
+        int64_t p = idx / cv;
+        int ox = (int)(p % out_w);
+        p /= out_w;
+        int oy = (int)(p % out_h);
+        int b = (int)(p / out_h);
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        const int zy0 = oy * down - pad0_y, zx0 = ox * down - pad0_x;
+        for (int ky = 0; ky < kh; ++ky) {
+            int zy = zy0 + ky;
+            if (zy < 0 || zy % up != 0) continue;
+            int iy = zy / up;
+            if (iy >= in_h) continue;
+            for (int kx = 0; kx < kw; ++kx) {
+                int zx = zx0 + kx;
+                if (zx < 0 || zx % up != 0) continue;
+                int ix = zx / up;
+                if (ix >= in_w) continue;
+                float f = taps[ky * kw + kx];
+                const T* src = x + (((int64_t)b * in_h + iy) * in_w + ix) * c + (int64_t)ci * VEC;
+                Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(src);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(f, io<T>::ld(&v.v[j]), acc[j]);
+            }
+        }
+        Pack<T, VEC> o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) io<T>::st(&o.v[j], acc[j]);
+        *reinterpret_cast<Pack<T, VEC>*>(y + idx * VEC) = o;
+    }
+}
+
+template <typename T, int VEC>
+static int launch_upfirdn(const void* x, void* y, const float* kernel, int n, int in_h, int in_w, int c,
+                          int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y,
+                          int pad0_x, int flip, float gain, cudaStream_t st) {
+    int64_t total = (int64_t)n * out_h * out_w * (c / VEC);
+    if (total == 0) return 0;
+    int64_t blocks = cdiv(total, 256);
+    int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    upfirdn2d_kernel<T, VEC><<<(unsigned)blocks, 256, 0, st>>>(
+        (const T*)x, (T*)y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down, pad0_y, pad0_x,
+        flip, gain, total);
+    count_launch();
+    return check_launch("upfirdn2d");
+}
+
+}  // namespace b200gan
+
+extern "C" int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, int dtype, int n, int in_h,
+                                 int in_w, int c, int out_h, int out_w, int kh, int kw, int up,
+                                 int down, int pad0_y, int pad0_x, int flip_kernel, float gain,
+                                 void* stream) {
+    using namespace b200gan;
+    B200_REQUIRE(kh >= 1 && kw >= 1 && kh <= kMaxTaps && kw <= kMaxTaps, "upfirdn2d: kernel %dx%d not in 1..16", kh, kw);
+    B200_REQUIRE(up >= 1 && down >= 1, "upfirdn2d: up/down must be >= 1");
+    B200_REQUIRE(n >= 0 && c >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 0 && out_w >= 0, "upfirdn2d: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    return B200_DISPATCH(dtype, [&] {
+        constexpr int V = 16 / sizeof(T);
+        bool aligned = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+        if (aligned)
+            return launch_upfirdn<T, V>(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down,
+                                        pad0_y, pad0_x, flip_kernel, gain, st);
+        return launch_upfirdn<T, 1>(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down,
+                                    pad0_y, pad0_x, flip_kernel, gain, st);
+    });
+}

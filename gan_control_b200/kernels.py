@@ -1,0 +1,279 @@
+"""Thin ctypes binding of libb200gan.so (include/b200gan.h) on torch CUDA tensors.
+
+Every function here launches hand-written sm_100a kernels and nothing else: there is no CPU
+path and no PyTorch fallback -- a missing library or a non-CUDA tensor raises.  torch is used
+only for device memory (outputs come from the caching allocator) and the current stream.
+
+Layout convention at this level: activations are physical NHWC, i.e. contiguous
+``(N, H, W, C)`` tensors; ``ops.py`` owns the logical-NCHW <-> NHWC views.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200gan.so')
+_lib = None
+
+F32, BF16 = 0, 1
+_c = ctypes
+_vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+
+class FcLayer(ctypes.Structure):
+    _fields_ = [('w', _vp), ('bias', _vp), ('in_dim', _i), ('out_dim', _i), ('in_off', _i),
+                ('out_off', _i), ('scale', _f), ('bias_mul', _f)]
+
+
+_SIGNATURES = {
+    'b200gan_version': ([], _i),
+    'b200gan_last_error': ([], _c.c_char_p),
+    'b200gan_launch_count': ([], _c.c_uint64),
+    'b200gan_upfirdn2d': ([_vp, _vp, _vp, _i] + [_i] * 6 + [_i] * 7 + [_f, _vp], _i),
+    'b200gan_bias_act_fwd': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
+    'b200gan_bias_act_bwd': ([_vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
+    'b200gan_reduce_nhwc': ([_vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
+    'b200gan_conv_fwd': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
+    'b200gan_conv_wgrad': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
+    'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
+    'b200gan_gemm_f32': ([_vp, _vp, _vp] + [_i] * 8 + [_f, _f, _vp], _i),
+    'b200gan_mapping_fwd': ([_vp, _vp, _vp] + [_i] * 6 + [_vp], _i),
+    'b200gan_adam_ema': ([_vp, _vp, _vp, _vp, _vp, _i64] + [_f] * 8 + [_vp], _i),
+}
+
+
+def lib():
+    """Load libb200gan.so (built by `python -m gan_control_b200.build`); fail loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: the sm_100a kernels are the only implementation of this '
+                f'package (no CPU / PyTorch fallback). Build it with `python -m gan_control_b200.build`.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the library lacks a declared symbol
+            fn.argtypes, fn.restype = args, res
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def launch_count():
+    return int(lib().b200gan_launch_count())
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f'libb200gan {what} failed (code {rc}): {lib().b200gan_last_error().decode()}')
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f'libb200gan supports float32 / bfloat16 activations, got {t.dtype}')
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('gan_control_b200 kernels run on CUDA (sm_100a) tensors only; got a '
+                               f'{t.device} tensor. There is no CPU fallback.')
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    """small fp32 side inputs (bias, rowscale, taps) as contiguous fp32"""
+    if t is None:
+        return None
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0):
+    """x: contiguous (N,H,W,C).  Returns contiguous (N,out_h,out_w,C)."""
+    _cuda(x, taps)
+    assert x.ndim == 4 and x.is_contiguous()
+    n, h, w, c = x.shape
+    taps = _f32c(taps)
+    y = torch.empty((n, out_h, out_w, c), dtype=x.dtype, device=x.device)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        _check(lib().b200gan_upfirdn2d(_ptr(x), _ptr(y), _ptr(taps), _dt(x), n, h, w, c, out_h, out_w,
+                                       taps.shape[0], taps.shape[1], up, down, pad0_y, pad0_x, int(flip),
+                                       float(gain), _stream()), 'upfirdn2d')
+    return y
+
+
+def _ew_shape(x, planar):
+    """(n, hw, c, inner) of a bias_act operand: NHWC (N,...,C) or planar NCHW (N,C,...)."""
+    if planar:
+        n, c = x.shape[0], x.shape[1]
+        return n, 1, c, max(1, x.numel() // max(1, n * c))
+    n, c = x.shape[0], x.shape[-1]
+    return n, max(1, x.numel() // max(1, n * c)), c, 1
+
+
+def bias_act_fwd(x, bias=None, rowscale=None, noise=None, noise_w=None, slope=0.2, gain=2 ** 0.5, planar=False):
+    """y = gain*lrelu(x*rowscale[n,c] + noise_w*noise[n,pix] + bias[c]).  x contiguous; channel axis
+    last (NHWC) or axis 1 (planar=True)."""
+    _cuda(x, bias, rowscale, noise, noise_w)
+    assert x.is_contiguous()
+    n, hw, c, inner = _ew_shape(x, planar)
+    bias, rowscale, noise_w = _f32c(bias), _f32c(rowscale), _f32c(noise_w)
+    if noise is not None:
+        noise = noise.detach().to(x.dtype).contiguous()
+        assert noise.numel() == n * hw * inner
+    y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        _check(lib().b200gan_bias_act_fwd(_ptr(x), _ptr(y), _ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w),
+                                          _dt(x), n, hw, c, inner, float(slope), float(gain), _stream()), 'bias_act_fwd')
+    return y
+
+
+def bias_act_bwd(gy, y, rowscale=None, slope=0.2, gain=2 ** 0.5, planar=False):
+    """gx = gy * gain * (y > 0 ? 1 : slope) * rowscale[n,c]."""
+    _cuda(gy, y, rowscale)
+    assert gy.is_contiguous() and y.is_contiguous() and gy.shape == y.shape and gy.dtype == y.dtype
+    n, hw, c, inner = _ew_shape(gy, planar)
+    rowscale = _f32c(rowscale)
+    gx = torch.empty_like(gy)
+    if gy.numel() == 0:
+        return gx
+    with torch.cuda.device(gy.device):
+        _check(lib().b200gan_bias_act_bwd(_ptr(gy), _ptr(y), _ptr(gx), _ptr(rowscale), _dt(gy), n, hw, c, inner,
+                                          float(slope), float(gain), _stream()), 'bias_act_bwd')
+    return gx
+
+
+def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None):
+    """sums of a*b*pixw[n,pix] over pixels: (C,) and/or (N,C), fp32.  a, b contiguous (N,...,C)."""
+    _cuda(a, b, pixw)
+    if pixw is not None:
+        pixw = pixw.detach().to(a.dtype).contiguous()
+        assert pixw.numel() * a.shape[-1] == a.numel()
+    assert a.is_contiguous() and (b is None or (b.is_contiguous() and b.shape == a.shape and b.dtype == a.dtype))
+    n, c = a.shape[0], a.shape[-1]
+    hw = max(1, a.numel() // max(1, n * c))
+    out_c = torch.zeros(c, dtype=torch.float32, device=a.device) if per_channel else None
+    out_nc = torch.zeros(n, c, dtype=torch.float32, device=a.device) if per_sample_channel else None
+    if a.numel():
+        with torch.cuda.device(a.device):
+            _check(lib().b200gan_reduce_nhwc(_ptr(a), _ptr(b), _ptr(pixw), _ptr(out_c), _ptr(out_nc), _dt(a), n, hw, c,
+                                             _stream()), 'reduce_nhwc')
+    return out_c, out_nc
+
+
+def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None, noise=None, noise_w=None,
+             slope=1.0, gain=1.0):
+    """x: (B,H,W,IC) contiguous; w: (Bw,KH,KW,OC,IC) contiguous, same dtype; -> (B,out_h,out_w,OC)."""
+    _cuda(x, w, bias, rowscale, noise, noise_w)
+    assert x.ndim == 4 and w.ndim == 5 and x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
+    b, h, wd, ic = x.shape
+    bw, kh, kw, oc, ic2 = w.shape
+    assert ic2 == ic and bw in (1, b), (x.shape, w.shape)
+    bias, rowscale, noise_w = _f32c(bias), _f32c(rowscale), _f32c(noise_w)
+    if noise is not None:
+        noise = noise.detach().to(x.dtype).contiguous()
+        assert noise.numel() == b * out_h * out_w
+    y = torch.empty((b, out_h, out_w, oc), dtype=x.dtype, device=x.device)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        _check(lib().b200gan_conv_fwd(_ptr(x), _ptr(w), _ptr(y), _dt(x), b, h, wd, ic, out_h, out_w, oc, kh, kw,
+                                      up, down, pad0, int(bw > 1),
+                                      _ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w), float(slope),
+                                      float(gain), _stream()), 'conv_fwd')
+    return y
+
+
+def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False):
+    """x: (B,H,W,IC), gy: (B,OH,OW,OC) contiguous -> fp32 (Bw,KH,KW,OC,IC)."""
+    _cuda(x, gy)
+    assert x.is_contiguous() and gy.is_contiguous() and x.dtype == gy.dtype
+    b, h, wd, ic = x.shape
+    b2, oh, ow, oc = gy.shape
+    assert b2 == b
+    gw = torch.zeros((b if per_sample else 1, kh, kw, oc, ic), dtype=torch.float32, device=x.device)
+    if x.numel() and gy.numel():
+        with torch.cuda.device(x.device):
+            _check(lib().b200gan_conv_wgrad(_ptr(x), _ptr(gy), _ptr(gw), _dt(x), b, h, wd, ic, oh, ow, oc, kh, kw, up,
+                                            down, pad0, int(per_sample), _stream()), 'conv_wgrad')
+    return gw
+
+
+def linear_fwd(x, w, bias, scale, bias_mul, act):
+    """y = act(scale * x @ w.T + bias*bias_mul); x (M,K) fp32/bf16 contiguous, w (N,K) fp32."""
+    _cuda(x, w, bias)
+    assert x.ndim == 2 and x.is_contiguous()
+    w, bias = _f32c(w), _f32c(bias)
+    m, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k
+    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    if m:
+        with torch.cuda.device(x.device):
+            _check(lib().b200gan_linear_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(x), m, n, k, float(scale),
+                                            float(bias_mul), int(act), _stream()), 'linear_fwd')
+    return y
+
+
+def gemm_f32(a, b, trans_a, trans_b, alpha=1.0):
+    """alpha * op(a) @ op(b) in fp32; op = transpose when the flag is set. 2-D contiguous inputs."""
+    _cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    m, k = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    k2, n = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    assert k == k2, (a.shape, b.shape, trans_a, trans_b)
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    if m and n:
+        if k == 0:
+            return c.zero_()
+        with torch.cuda.device(a.device):
+            # kernel convention: B(k,n) = b[n*ldb + k] when its trans_b flag = 1 ("NT")
+            _check(lib().b200gan_gemm_f32(_ptr(a), _ptr(b), _ptr(c), m, n, k, a.shape[1], b.shape[1], n,
+                                          int(trans_a), int(trans_b), float(alpha), 0.0, _stream()), 'gemm_f32')
+    return c
+
+
+def mapping_fwd(z, layer_table, n_groups, n_layers, row_width, normalize):
+    """Persistent mapping-network kernel.  z (B, z_dim) fp32; layer_table: uint8 CUDA tensor holding
+    n_layers*n_groups `FcLayer` structs.  Returns acts (n_layers+1, B, row_width) fp32."""
+    _cuda(z, layer_table)
+    z = _f32c(z)
+    batch, z_dim = z.shape
+    acts = torch.zeros((n_layers + 1, batch, row_width), dtype=torch.float32, device=z.device)
+    if batch:
+        with torch.cuda.device(z.device):
+            _check(lib().b200gan_mapping_fwd(_ptr(z), _ptr(acts), _ptr(layer_table), n_groups, n_layers, batch, z_dim,
+                                             row_width, int(normalize), _stream()), 'mapping_fwd')
+    return acts
+
+
+def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay=0.0, grad_scale=1.0):
+    """In-place Adam step (torch.optim.Adam semantics) on flat fp32 buffers, fused with EMA."""
+    _cuda(p, g, m, v, ema)
+    for t in (p, g, m, v) + ((ema,) if ema is not None else ()):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    with torch.cuda.device(p.device):
+        _check(lib().b200gan_adam_ema(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(ema), p.numel(), float(lr), float(beta1),
+                                      float(beta2), float(eps), float(bc1), float(bc2), float(ema_decay),
+                                      float(grad_scale), _stream()), 'adam_ema')

@@ -1,0 +1,334 @@
+"""Differentiable StyleGAN2 operators on top of libb200gan (kernels.py).
+
+Public functions keep the reference signatures (``gan_model.py:39-50`` and the upstream
+``conv2d_gradfix`` names the README points at):
+
+    upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0))
+    fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5)
+    conv2d(input, weight, bias=None, stride=1, padding=0)          # conv2d_gradfix.conv2d
+    conv_transpose2d(input, weight, bias=None, stride=1, padding=0)
+
+Every op is a ``torch.autograd.Function`` whose backward is written with the SAME small set of
+Functions (a conv "gather", its weight gradient, upfirdn2d, the bias-act gradient, a GEMM), so the
+set is closed under differentiation: R1 (``generator_trainer.py:713-719``) and path-length
+(``:601-614``) double-backward run through the CUDA kernels too.
+
+Tensors are logical NCHW like the reference; physically the kernels want NHWC, so 4-D activations
+travel in ``torch.channels_last`` (a permuted view, no copy once the network is in that format).
+"""
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+
+SQRT2 = math.sqrt(2.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# layout helpers
+# ---------------------------------------------------------------------------------------------
+def _nhwc(x):
+    """logical (N,C,H,W) -> contiguous (N,H,W,C) (a view when x is channels_last)."""
+    xp = x.permute(0, 2, 3, 1)
+    return xp if xp.is_contiguous() else xp.contiguous()
+
+
+def _nchw(y):
+    """contiguous (N,H,W,C) -> logical (N,C,H,W) with channels_last strides."""
+    return y.permute(0, 3, 1, 2)
+
+
+def up32(t):
+    """at least fp32: bf16 -> fp32; fp32 / fp64 (CPU algebra tests) unchanged"""
+    return t if t.dtype in (torch.float32, torch.float64) else t.float()
+
+
+def _is_nhwc(x):
+    return x.ndim == 4 and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# upfirdn2d                                  (gan_model.py:45-50 / pytorch_upfirdn2d.py:9-51)
+# ---------------------------------------------------------------------------------------------
+class _UpFirDn2d(Function):
+    @staticmethod
+    def forward(ctx, x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip):
+        n, c, h, w = x.shape
+        ctx.cfg = (up, down, pad0_y, pad0_x, h, w, flip, taps.shape[0], taps.shape[1])
+        ctx.save_for_backward(taps)
+        if x.is_contiguous() and not (_is_nhwc(x) and c > 1):
+            # planar NCHW == NHWC with one channel: no layout change, no copy
+            y = K.upfirdn2d(x.reshape(n * c, h, w, 1), taps, up, down, pad0_y, pad0_x, out_h, out_w, flip)
+            return y.view(n, c, out_h, out_w)
+        return _nchw(K.upfirdn2d(_nhwc(x), taps, up, down, pad0_y, pad0_x, out_h, out_w, flip))
+
+    @staticmethod
+    def backward(ctx, gy):
+        taps, = ctx.saved_tensors
+        up, down, p0y, p0x, h, w, flip, kh, kw = ctx.cfg
+        # adjoint = the same op with up<->down, reversed taps, pad0' = k-1-pad0
+        gx = _UpFirDn2d.apply(gy, taps, down, up, kh - 1 - p0y, kw - 1 - p0x, h, w, not flip)
+        return gx, None, None, None, None, None, None, None, None
+
+
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
+    """Drop-in for ``gan_model.upfirdn2d`` (gm.py:45-50)."""
+    n, c, h, w = input.shape
+    kh, kw = kernel.shape
+    out_h = (h * up + pad[0] + pad[1] - kh) // down + 1
+    out_w = (w * up + pad[0] + pad[1] - kw) // down + 1
+    return _UpFirDn2d.apply(input, kernel, up, down, pad[0], pad[0], out_h, out_w, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# bias + leaky-ReLU                                                    (gan_model.py:25-41)
+# ---------------------------------------------------------------------------------------------
+def _planar(x):
+    """bias_act operand layout: NHWC when the 4-D tensor is channels_last, else planar."""
+    return not (_is_nhwc(x) and x.shape[1] > 1)
+
+
+class _BiasActGrad(Function):
+    """gx = gy * gain * (y > 0 ? 1 : slope) -- linear in gy, so it is its own derivative."""
+
+    @staticmethod
+    def forward(ctx, gy, y, slope, gain):
+        ctx.cfg = (slope, gain)
+        ctx.save_for_backward(y)
+        if _planar(y):
+            return K.bias_act_bwd(gy.contiguous(), y.contiguous(), None, slope, gain, planar=True)
+        return _nchw(K.bias_act_bwd(_nhwc(gy), _nhwc(y), None, slope, gain))
+
+    @staticmethod
+    def backward(ctx, ggx):
+        y, = ctx.saved_tensors
+        return _BiasActGrad.apply(ggx, y, *ctx.cfg), None, None, None
+
+
+class _BiasAct(Function):
+    """y = gain * lrelu(x + bias[c]); channel axis = 1."""
+
+    @staticmethod
+    def forward(ctx, x, bias, slope, gain):
+        ctx.cfg = (slope, gain)
+        if _planar(x):
+            y = K.bias_act_fwd(x.contiguous(), bias, slope=slope, gain=gain, planar=True)
+        else:
+            y = _nchw(K.bias_act_fwd(_nhwc(x), bias, slope=slope, gain=gain))
+        ctx.save_for_backward(y)
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, = ctx.saved_tensors
+        gx = _BiasActGrad.apply(gy, y, *ctx.cfg)
+        gb = None
+        if ctx.bias_dtype is not None and ctx.needs_input_grad[1]:
+            dims = [d for d in range(gx.ndim) if d != 1]
+            gb = up32(gx).sum(dims).to(ctx.bias_dtype)
+        return gx, gb, None, None
+
+
+def fused_leaky_relu(input, bias, negative_slope=0.2, scale=SQRT2):
+    """Drop-in for ``gan_model.fused_leaky_relu`` (gm.py:39-41)."""
+    return _BiasAct.apply(input, bias, negative_slope, scale)
+
+
+class _ModEpilogue(Function):
+    """StyledConv tail in one pass: y = gain*lrelu(x*d[b,c] + nw*noise[b,1,h,w] + bias[c])
+    (demod scale of gm.py:288-289 applied to the activation, NoiseInjection gm.py:340-345,
+    FusedLeakyReLU gm.py:32-35).  d / noise / bias may be None."""
+
+    @staticmethod
+    def forward(ctx, x, d, noise, noise_w, bias, slope, gain):
+        ctx.cfg = (slope, gain)
+        y = _nchw(K.bias_act_fwd(_nhwc(x), bias, d, noise, noise_w, slope, gain))
+        ctx.save_for_backward(x, d, noise, noise_w, y)
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, d, noise, noise_w, y = ctx.saved_tensors
+        slope, gain = ctx.cfg
+        need = ctx.needs_input_grad
+        gz = _BiasActGrad.apply(gy, y, slope, gain)          # d loss / d (pre-activation)
+        gx = gd = gnoise = gnw = gb = None
+        if torch.is_grad_enabled():
+            # create_graph=True (R1 / path-length): plain differentiable torch arithmetic on gz
+            gz32 = up32(gz)
+            if need[0]:
+                gx = gz if d is None else (gz32 * up32(d[:, :, None, None])).to(gz.dtype)
+            if d is not None and need[1]:
+                gd = (gz32 * up32(x)).sum((2, 3)).to(d.dtype)
+            if noise is not None and need[2]:
+                gnoise = (gz32.sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
+            if noise is not None and need[3]:
+                gnw = (gz32.sum(1, keepdim=True) * up32(noise)).sum().reshape(noise_w.shape).to(noise_w.dtype)
+            if ctx.bias_dtype is not None and need[4]:
+                gb = gz32.sum((0, 2, 3)).to(ctx.bias_dtype)
+        else:
+            gzp = _nhwc(gz)
+            if need[0]:
+                gx = gz if d is None else _nchw(K.bias_act_bwd(_nhwc(gy), _nhwc(y), d, slope, gain))
+            if d is not None and need[1]:
+                gd = K.reduce_nhwc(gzp, _nhwc(x), per_channel=False, per_sample_channel=True)[1].to(d.dtype)
+            if noise is not None and need[2]:
+                gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
+            if noise is not None and need[3]:
+                gnw = K.reduce_nhwc(gzp, None, per_channel=True, pixw=noise)[0].sum().reshape(noise_w.shape).to(noise_w.dtype)
+            if ctx.bias_dtype is not None and need[4]:
+                gb = K.reduce_nhwc(gzp, None, per_channel=True)[0].to(ctx.bias_dtype)
+        return gx, gd, gnoise, gnw, gb, None, None
+
+
+def mod_epilogue(x, d=None, noise=None, noise_w=None, bias=None, slope=0.2, gain=SQRT2):
+    return _ModEpilogue.apply(x, d, noise, noise_w, bias, slope, gain)
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution family
+# ---------------------------------------------------------------------------------------------
+def _kernel_layout(w, dtype):
+    """(Bw,OC,IC,KH,KW) parameter layout -> (Bw,KH,KW,OC,IC) K-major operand in `dtype`."""
+    return w.detach().permute(0, 3, 4, 1, 2).to(dtype).contiguous()
+
+
+class _ConvGather(Function):
+    """y[b,o,oy,ox] = sum_{i,ky,kx} z[b,i,oy*down+ky-pad0,ox*down+kx-pad0] * w[wb,o,i,ky,kx]
+    with z = x zero-upsampled by `up` (include/b200gan.h).  w: (Bw,OC,IC,KH,KW), Bw in {1,B}."""
+
+    @staticmethod
+    def forward(ctx, x, w, up, down, pad0, out_h, out_w):
+        ctx.cfg = (up, down, pad0, x.shape[2], x.shape[3])
+        ctx.save_for_backward(x, w)
+        y = K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0)
+        return _nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        up, down, pad0, h, wd = ctx.cfg
+        kh, kw = w.shape[3], w.shape[4]
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            wt = w.flip(3, 4).transpose(1, 2)                  # taps reversed, OC <-> IC
+            gx = _ConvGather.apply(gy, wt, down, up, kh - 1 - pad0, h, wd)
+        if ctx.needs_input_grad[1]:
+            gw = _ConvWgrad.apply(x, gy, up, down, pad0, kh, kw, w.shape[0] > 1).to(w.dtype)
+        return gx, gw, None, None, None, None, None
+
+
+class _ConvWgrad(Function):
+    """gw[wb,o,i,ky,kx] = sum_{b,oy,ox} gy[b,o,oy,ox] * z[b,i,oy*down+ky-pad0,ox*down+kx-pad0]
+    (fp32 result; summed over the batch unless per_sample)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, up, down, pad0, kh, kw, per_sample):
+        ctx.cfg = (up, down, pad0, kh, kw, x.shape[2], x.shape[3], gy.shape[2], gy.shape[3])
+        ctx.save_for_backward(x, gy)
+        gw = K.conv_wgrad(_nhwc(x), _nhwc(gy), kh, kw, up, down, pad0, per_sample)
+        return gw.permute(0, 3, 4, 1, 2)                       # (Bw,OC,IC,KH,KW) view
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        up, down, pad0, kh, kw, h, wd, oh, ow = ctx.cfg
+        gx = ggy = None
+        if ctx.needs_input_grad[0]:
+            gx = _ConvGather.apply(gy, ggw.flip(3, 4).transpose(1, 2), down, up, kh - 1 - pad0, h, wd)
+        if ctx.needs_input_grad[1]:
+            ggy = _ConvGather.apply(x, ggw, up, down, pad0, oh, ow)
+        return gx, ggy, None, None, None, None, None, None
+
+
+def conv_gather(x, w, up=1, down=1, pad0=0, out_hw=None):
+    """General form; `w` (Bw,OC,IC,KH,KW).  Default output extent = 'valid' over the padded,
+    zero-upsampled input with symmetric padding pad0."""
+    if out_hw is None:
+        zh, zw = (x.shape[2] - 1) * up + 1, (x.shape[3] - 1) * up + 1
+        out_hw = ((zh + 2 * pad0 - w.shape[3]) // down + 1, (zw + 2 * pad0 - w.shape[4]) // down + 1)
+    return _ConvGather.apply(x, w, up, down, pad0, out_hw[0], out_hw[1])
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0):
+    """``conv2d_gradfix.conv2d`` / ``F.conv2d`` (groups=1, dilation=1).  weight (OC,IC,KH,KW), or
+    (B,OC,IC,KH,KW) for per-sample weights (the reference's groups=batch trick, gm.py:326-329)."""
+    w = weight if weight.ndim == 5 else weight.unsqueeze(0)
+    y = conv_gather(input, w, 1, stride, padding)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1).to(y.dtype)
+    return y
+
+
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0):
+    """``F.conv_transpose2d`` (groups=1).  weight (IC,OC,KH,KW) like torch, or (B,IC,OC,KH,KW)."""
+    w = weight if weight.ndim == 5 else weight.unsqueeze(0)
+    w = w.flip(3, 4).transpose(1, 2)                            # -> gather form (Bw,OC,IC,KH,KW)
+    kh, kw = w.shape[3], w.shape[4]
+    h, wd = input.shape[2], input.shape[3]
+    out_hw = ((h - 1) * stride - 2 * padding + kh, (wd - 1) * stride - 2 * padding + kw)
+    y = _ConvGather.apply(input, w, stride, 1, kh - 1 - padding, out_hw[0], out_hw[1])
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1).to(y.dtype)
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# dense layers                                                         (gan_model.py:189-197)
+# ---------------------------------------------------------------------------------------------
+class _Gemm(Function):
+    """alpha * op(a) @ op(b), fp32, closed under differentiation."""
+
+    @staticmethod
+    def forward(ctx, a, b, trans_a, trans_b, alpha):
+        ctx.cfg = (trans_a, trans_b, alpha)
+        ctx.save_for_backward(a, b)
+        return K.gemm_f32(a.contiguous(), b.contiguous(), trans_a, trans_b, alpha)
+
+    @staticmethod
+    def backward(ctx, gc):
+        a, b = ctx.saved_tensors
+        ta, tb, alpha = ctx.cfg
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            # C = op(a) op(b):  d op(a) = gc op(b)^T
+            ga = _Gemm.apply(b, gc, tb, True, alpha) if ta else _Gemm.apply(gc, b, False, not tb, alpha)
+        if ctx.needs_input_grad[1]:
+            gb = _Gemm.apply(gc, a, True, ta, alpha) if tb else _Gemm.apply(a, gc, not ta, False, alpha)
+        return (None if ga is None else ga.to(a.dtype)), (None if gb is None else gb.to(b.dtype)), None, None, None
+
+
+class _EqualLinear(Function):
+    """y = act(scale * x @ w.T + bias * bias_mul) in one kernel; backward via _Gemm/_BiasActGrad."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, scale, bias_mul, act):
+        y = K.linear_fwd(x.contiguous(), w, bias, scale, bias_mul, act)
+        ctx.cfg = (scale, bias_mul, act)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        scale, bias_mul, act = ctx.cfg
+        gz = _BiasActGrad.apply(gy, y, 0.2, SQRT2) if act else gy
+        gz32 = up32(gz)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _Gemm.apply(gz32, w, False, False, scale).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            gw = _Gemm.apply(gz32, up32(x), True, False, scale).to(w.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gz32.sum(0) * bias_mul
+        return gx, gw, gb, None, None, None
+
+
+def equal_linear(x, weight, bias, scale, lr_mul=1.0, activation=False):
+    """``EqualLinear.forward`` (gm.py:189-197) on a 2-D input."""
+    return _EqualLinear.apply(x, weight, bias, scale, lr_mul, bool(activation))

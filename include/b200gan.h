@@ -1,0 +1,160 @@
+/*
+ * b200gan.h -- C ABI of libb200gan.so, the sm_100a StyleGAN2 operator library
+ * behind gan-control's generator / discriminator hot path.
+ *
+ * The reference (amazon-science/gan-control) has no native boundary of its own:
+ * `models/gan_model.py:19-50` is a source-level switch (`FUSED`) whose True
+ * branch is a stub that would import `FusedLeakyReLU, fused_leaky_relu,
+ * upfirdn2d` (and, upstream, `conv2d_gradfix`) from a CUDA-op package located at
+ * `gan_control.models.op` (`trainers/non_leaking.py:6`).  This header is the
+ * C-level contract that package binds: every entry point names the reference
+ * computation it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - plain C types only; tensors are raw device pointers + explicit sizes.
+ *  - activations are NHWC ("channels last"): x[n][h][w][c], c contiguous.
+ *    An NCHW-contiguous tensor (N,C,H,W) is the NHWC tensor (N*C,H,W,1).
+ *  - `dtype`: B200GAN_F32 or B200GAN_BF16 storage; all arithmetic accumulates
+ *    in fp32.  Reductions / weight gradients are always written as fp32.
+ *  - every call is asynchronous on `stream` (a cudaStream_t), never allocates
+ *    device memory, never synchronises, and is re-entrant.
+ *  - return value: 0 on success, otherwise a negative B200GAN_E* code or a
+ *    positive cudaError_t; `b200gan_last_error()` gives a thread-local message.
+ */
+#ifndef B200GAN_H_
+#define B200GAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GAN_F32 0
+#define B200GAN_BF16 1
+
+#define B200GAN_EINVAL (-1)   /* bad argument (shape / dtype / alignment)   */
+#define B200GAN_ENOSUP (-2)   /* configuration not supported by this build   */
+
+int b200gan_version(void);
+const char* b200gan_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * `gpu_launches`); monotonically increasing. */
+uint64_t b200gan_launch_count(void);
+
+/* ---- upfirdn2d ---------------------------------------------------------
+ * Replaces `upfirdn2d(input, kernel, up, down, pad)` gm.py:45-50 ->
+ * `upfirdn2d_native` pytorch_upfirdn2d.py:9-51.   Per channel:
+ *   y[oy][ox] = sum_{ky,kx} z[oy*down + ky - pad0][ox*down + kx - pad0] * f[ky][kx]
+ * where z is x zero-upsampled by `up` (sample i at z[i*up]) and zero outside,
+ * f = kernel flipped in both axes when `flip_kernel` != 0 (the reference's
+ * true convolution; the adjoint op passes flip_kernel = 0).  The output extent
+ * (out_h, out_w) is explicit, so a trailing pad/crop is implicit.
+ * kernel: fp32 [kh][kw] on the device, kh,kw <= 16.                        */
+int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, int dtype,
+                      int n, int in_h, int in_w, int c, int out_h, int out_w,
+                      int kh, int kw, int up, int down, int pad0_y, int pad0_x,
+                      int flip_kernel, float gain, void* stream);
+
+/* ---- bias + noise + scaled leaky-ReLU -----------------------------------
+ * Replaces `fused_leaky_relu` / `FusedLeakyReLU` gm.py:25-41, the noise add of
+ * `NoiseInjection` gm.py:340-345 and the demodulation scale of gm.py:288-289
+ * when the activation-scaled form is used:
+ *   y = gain * lrelu_slope( x * rowscale[n][c] + noise_w * noise[n][hw] + bias[c] )
+ * Element e of x has channel (e / inner) % c and sample e / (c*inner*outer?) --
+ * layout is described by (n, hw, c, inner): NHWC -> inner = 1 (x[n][hw][c]);
+ * NCHW -> inner = hw with `hw` passed as 1 (x[n][c][inner]).
+ * Any of bias / rowscale / noise may be NULL.  slope = 1, gain = 1 is linear. */
+int b200gan_bias_act_fwd(const void* x, void* y, const float* bias, const float* rowscale,
+                         const void* noise, const float* noise_w, int dtype,
+                         int64_t n, int64_t hw, int64_t c, int64_t inner,
+                         float slope, float gain, void* stream);
+/* gx = gy * gain * (y > 0 ? 1 : slope) [* rowscale]; `y` is the saved OUTPUT
+ * (sign-preserving).  Linear in gy => it is its own
+ * double-backward. */
+int b200gan_bias_act_bwd(const void* gy, const void* y, void* gx, const float* rowscale, int dtype,
+                         int64_t n, int64_t hw, int64_t c, int64_t inner,
+                         float slope, float gain, void* stream);
+/* Pixel reductions of  a[n][p][c] * b[n][p][c] * pixw[n][p]  (b, pixw may be NULL):
+ * out_c[c] = sum over n,p (bias / noise-strength grads), out_nc[n][c] = sum over p
+ * (demod-scale grads); either may be NULL.  NHWC; fp32 outputs must be zero-initialised by
+ * the caller (atomic accumulation). */
+int b200gan_reduce_nhwc(const void* a, const void* b, const void* pixw, float* out_c, float* out_nc,
+                        int dtype, int64_t n, int64_t hw, int64_t c, void* stream);
+
+/* ---- convolution family ----------------------------------------------------
+ * One gather form covers every convolution on the path and every data
+ * gradient of them:
+ *   y[b][oy][ox][o] = sum_{ky,kx,i} z[b][oy*down + ky - pad0][ox*down + kx - pad0][i]
+ *                                   * w[wb][ky][kx][o][i]
+ * z = x zero-upsampled by `up` (extent (H-1)*up+1), zero outside; wb = b when
+ * `w_per_sample`, else 0.
+ *   up=1,down=1 : F.conv2d stride 1 (EqualConv2d gm.py:152-160, ModulatedConv2d
+ *                 plain branch gm.py:326-329 with groups=batch => w_per_sample)
+ *   up=1,down=2 : stride-2 conv after Blur (ConvLayer downsample gm.py:857-881)
+ *   up=2,down=1 : F.conv_transpose2d stride 2 (gm.py:304) with the kernel
+ *                 flipped/transposed by the caller, pad0 = k-1
+ * weights: [wb][kh][kw][oc][ic] in `dtype`, ic contiguous ("K-major").
+ * Optional fused epilogue (NULL = off), applied in this order:
+ *   v = acc * rowscale[b][o] + noise_w * noise[b][oy][ox] + bias[o];
+ *   y = gain * lrelu_slope(v)                                               */
+int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype,
+                     int b, int in_h, int in_w, int ic, int out_h, int out_w, int oc,
+                     int kh, int kw, int up, int down, int pad0, int w_per_sample,
+                     const float* bias, const float* rowscale, const void* noise, const float* noise_w,
+                     float slope, float gain, void* stream);
+/* Weight gradient of the form above:
+ *   gw[wb][ky][kx][o][i] += sum_{b,oy,ox} gy[b][oy][ox][o] * z[b][oy*down+ky-pad0][..][i]
+ * gw is fp32, same [wb][kh][kw][oc][ic] layout, must be zero-initialised
+ * (split-K atomic accumulation). */
+int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int dtype,
+                       int b, int in_h, int in_w, int ic, int out_h, int out_w, int oc,
+                       int kh, int kw, int up, int down, int pad0, int w_per_sample,
+                       void* stream);
+
+/* ---- dense layers ------------------------------------------------------------
+ * Replaces `EqualLinear.forward` gm.py:189-197 (`F.linear` + bias*lr_mul
+ * [+ fused_leaky_relu]):  y[m][n] = act( scale * sum_k x[m][k] w[n][k] + bias[n]*bias_mul )
+ * x, y in `dtype`; w, bias fp32 (parameters). act = 1 -> sqrt(2)*lrelu_0.2.   */
+int b200gan_linear_fwd(const void* x, const float* w, const float* bias, void* y, int dtype,
+                       int m, int n, int k, float scale, float bias_mul, int act, void* stream);
+/* Generic small fp32-accumulating GEMM used by the linear backward passes:
+ *   c[m][n] (+)= alpha * sum_k A(m,k) * B(k,n);  A(m,k) = a[m*lda + k] or a[k*lda + m] (trans_a),
+ *   B(k,n) = b[n*ldb + k] (trans_b = 1, "NT") or b[k*ldb + n].  All fp32.       */
+int b200gan_gemm_f32(const float* a, const float* b, float* c, int m, int n, int k,
+                     int lda, int ldb, int ldc, int trans_a, int trans_b, float alpha, float beta,
+                     void* stream);
+
+/* Whole mapping network in one persistent (cooperative) kernel:
+ * `Generator.style` gm.py:633-642 (vanilla) and `MultiFcStack` gm.py:489-502
+ * (block-diagonal split-FC; PixelNorm gm.py:52-57 per slice), and the controller
+ * `FcStack` controller_model.py:24-43 (normalize = 0).
+ * `layers` is a DEVICE array of n_layers * n_groups descriptors, layer-major
+ * (layers[l * n_groups + g]).  `acts` is a caller-provided fp32 buffer
+ * [n_layers + 1][batch][row_width]: row 0 receives the (normalised) input, row l
+ * the output of layer l; the last row is the w latent.  It doubles as the saved
+ * activations of the backward pass.                                          */
+typedef struct {
+    const float* w;      /* [out_dim][in_dim] fp32 */
+    const float* bias;   /* [out_dim] fp32 */
+    int in_dim, out_dim;
+    int in_off, out_off; /* column offsets into the input / output activation rows */
+    float scale;         /* lr_mul / sqrt(in_dim) */
+    float bias_mul;      /* lr_mul */
+} b200gan_fc_layer;
+int b200gan_mapping_fwd(const float* z, float* acts, const b200gan_fc_layer* layers,
+                        int n_groups, int n_layers, int batch, int z_dim, int row_width,
+                        int normalize, void* stream);
+
+/* ---- optimiser ------------------------------------------------------------------
+ * Adam step as `torch.optim.Adam` (gt.py:161-173) fused with the generator EMA
+ * `accumulate` (trainers/utils.py:8-12; ema may be NULL).  fp32, in place.      */
+int b200gan_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t numel,
+                     float lr, float beta1, float beta2, float eps, float bias_c1, float bias_c2,
+                     float ema_decay, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GAN_H_ */

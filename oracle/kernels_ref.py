@@ -1,0 +1,148 @@
+"""CPU stand-ins for every entry point of `gan_control_b200/kernels.py` (TEST INFRASTRUCTURE).
+
+Each function restates the *contract* of one libb200gan kernel (include/b200gan.h) with plain
+torch-CPU arithmetic in the dtype it is given (fp64 allowed).  Two uses, both in `tests/` only:
+
+* CPU suite: `tests/conftest.py::cpu_kernels` monkeypatches these over `kernels.*` so that the
+  host-side autograd algebra of `ops.py` / `modules.py` (backward and double-backward formulas,
+  layouts, geometry) is verified against the reference-generated goldens without a GPU;
+* GPU suite: each CUDA kernel is compared against its stand-in on random inputs.
+
+The product never imports this module.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def _gather_pad(z, pad0_y, pad0_x, need_h, need_w):
+    """zero-extend / crop so that index 0 of the result is z-index -pad0 and the extent is need_*"""
+    zh, zw = z.shape[-2:]
+    z = F.pad(z, [max(pad0_x, 0), max(0, need_w - pad0_x - zw), max(pad0_y, 0), max(0, need_h - pad0_y - zh)])
+    z = z[..., max(-pad0_y, 0):, max(-pad0_x, 0):]
+    return z[..., :need_h, :need_w]
+
+
+def _zero_upsample(x, up):
+    if up == 1:
+        return x
+    n, c, h, w = x.shape
+    z = x.new_zeros(n, c, (h - 1) * up + 1, (w - 1) * up + 1)
+    z[:, :, ::up, ::up] = x
+    return z
+
+
+def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0):
+    xn = x.permute(0, 3, 1, 2)
+    c = xn.shape[1]
+    kh, kw = taps.shape
+    z = _gather_pad(_zero_upsample(xn, up), pad0_y, pad0_x, (out_h - 1) * down + kh, (out_w - 1) * down + kw)
+    f = (taps.flip(0, 1) if flip else taps).to(x.dtype) * gain
+    y = F.conv2d(z, f[None, None].expand(c, 1, kh, kw), groups=c, stride=down)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _bcast(v, x, planar, kind):
+    """reshape a per-channel (C,), per-sample-channel (N,C) or per-pixel (N,pix) side input"""
+    n = x.shape[0]
+    if planar:
+        c = x.shape[1]
+        tail = (1,) * (x.ndim - 2)
+        if kind == 'c':
+            return v.reshape((1, c) + tail)
+        if kind == 'nc':
+            return v.reshape((n, c) + tail)
+        return v.reshape((n, 1) + tuple(x.shape[2:]))
+    c = x.shape[-1]
+    mid = (1,) * (x.ndim - 2)
+    if kind == 'c':
+        return v.reshape((1,) + mid + (c,))
+    if kind == 'nc':
+        return v.reshape((n,) + mid + (c,))
+    return v.reshape((n,) + tuple(x.shape[1:-1]) + (1,))
+
+
+def bias_act_fwd(x, bias=None, rowscale=None, noise=None, noise_w=None, slope=0.2, gain=2 ** 0.5, planar=False):
+    v = x
+    if rowscale is not None:
+        v = v * _bcast(rowscale.to(x.dtype), x, planar, 'nc')
+    if noise is not None:
+        v = v + noise_w.to(x.dtype).reshape(()) * _bcast(noise.to(x.dtype).contiguous(), x, planar, 'pix')
+    if bias is not None:
+        v = v + _bcast(bias.to(x.dtype), x, planar, 'c')
+    return (gain * torch.where(v > 0, v, v * slope)).contiguous()
+
+
+def bias_act_bwd(gy, y, rowscale=None, slope=0.2, gain=2 ** 0.5, planar=False):
+    g = gy * gain * torch.where(y > 0, torch.ones_like(y), torch.full_like(y, slope))
+    if rowscale is not None:
+        g = g * _bcast(rowscale.to(gy.dtype), gy, planar, 'nc')
+    return g.contiguous()
+
+
+def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None):
+    v = a.double() if a.dtype != torch.float64 else a
+    if b is not None:
+        v = v * b.to(v.dtype)
+    if pixw is not None:
+        v = v * pixw.to(v.dtype).reshape(tuple(a.shape[:-1]) + (1,))
+    n, c = a.shape[0], a.shape[-1]
+    v = v.reshape(n, -1, c)
+    out_t = torch.float64 if a.dtype == torch.float64 else torch.float32
+    return (v.sum((0, 1)).to(out_t) if per_channel else None,
+            v.sum(1).to(out_t) if per_sample_channel else None)
+
+
+def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None, noise=None, noise_w=None,
+             slope=1.0, gain=1.0):
+    b = x.shape[0]
+    bw, kh, kw, oc, ic = w.shape
+    xn = x.permute(0, 3, 1, 2)
+    z = _gather_pad(_zero_upsample(xn, up), pad0, pad0, (out_h - 1) * down + kh, (out_w - 1) * down + kw)
+    wt = w.permute(0, 3, 4, 1, 2)                                      # (Bw, OC, IC, KH, KW)
+    if bw == 1:
+        y = F.conv2d(z, wt[0], stride=down)
+    else:
+        y = torch.cat([F.conv2d(z[i:i + 1], wt[i], stride=down) for i in range(b)], 0)
+    y = y.permute(0, 2, 3, 1).contiguous()
+    if bias is not None or rowscale is not None or noise is not None or slope != 1.0 or gain != 1.0:
+        y = bias_act_fwd(y, bias, rowscale, noise, noise_w, slope, gain)
+    return y
+
+
+def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False):
+    b, _, _, ic = x.shape
+    oc = gy.shape[-1]
+    with torch.enable_grad():
+        w = x.new_zeros((b if per_sample else 1, kh, kw, oc, ic), requires_grad=True)
+        y = conv_fwd(x.detach(), w, gy.shape[1], gy.shape[2], up, down, pad0)
+        gw, = torch.autograd.grad(y, w, gy.detach())
+    return gw if x.dtype == torch.float64 else gw.float()
+
+
+def linear_fwd(x, w, bias, scale, bias_mul, act):
+    y = (x @ w.to(x.dtype).t()) * scale
+    if bias is not None:
+        y = y + bias.to(x.dtype) * bias_mul
+    if act:
+        y = (2 ** 0.5) * torch.where(y > 0, y, 0.2 * y)
+    return y
+
+
+def gemm_f32(a, b, trans_a, trans_b, alpha=1.0):
+    a2 = a.t() if trans_a else a
+    b2 = b.t() if trans_b else b
+    return (alpha * (a2 @ b2)).contiguous()
+
+
+def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay=0.0, grad_scale=1.0):
+    gi = g * grad_scale
+    m.mul_(beta1).add_(gi, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)
+    if ema is not None:
+        ema.mul_(ema_decay).add_(p, alpha=1 - ema_decay)
+
+
+def launch_count():
+    return 0

@@ -20,3 +20,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def cpu_kernels(monkeypatch):
+    """Replace every libb200gan entry point by its CPU stand-in (oracle/kernels_ref.py) so the
+    host-side autograd algebra can be checked without a GPU.  Tests only -- the product has no
+    such switch."""
+    from gan_control_b200 import kernels
+    from oracle import kernels_ref
+    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad',
+                 'linear_fwd', 'gemm_f32', 'adam_ema', 'launch_count']:
+        monkeypatch.setattr(kernels, name, getattr(kernels_ref, name))
+    return kernels_ref
