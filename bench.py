@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the FFHQ-1024 G+D train step on 1/2/4/8 B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A "step" is one `discriminator_update` + one `generator_update` (generator_trainer.py:351-353) at
+BASELINE.json configs[1]: Generator(1024)/Discriminator(1024), channel_multiplier 2, per-GPU batch
+16, bf16 activations / fp32 accumulate and parameters, synthetic images, random-init weights, with
+the lazy regularisers at their real cadence (R1 every 16, path-length every 4 iterations).
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'images/sec FFHQ-1024 G+D train step'
+UNIT = 'images/s'
+# algorithmic work per image of the plain step, BASELINE.md section 2: 4*G_f + 8*D_f
+GFLOP_PER_IMG = {1024: 4 * 148.5 + 8 * 153.3, 512: 4 * 119.3 + 8 * 123.2, 256: 4 * 90.2 + 8 * 93.1}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=16)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--size', type=int, default=1024)
+    ap.add_argument('--batch', type=int, default=16, help='per-GPU batch')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-reg', action='store_true', help='plain steps only (no R1 / path-length)')
+    ap.add_argument('--cpu-sample-size', type=int, default=None, help='resolution of the CPU-baseline sample')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-roofline', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm),
+                'power_w_max': max(float(r[2]) for r in self.rows if r[2].replace('.', '').isdigit())}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(size, batch, threads, steps=1, warmup=0):
+    """The reference's own CPU implementation of the step (oracle port of gan_model.py +
+    generator_trainer.py step functions, fp32, FUSED=False arithmetic) on `batch` images."""
+    import torch
+    from oracle import params as P, stylegan2_oracle as O
+    torch.set_num_threads(threads)
+    sd_g = {k: v.requires_grad_(not k.endswith('kernel') and not k.startswith('noises.'))
+            for k, v in P.seeded_state_dict(P.generator_shapes(size, 512, 8, 2), 1).items()}
+    sd_d = {k: v.requires_grad_(not k.endswith('kernel')) for k, v in P.seeded_state_dict(P.discriminator_shapes(size, 2), 2).items()}
+    gp = [v for v in sd_g.values() if v.requires_grad]
+    dp = [v for v in sd_d.values() if v.requires_grad]
+    lr_g, b_g = O.lazy_adam_hparams(0.002, 4)
+    lr_d, b_d = O.lazy_adam_hparams(0.002, 16)
+    g_opt = torch.optim.Adam(gp, lr=lr_g, betas=b_g)
+    d_opt = torch.optim.Adam(dp, lr=lr_d, betas=b_d)
+    real = torch.randn(batch, 3, size, size).clamp_(-1, 1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        # discriminator_step (gt.py:645-667)
+        with torch.no_grad():
+            fake = O.generator_forward(sd_g, [torch.randn(batch, 512)], size)
+        d_loss = O.d_logistic_loss(O.discriminator_forward(sd_d, real, size), O.discriminator_forward(sd_d, fake, size)) / batch
+        d_opt.zero_grad()
+        d_loss.backward(inputs=dp)
+        d_opt.step()
+        # generator_step (gt.py:407-436)
+        fake = O.generator_forward(sd_g, [torch.randn(batch, 512)], size)
+        g_loss = O.g_nonsaturating_loss(O.discriminator_forward(sd_d, fake, size))
+        g_opt.zero_grad()
+        g_loss.backward(inputs=gp)
+        g_opt.step()
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warmup:]) / steps
+    return batch / t, t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on this box's host cores (see module docstring)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    size = args.cpu_sample_size or args.size
+    v, t = cpu_reference_step(size, 1, threads, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'FFHQ-{size} G+D plain train step, reference FUSED=False arithmetic on host CPU',
+                       'global_batch': 1, 'note': 'bounded sample: 1 image per step, <=2 timed steps'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': f'{max(1, min(args.steps, 2))} plain G+D step(s) on 1 image at {size}x{size}, fp32'},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def conv_roofline(torch, K, dtype, size, batch):
+    """Dominant kernel = the modulated / plain 3x3 convolution.  Time the forward convolution of the
+    layer with the most FLOPs per launch at this resolution, alone, with CUDA events on the launching
+    stream, inputs >> L2."""
+    # the 64ch 3x3 conv at size/2 (G conv512 / D res512.conv1 at size 1024): 19.33 GFLOP/img
+    res = size // 2
+    ch = {1024: 64, 512: 128, 256: 256}.get(size, 64)
+    x = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
+    w = (torch.randn(1, 3, 3, ch, ch, device='cuda') / (3 * ch ** 0.5)).to(dtype)
+    flops = 2.0 * batch * res * res * ch * ch * 9
+    for _ in range(3):
+        K.conv_fwd(x, w, res, res, 1, 1, 1)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        K.conv_fwd(x, w, res, res, 1, 1, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return flops / (ms * 1e-3) / 1e12, ms, f'conv3x3 {ch}->{ch} @{res}x{res} batch {batch}'
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from gan_control_b200 import kernels as K, modules as M
+    from gan_control_b200.train_step import GanTrainStep
+    act = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    size, batch = args.size, args.batch
+    torch.manual_seed(1234)          # identical init on every rank (replicas stay in sync by construction)
+    g = M.Generator(size, 512, 8, channel_multiplier=2, conv_transpose=True, act_dtype=act).to(dev)
+    g_ema = M.Generator(size, 512, 8, channel_multiplier=2, conv_transpose=True, act_dtype=act).to(dev)
+    d = M.Discriminator(size, channel_multiplier=2, act_dtype=act).to(dev)
+    step = GanTrainStep(g, d, g_ema, batch=batch, world_size=world)
+    torch.manual_seed(1000 + rank)   # independent latents / noise / data per replica
+    host_real = torch.randn(batch, 3, size, size).clamp_(-1, 1).pin_memory()
+    dev_real = host_real.to(dev)
+    reg = not args.no_reg
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e, first_iter):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = K.launch_count()
+        e0.record()
+        sink = 0.0
+        for it in range(n_steps):
+            i = first_iter + it
+            if e2e:
+                real = host_real.to(dev, non_blocking=True)      # this step's inputs from pinned host memory
+            else:
+                real = dev_real
+            d_loss, g_loss = step.train_step(i, real, regularize=reg)
+            if e2e:
+                sink += float(torch.stack([d_loss.float(), g_loss.float()]).cpu().sum())   # D2H read of the step's result
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / n_steps, K.launch_count() - n0
+
+    # warm-up (also runs one of each regulariser so every kernel / allocation exists)
+    for it in range(args.warmup):
+        step.train_step(it * 4, dev_real, regularize=reg and it == 0)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_step, launches = timed(args.steps, False, 1)
+    clocks = sampler.summary() if sampler else None
+    ms_e2e, _ = timed(max(1, args.steps // 2), True, 1)
+    ms_plain, _ = timed(max(1, min(args.steps, 4)), False, 1) if False else (None, None)
+    global_batch = batch * world
+    value = global_batch / (ms_step * 1e-3)
+    e2e_value = global_batch / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks, peak_kind = measured_peaks()
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if act == torch.bfloat16 else 'f32', 'data': 'synthetic',
+        'config': {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]): Generator({size})+Discriminator({size}) '
+                               f'channel_multiplier 2, random init, lazy regularisers at real cadence '
+                               f'(R1 /16, path-length /4)' + ('' if reg else ' DISABLED'),
+                   'global_batch': global_batch, 'per_gpu_batch': batch, 'parallelism': f'dp{world}',
+                   'l2': 'inputs larger than L2 (each step streams >10 GB of activations; no explicit flush)'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
+                'h2d_bytes_per_step': host_real.numel() * 4, 'd2h_bytes_per_step': 8},
+        'gpu_launches': launches,
+        'step_tflops': GFLOP_PER_IMG.get(size, 0) * value / 1e3,
+    }
+    if not args.skip_roofline:
+        tf, ms, what = conv_roofline(torch, K, act, size, batch)
+        peak = peaks.get('bf16_tflops', 1590.0)
+        line['roofline'] = {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak,
+                            'traffic': None, 'kernel': what, 'kernel_ms': ms, 'peak_source': peak_kind + ' (burst, kernel timed alone)'}
+    if not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        csize = args.cpu_sample_size or size
+        v, t = cpu_reference_step(csize, 1, threads)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': f'1 plain G+D step on 1 image at {csize}x{csize}, fp32, {t:.1f} s'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

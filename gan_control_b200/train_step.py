@@ -1,0 +1,334 @@
+"""The G+D training step of gan-control on the B200 path.
+
+Host-side mirror of ``GeneratorTrainer``'s step functions for the vanilla (adversarial + R1 +
+path-length) objective, with the same names and arithmetic:
+
+    discriminator_step            generator_trainer.py:645-667   (d_logistic_loss :690-695)
+    discriminator_regularize_step generator_trainer.py:697-719   (d_r1_loss :713-719)
+    generator_step                generator_trainer.py:407-436   (g_nonsaturating_loss :563-566)
+    generator_regularize_step     generator_trainer.py:568-624   (g_path_regularize :601-614)
+    optimiser setup               generator_trainer.py:158-173   (lazy-regularisation Adam)
+    accumulate (EMA)              trainers/utils.py:8-12, decay generator_trainer.py:332
+
+What is B200-native here:
+  * one process per GPU; the reference's single-process ``nn.DataParallel`` (gt.py:195-199:
+    replicate + scatter + gather every forward) is replaced by replicas that stay bit-identical
+    and exchange ONLY gradients: each network's parameters and gradients live in two flat fp32
+    arenas, gradients are all-reduced (NCCL over NVLink/NVSwitch) straight out of the arena in
+    buckets as backward produces them, no flatten/unflatten copies;
+  * Adam + the g_ema accumulation are one fused kernel over the arena (b200gan_adam_ema);
+  * no per-step ``.item()`` host syncs (gt.py:429,659,705): losses stay on the device.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import kernels as K
+from .ops import up32
+
+
+# ---------------------------------------------------------------------------------------------
+# losses (gt.py:563-566, 690-695, 713-719, 601-624)
+# ---------------------------------------------------------------------------------------------
+def g_nonsaturating_loss(fake_pred):
+    return F.softplus(-fake_pred).mean()
+
+
+def d_logistic_loss(real_pred, fake_pred):
+    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean()
+
+
+def d_r1_loss(real_pred, real_img):
+    grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    return up32(grad_real).pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+
+
+def g_path_regularize(fake_img, latents, mean_path_length, decay=0.01, pl_noise=None, all_reduce_mean=None):
+    if pl_noise is None:
+        pl_noise = torch.randn_like(fake_img)
+    pl_noise = pl_noise / math.sqrt(fake_img.shape[2] * fake_img.shape[3])
+    grad, = torch.autograd.grad(outputs=(fake_img * pl_noise).sum(), inputs=latents, create_graph=True)
+    path_lengths = torch.sqrt(grad.pow(2).sum(2).mean(1))
+    batch_mean = path_lengths.mean()
+    if all_reduce_mean is not None:
+        # the reference averages over the gathered full batch (gt.py:579,621-622)
+        batch_mean = batch_mean + (all_reduce_mean(batch_mean.detach()) - batch_mean.detach())
+    path_mean = mean_path_length + decay * (batch_mean - mean_path_length)
+    path_penalty = (path_lengths - path_mean).pow(2).mean()
+    return path_penalty, path_mean.detach(), path_lengths
+
+
+# ---------------------------------------------------------------------------------------------
+# flat parameter / gradient arenas
+# ---------------------------------------------------------------------------------------------
+class ParamArena:
+    """All parameters of a module as views into ONE fp32 buffer, gradients into another.
+
+    ``tail`` names parameters placed last so that a regularisation step can leave them out of the
+    optimiser (the reference's ``set_grad_none(..., none_*_grads)``, gt.py:594,708)."""
+
+    ALIGN = 32    # elements; keeps every view 128-byte aligned
+
+    def __init__(self, module, tail=()):
+        named = [(n, p) for n, p in module.named_parameters()]
+        head = [(n, p) for n, p in named if n not in tail]
+        last = [(n, p) for n, p in named if n in tail]
+        self.names, self.params, self.offsets = [], [], []
+        off = 0
+        for group in (head, last):
+            if group is last:
+                self.split = off
+            for n, p in group:
+                self.names.append(n)
+                self.params.append(p)
+                self.offsets.append(off)
+                off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        if not last:
+            self.split = off
+        self.numel = off
+        dev, dtype = named[0][1].device, named[0][1].dtype     # fp32 (fp64 only in the CPU algebra tests)
+        self.data = torch.zeros(off, dtype=dtype, device=dev)
+        self.grad = torch.zeros(off, dtype=dtype, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            assert p.dtype == dtype
+            view = self.data[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def check_views(self):
+        """backward must accumulate in place; a replaced .grad would silently drop out of the arena"""
+        for p, o in zip(self.params, self.offsets):
+            assert p.grad is not None and p.grad.data_ptr() == self.grad.data_ptr() + self.grad.element_size() * o, \
+                'a parameter gradient left the flat arena'
+
+
+class ArenaAdam:
+    """torch.optim.Adam semantics (eps 1e-8, no weight decay) on an arena, fused with EMA."""
+
+    def __init__(self, arena, lr, betas, ema_arena=None):
+        self.arena, self.lr, self.betas, self.ema = arena, lr, betas, ema_arena
+        self.m = torch.zeros_like(arena.data)
+        self.v = torch.zeros_like(arena.data)
+        self.steps = [0, 0]            # [head, tail] ranges step separately (see ParamArena.tail)
+
+    def step(self, skip_tail=False, ema_decay=None, grad_scale=1.0):
+        a = self.arena
+        ranges = [(0, a.split, 0)] + ([] if skip_tail or a.split == a.numel else [(a.split, a.numel, 1)])
+        for lo, hi, which in ranges:
+            if hi <= lo:
+                continue
+            self.steps[which] += 1
+            ema = None
+            if self.ema is not None and ema_decay is not None:
+                ema = self.ema.data[lo:hi]
+            K.adam_ema(a.data[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], ema, self.lr, self.betas[0],
+                       self.betas[1], 1e-8, self.steps[which], ema_decay if ema is not None else 0.0, grad_scale)
+
+
+class GradBuckets:
+    """Bucketed gradient all-reduce out of a ParamArena, launched as backward fills buckets."""
+
+    def __init__(self, arena, world_size, bucket_mb=32, group=None):
+        self.arena, self.world, self.group = arena, world_size, group
+        self.enabled = world_size > 1
+        self.pending = []
+        if not self.enabled:
+            return
+        cap = bucket_mb * (1 << 20) // 4
+        self.bucket_of, self.bucket_range, self.bucket_size = {}, [], []
+        # backward produces gradients roughly in reverse registration order: bucket from the end
+        hi = arena.numel
+        members = 0
+        lo_edge = hi
+        idx = 0
+        for i in reversed(range(len(arena.params))):
+            lo_edge = arena.offsets[i]
+            self.bucket_of[i] = idx
+            members += 1
+            if hi - lo_edge >= cap or i == 0:
+                self.bucket_range.append((lo_edge, hi))
+                self.bucket_size.append(members)
+                hi, members, idx = lo_edge, 0, idx + 1
+        self.count = [0] * len(self.bucket_range)
+        for i, p in enumerate(arena.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self.active = False
+
+    def _make_hook(self, i):
+        def hook(param):
+            if not self.active:
+                return
+            b = self.bucket_of[i]
+            self.count[b] += 1
+            if self.count[b] == self.bucket_size[b]:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        lo, hi = self.bucket_range[b]
+        self.launched[b] = True
+        self.pending.append(dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def begin(self, expected=None):
+        """arm the hooks for one backward pass"""
+        if not self.enabled:
+            return
+        self.active = True
+        self.count = [0] * len(self.bucket_range)
+        self.launched = [False] * len(self.bucket_range)
+
+    def finish(self):
+        """after backward: reduce whatever did not fill (parameters without a gradient this pass),
+        wait for everything; gradients are SUMS over ranks (the optimiser divides by world)."""
+        if not self.enabled:
+            return
+        self.active = False
+        for b in range(len(self.bucket_range)):
+            if not self.launched[b]:
+                self._launch(b)
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+
+# ---------------------------------------------------------------------------------------------
+class GanTrainStep:
+    """One process = one GPU = one replica.  ``batch`` is the per-replica batch."""
+
+    def __init__(self, generator, discriminator, g_ema=None, batch=16, lr_g=0.002, lr_d=0.002, r1=1.0,
+                 d_reg_every=16, g_reg_every=4, path_regularize=2.0, path_batch_shrink=2, mixing=0.0,
+                 g_moving_average=10000, latent_size=512, world_size=1, bucket_mb=32, global_batch=None):
+        self.g, self.d, self.g_ema = generator, discriminator, g_ema
+        self.batch, self.world = batch, world_size
+        self.global_batch = global_batch or batch * world_size
+        self.r1, self.d_reg_every, self.g_reg_every = r1, d_reg_every, g_reg_every
+        self.path_regularize, self.path_batch_shrink, self.mixing = path_regularize, path_batch_shrink, mixing
+        self.latent_size = latent_size
+        self.device = next(generator.parameters()).device
+        self.mean_path_length = torch.zeros((), device=self.device, dtype=next(generator.parameters()).dtype)
+        self.accum = 0.5 ** (self.global_batch / g_moving_average)                       # gt.py:332
+        # parameters that get no gradient from the regularisers (gt.py:301-327 dry_run finds them):
+        g_tail = [n for n, _ in generator.named_parameters() if n.startswith('to_rgb') and n.endswith('.bias')
+                  and 'modulation' not in n]
+        d_tail = ['final_linear.1.bias']
+        self.g_arena = ParamArena(generator, tail=g_tail)
+        self.d_arena = ParamArena(discriminator, tail=d_tail)
+        self.ema_arena = ParamArena(g_ema, tail=g_tail) if g_ema is not None else None
+        if self.ema_arena is not None:
+            self.ema_arena.data.copy_(self.g_arena.data)                                 # accumulate(g_ema, g, 0)
+        g_ratio = g_reg_every / (g_reg_every + 1)                                        # gt.py:158-173
+        d_ratio = d_reg_every / (d_reg_every + 1)
+        self.g_optim = ArenaAdam(self.g_arena, lr_g * g_ratio, (0 ** g_ratio, 0.99 ** g_ratio), self.ema_arena)
+        self.d_optim = ArenaAdam(self.d_arena, lr_d * d_ratio, (0 ** d_ratio, 0.99 ** d_ratio))
+        self.g_buckets = GradBuckets(self.g_arena, world_size, bucket_mb)
+        self.d_buckets = GradBuckets(self.d_arena, world_size, bucket_mb)
+        self.stats = {}
+
+    # -- helpers ------------------------------------------------------------------------------
+    @staticmethod
+    def requires_grad(model, flag=True):                                                 # tu:13-15
+        for p in model.parameters():
+            p.requires_grad_(flag)
+
+    def mixing_noise(self, batch):                                                       # tu:19-23
+        import random
+        if self.mixing > 0 and random.random() < self.mixing:
+            return list(torch.randn(2, batch, self.latent_size, device=self.device).unbind(0))
+        return [torch.randn(batch, self.latent_size, device=self.device)]
+
+    def _mean_over_ranks(self, t):
+        if self.world > 1:
+            t = t.clone()
+            dist.all_reduce(t)
+            t /= self.world
+        return t
+
+    # -- discriminator ------------------------------------------------------------------------
+    def discriminator_step(self, real_img, noise):
+        self.requires_grad(self.g, False)
+        self.requires_grad(self.d, True)
+        self.d_arena.zero_grad()
+        with torch.no_grad():
+            fake_img, _ = self.g(noise)
+        fake_pred, _ = self.d(fake_img)
+        real_pred, _ = self.d(real_img)
+        d_loss = d_logistic_loss(real_pred, fake_pred)
+        d_loss = d_loss / self.global_batch          # gt.py:656 `d_loss.div_(len(mini_real_img))`, kept
+        self.d_buckets.begin()
+        d_loss.backward()
+        self.d_buckets.finish()
+        self.d_optim.step(grad_scale=1.0 / self.world)
+        self.stats['d_loss'] = d_loss.detach()
+        return d_loss.detach()
+
+    def discriminator_regularize_step(self, real_img):
+        self.requires_grad(self.g, False)
+        self.requires_grad(self.d, True)
+        self.d_arena.zero_grad()
+        real_img = real_img.detach().requires_grad_(True)
+        real_pred, _ = self.d(real_img)
+        r1_loss = d_r1_loss(real_pred, real_img)
+        self.d_buckets.begin()
+        (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * real_pred[0]).sum().backward()   # gt.py:706
+        self.d_buckets.finish()
+        self.d_optim.step(skip_tail=True, grad_scale=1.0 / self.world)                    # set_grad_none gt.py:708
+        self.stats['r1_loss'] = r1_loss.detach()
+        return r1_loss.detach()
+
+    # -- generator ----------------------------------------------------------------------------
+    def generator_step(self, noise, ema=True):
+        self.requires_grad(self.g, True)
+        self.requires_grad(self.d, False)
+        self.g_arena.zero_grad()
+        fake_img, _ = self.g(noise)
+        fake_pred, _ = self.d(fake_img)
+        g_loss = g_nonsaturating_loss(fake_pred)
+        self.g_buckets.begin()
+        g_loss.backward()
+        self.g_buckets.finish()
+        self.g_optim.step(ema_decay=self.accum if ema else None, grad_scale=1.0 / self.world)
+        self.stats['g_loss'] = g_loss.detach()
+        return g_loss.detach()
+
+    def generator_regularize_step(self, noise=None, pl_noise=None):
+        self.requires_grad(self.g, True)
+        self.requires_grad(self.d, False)
+        self.g_arena.zero_grad()
+        path_batch = max(1, self.batch // self.path_batch_shrink)
+        if noise is None:
+            noise = self.mixing_noise(path_batch)
+        fake_img, latents = self.g(noise, return_latents=True)
+        path_loss, self.mean_path_length, path_lengths = g_path_regularize(
+            fake_img, latents, self.mean_path_length, pl_noise=pl_noise,
+            all_reduce_mean=self._mean_over_ranks if self.world > 1 else None)
+        weighted = self.path_regularize * self.g_reg_every * path_loss                     # gt.py:587-590
+        if self.path_batch_shrink:
+            weighted = weighted + 0 * up32(fake_img[0, 0, 0, 0])
+        self.g_buckets.begin()
+        weighted.backward()
+        self.g_buckets.finish()
+        self.g_optim.step(skip_tail=True, grad_scale=1.0 / self.world)                    # set_grad_none gt.py:594
+        self.stats['path_loss'] = path_loss.detach()
+        return path_loss.detach()
+
+    # -- one iteration (gt.py:343-353: discriminator_update, generator_update) ------------------------
+    def train_step(self, i, real_img, regularize=True):
+        noise = self.mixing_noise(self.batch)
+        d_loss = self.discriminator_step(real_img, noise)
+        if regularize and i % self.d_reg_every == 0:
+            self.discriminator_regularize_step(real_img)
+        noise = self.mixing_noise(self.batch)
+        do_g_reg = regularize and i % self.g_reg_every == 0
+        g_loss = self.generator_step(noise, ema=not do_g_reg)
+        if do_g_reg:
+            self.generator_regularize_step()
+            # accumulate() runs once per iteration after both G updates (gt.py:362-369)
+            if self.ema_arena is not None:
+                self.ema_arena.data.mul_(self.accum).add_(self.g_arena.data, alpha=1 - self.accum)
+        return d_loss, g_loss

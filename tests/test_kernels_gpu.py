@@ -1,0 +1,150 @@
+"""Each libb200gan kernel against its contract stand-in (oracle/kernels_ref.py, evaluated in fp64
+on the CPU) on seeded random inputs: fp32 storage to ~1e-5, bf16 storage to bf16 rounding."""
+import numpy as np
+import pytest
+import torch
+
+from gan_control_b200 import kernels as K
+from oracle import kernels_ref as R
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def rnd(seed, *shape):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape))
+
+
+def tol(dt):
+    return 2e-5 if dt == torch.float32 else 1.2e-2
+
+
+def prep(t, dt):
+    """device tensor in dt and the fp64 CPU value it actually holds"""
+    d = t.to(dt).cuda()
+    return d, d.cpu().double()
+
+
+def close(out, ref, dt, what=''):
+    err = float((out.detach().cpu().double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    assert err < tol(dt), f'{what}: rel err {err:.3e}'
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('cfg', [
+    # n, h, w, c, kh, up, down, pad0, out_h, out_w, flip
+    (2, 9, 9, 8, 4, 1, 1, 1, 8, 8, True), (2, 6, 7, 3, 4, 2, 1, 2, 12, 14, True), (3, 8, 8, 16, 4, 1, 1, 2, 9, 9, False),
+    (2, 21, 21, 1, 12, 1, 2, 0, 5, 5, True), (1, 10, 10, 4, 12, 2, 1, 0, 9, 9, True), (2, 9, 7, 5, 4, 1, 1, -1, 7, 5, True),
+    (2, 33, 33, 32, 4, 1, 1, 1, 32, 32, True), (2, 5, 5, 24, 4, 1, 2, 1, 2, 2, False),
+])
+def test_upfirdn2d(cfg, dt):
+    n, h, w, c, k, up, down, pad0, oh, ow, flip = cfg
+    x, xr = prep(rnd(1, n, h, w, c), dt)
+    taps = rnd(2, k, k).float()
+    y = K.upfirdn2d(x, taps.cuda(), up, down, pad0, pad0, oh, ow, flip, 1.5)
+    close(y, R.upfirdn2d(xr, taps.double(), up, down, pad0, pad0, oh, ow, flip, 1.5), dt)
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('shape,planar', [((3, 5, 7, 16), False), ((2, 4, 4, 3), False), ((2, 5, 6, 6), True), ((4, 24), True)])
+def test_bias_act(shape, planar, dt):
+    x, xr = prep(rnd(3, *shape), dt)
+    c = shape[1] if planar else shape[-1]
+    n = shape[0]
+    bias, rs, nw = rnd(4, c).float(), (rnd(5, n, c).abs() + 0.5).float(), torch.tensor([0.7])
+    npix = int(np.prod(shape)) // (n * c)
+    noise, noiser = prep(rnd(6, n, npix), dt)
+    y = K.bias_act_fwd(x, bias.cuda(), rs.cuda(), noise, nw.cuda(), 0.2, 2 ** 0.5, planar)
+    yr = R.bias_act_fwd(xr, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5, planar)
+    close(y, yr, dt, 'fwd')
+    gy, gyr = prep(rnd(7, *shape), dt)
+    ysaved = y.cpu().double()
+    close(K.bias_act_bwd(gy, y, rs.cuda(), 0.2, 2 ** 0.5, planar), R.bias_act_bwd(gyr, ysaved, rs.double(), 0.2, 2 ** 0.5, planar), dt, 'bwd')
+    close(K.bias_act_fwd(x, None, None, None, None, 1.0, 1.0, planar), xr, dt, 'identity')
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('shape', [(3, 9, 9, 16), (2, 64, 64, 40), (1, 3, 3, 513), (16, 4, 4, 512)])
+def test_reduce_nhwc(shape, dt):
+    a, ar = prep(rnd(8, *shape), dt)
+    b, br = prep(rnd(9, *shape), dt)
+    pw, pwr = prep(rnd(10, *shape[:-1]), dt)
+    oc, onc = K.reduce_nhwc(a, b, True, True)
+    rc, rnc = R.reduce_nhwc(ar, br, True, True)
+    scale = float(rnc.abs().max())
+    assert float((oc.cpu().double() - rc).abs().max()) < 1e-4 * max(scale, float(rc.abs().max()))
+    assert float((onc.cpu().double() - rnc).abs().max()) < 1e-4 * scale
+    oc2, _ = K.reduce_nhwc(a, None, True, False, pixw=pw)
+    rc2, _ = R.reduce_nhwc(ar, None, True, False, pixw=pwr)
+    assert float((oc2.cpu().double() - rc2).abs().max()) < 1e-4 * float(rc2.abs().max() + 1)
+
+
+CONV_CASES = [
+    # b, h, w, ic, oc, k, up, down, pad0, per_sample
+    (2, 8, 8, 16, 32, 3, 1, 1, 1, False), (3, 7, 9, 8, 12, 3, 1, 1, 1, True), (2, 6, 6, 8, 6, 3, 2, 1, 2, True),
+    (2, 9, 9, 16, 8, 3, 1, 2, 0, False), (2, 8, 8, 3, 32, 1, 1, 1, 0, False), (2, 4, 4, 513, 64, 3, 1, 1, 1, False),
+    (4, 16, 16, 64, 3, 1, 1, 1, 0, True), (2, 7, 7, 8, 8, 1, 1, 2, 0, False), (1, 12, 12, 24, 40, 3, 1, 1, 1, False),
+    (2, 5, 5, 32, 16, 3, 2, 1, 2, False), (2, 17, 17, 16, 16, 3, 1, 2, 0, True), (3, 4, 4, 128, 128, 3, 1, 1, 1, False),
+]
+
+
+def conv_out_hw(h, w, k, up, down, pad0):
+    zh, zw = (h - 1) * up + 1, (w - 1) * up + 1
+    return (zh + 2 * pad0 - k) // down + 1, (zw + 2 * pad0 - k) // down + 1
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_fwd_and_wgrad(case, dt):
+    b, h, w, ic, oc, k, up, down, pad0, ps = case
+    oh, ow = conv_out_hw(h, w, k, up, down, pad0)
+    x, xr = prep(rnd(11, b, h, w, ic), dt)
+    wt, wr = prep(rnd(12, b if ps else 1, k, k, oc, ic) / (ic * k * k) ** 0.5, dt)
+    y = K.conv_fwd(x, wt, oh, ow, up, down, pad0)
+    close(y, R.conv_fwd(xr, wr, oh, ow, up, down, pad0), dt, 'fwd')
+    # fused epilogue
+    bias, rs, nw = rnd(13, oc).float(), (rnd(14, b, oc).abs() + 0.5).float(), torch.tensor([0.3])
+    noise, noiser = prep(rnd(15, b, oh, ow), dt)
+    y2 = K.conv_fwd(x, wt, oh, ow, up, down, pad0, bias.cuda(), rs.cuda(), noise, nw.cuda(), 0.2, 2 ** 0.5)
+    close(y2, R.conv_fwd(xr, wr, oh, ow, up, down, pad0, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5), dt, 'fwd+epilogue')
+    gy, gyr = prep(rnd(16, b, oh, ow, oc), dt)
+    gw = K.conv_wgrad(x, gy, k, k, up, down, pad0, ps)
+    gwr = R.conv_wgrad(xr, gyr, k, k, up, down, pad0, ps)
+    err = float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max())
+    assert err < 1e-4, f'wgrad rel err {err:.2e}'
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+def test_linear_and_gemm(dt):
+    x, xr = prep(rnd(20, 7, 96), dt)
+    w, b = rnd(21, 40, 96).float(), rnd(22, 40).float()
+    for act in [0, 1]:
+        close(K.linear_fwd(x, w.cuda(), b.cuda(), 0.05, 0.3, act), R.linear_fwd(xr, w.double(), b.double(), 0.05, 0.3, act), dt)
+    if dt == torch.float32:
+        for ta in [False, True]:
+            for tb in [False, True]:
+                a = rnd(23, *((33, 17) if ta else (17, 33))).float()
+                bb = rnd(24, *((50, 33) if tb else (33, 50))).float()
+                close(K.gemm_f32(a.cuda(), bb.cuda(), ta, tb, 0.7), R.gemm_f32(a.double(), bb.double(), ta, tb, 0.7), dt, f'gemm {ta}{tb}')
+        # split-K path: skinny M, long K
+        a, bb = rnd(25, 16, 8192).float(), rnd(26, 512, 8192).float()
+        close(K.gemm_f32(a.cuda(), bb.cuda(), False, True, 1.0), R.gemm_f32(a.double(), bb.double(), False, True, 1.0), dt, 'split-k')
+
+
+def test_adam_ema():
+    p, g = rnd(30, 1000).float(), rnd(31, 1000).float()
+    m, v, ema = torch.zeros(1000), torch.zeros(1000), p.clone()
+    dev = [t.clone().cuda() for t in (p, g, m, v, ema)]
+    ref = [t.clone().double() for t in (p, g, m, v, ema)]
+    for step in (1, 2, 3):
+        K.adam_ema(*dev, lr=0.002, beta1=0.0, beta2=0.99, eps=1e-8, step=step, ema_decay=0.998)
+        R.adam_ema(*ref, lr=0.002, beta1=0.0, beta2=0.99, eps=1e-8, step=step, ema_decay=0.998)
+    for d, r in zip(dev, ref):
+        assert float((d.cpu().double() - r).abs().max()) < 1e-5
+    # agrees with torch.optim.Adam
+    pt = torch.nn.Parameter(p.clone().cuda())
+    opt = torch.optim.Adam([pt], lr=0.002, betas=(0.0, 0.99))
+    for _ in range(3):
+        pt.grad = g.cuda()
+        opt.step()
+    assert float((pt.detach() - dev[0]).abs().max()) < 1e-5

@@ -1,0 +1,224 @@
+"""Parity of the CUDA path with the reference (FUSED=False) through the reference-facing API:
+ops and modules on cuda vs the goldens generated from /root/reference, fp32 storage to 1e-3
+relative (north_star tolerance; measured ~1e-6..1e-5), bf16 storage reported and bounded."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from gan_control_b200 import modules as M
+from gan_control_b200 import ops
+from oracle import params as P
+from oracle import stylegan2_oracle as O
+from golden_io import Fixture, reduce_like_golden, max_rel, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3            # north_star: within 1e-3 relative of the fp32 reference
+DEV = 'cuda'
+UP_CASES = ['g_upblur', 'rgb_skip', 'd_conv2_blur', 'd_skip_blur', 'ada_up', 'ada_down', 'down_module', 'negpad', 'rect']
+
+
+def rnd(seed, *shape, dtype=torch.float32):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape)).to(dtype)
+
+
+@pytest.mark.parametrize('layout', ['nchw', 'channels_last'])
+@pytest.mark.parametrize('name', UP_CASES)
+def test_upfirdn2d(name, layout):
+    fx = Fixture('upfirdn2d')
+    up, down, p0, p1 = [int(v) for v in fx.np(name + '.cfg')]
+    x = fx.t(name + '.x', torch.float32, DEV)
+    if layout == 'channels_last':
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y = ops.upfirdn2d(x, fx.t(name + '.k', torch.float32, DEV), up, down, (p0, p1))
+    assert max_rel(y, fx.t(name + '.y')) < 1e-5
+    gx, = torch.autograd.grad(y, x, fx.t(name + '.gy', torch.float32, DEV))
+    assert max_rel(gx, fx.t(name + '.gx')) < 1e-5
+
+
+def test_fused_leaky_relu_and_linear():
+    fx = Fixture('bias_act')
+    for c in ['c0', 'c1']:
+        x = fx.t(c + '.x', torch.float32, DEV).requires_grad_(True)
+        b = fx.t(c + '.b', torch.float32, DEV).requires_grad_(True)
+        y = ops.fused_leaky_relu(x, b)
+        assert max_rel(y, fx.t(c + '.y')) < 1e-6
+        gx, gb = torch.autograd.grad(y, (x, b), fx.t(c + '.gy', torch.float32, DEV))
+        assert max_rel(gx, fx.t(c + '.gx')) < 1e-6 and max_rel(gb, fx.t(c + '.gb')) < 1e-5
+    fx = Fixture('equal_linear')
+    for c in ['c0', 'c1', 'c2']:
+        lr_mul, act = fx.np(c + '.cfg')
+        w = fx.t(c + '.w', torch.float32)
+        m = M.EqualLinear(w.shape[1], w.shape[0], lr_mul=float(lr_mul), activation='fused_lrelu' if act else None)
+        m.weight.data.copy_(w)
+        m.bias.data.copy_(fx.t(c + '.b', torch.float32))
+        m.to(DEV)
+        x = fx.t(c + '.x', torch.float32, DEV).requires_grad_(True)
+        y = m(x)
+        assert max_rel(y, fx.t(c + '.y')) < 1e-5
+        g = torch.autograd.grad(y, (x, m.weight, m.bias), fx.t(c + '.gy', torch.float32, DEV))
+        for gi, n in zip(g, ['gx', 'gw', 'gb']):
+            assert max_rel(gi, fx.t(f'{c}.{n}')) < 1e-5, n
+
+
+@pytest.mark.parametrize('form', ['weight', 'activation'])
+@pytest.mark.parametrize('name', ['plain3', 'up3', 'rgb1', 'plain3_b1'])
+def test_modulated_conv(name, form):
+    fx = Fixture('modconv')
+    ic, oc, k, demod, up, h, b, sdim = [int(v) for v in fx.np(name + '.cfg')]
+    m = M.ModulatedConv2d(ic, oc, k, sdim, demodulate=bool(demod), upsample=bool(up), conv_transpose=True)
+    m.form = form
+    m.weight.data.copy_(fx.t(name + '.w'))
+    m.modulation.weight.data.copy_(fx.t(name + '.mw'))
+    m.modulation.bias.data.copy_(fx.t(name + '.mb'))
+    m.to(DEV)
+    x = fx.t(name + '.x', torch.float32, DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    s = fx.t(name + '.s', torch.float32, DEV).requires_grad_(True)
+    y = m(x, s)
+    assert max_rel(y, fx.t(name + '.y')) < 1e-5
+    ps = (x, s, m.weight, m.modulation.weight, m.modulation.bias)
+    g = torch.autograd.grad(y, ps, fx.t(name + '.gy', torch.float32, DEV), create_graph=True)
+    for gi, n in zip(g, ['gx', 'gs', 'gw', 'gmw', 'gmb']):
+        assert max_rel(gi, fx.t(f'{name}.{n}')) < 1e-4, n
+    pl = g[1].pow(2).sum()
+    assert max_rel(pl, fx.t(name + '.pl')) < 1e-4
+    gg = torch.autograd.grad(pl, (x, s, m.weight, m.modulation.weight), allow_unused=True)
+    for gi, n in zip(gg, ['pl_gx', 'pl_gs', 'pl_gw', 'pl_gmw']):
+        if gi is not None:
+            assert max_rel(gi, fx.t(f'{name}.{n}')) < TOL, n
+    g2 = torch.autograd.grad(m(x, s), ps, fx.t(name + '.gy', torch.float32, DEV))
+    for gi, n in zip(g2, ['gx', 'gs', 'gw', 'gmw', 'gmb']):
+        assert max_rel(gi, fx.t(f'{name}.{n}')) < 1e-4, n
+
+
+def test_styled_conv_and_to_rgb():
+    fx = Fixture('modconv')
+    for up in [0, 1]:
+        n = f'styled_up{up}'
+        m = M.StyledConv(8, 6, 3, 16, upsample=bool(up), conv_transpose=True)
+        m.load_state_dict(fx.sub(n + '.sd.', torch.float32))
+        m.to(DEV)
+        y = m(fx.t(n + '.x', torch.float32, DEV), fx.t(n + '.s', torch.float32, DEV), noise=fx.t(n + '.noise', torch.float32, DEV))
+        assert max_rel(y, fx.t(n + '.y')) < 1e-5
+    m = M.ToRGB(8, 16, conv_transpose=True)
+    m.load_state_dict(fx.sub('torgb.sd.', torch.float32))
+    m.to(DEV)
+    y = m(fx.t('torgb.x', torch.float32, DEV), fx.t('torgb.s', torch.float32, DEV), fx.t('torgb.skip', torch.float32, DEV))
+    assert max_rel(y, fx.t('torgb.y')) < 1e-5
+
+
+GROUPS = [('id', 0, 24), ('pose', 24, 40), ('other', 40, 64)]
+
+
+def _fc_config(groups):
+    return M.FcConfig([g[0] for g in groups], {n: {'latent_place': [lo, hi], 'latent_size': hi - lo} for n, lo, hi in groups})
+
+
+@pytest.mark.parametrize('name,fcg', [('g16', None), ('g16split', GROUPS)])
+def test_generator_fp32(name, fcg):
+    fx = Fixture('networks')
+    size, sdim, n_mlp, seed = [int(v) for v in fx.np(name + '.cfg')]
+    shapes = P.generator_shapes(size, sdim, n_mlp, 2, fcg)
+    g = M.Generator(size, sdim, n_mlp, channel_multiplier=2, conv_transpose=True, split_fc=fcg is not None,
+                    fc_config=_fc_config(fcg) if fcg else None)
+    g.load_state_dict(P.seeded_state_dict(shapes, seed))
+    g.to(DEV)
+    z, z2 = rnd(seed * 10, 2, sdim).to(DEV), rnd(seed * 10 + 1, 2, sdim).to(DEV)
+    noise = [rnd(seed * 100 + i, 2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)).to(DEV) for i in range(g.num_layers)]
+    img, lat = g([z], noise=noise, return_latents=True)
+    assert max_rel(lat, fx.t(f'{name}.f64.latent')) < 1e-4
+    e = max_rel(img, fx.t(f'{name}.f64.img'))
+    print(f'{name}: fp32 image max-rel err vs fp64 reference {e:.2e}')
+    assert e < TOL
+    assert max_rel(g([z, z2], noise=noise, inject_index=3)[0], fx.t(f'{name}.f64.img_mix')) < TOL
+    assert max_rel(g([z], randomize_noise=False)[0], fx.t(f'{name}.f64.img_fixed_noise')) < TOL
+    # path-length regulariser (double backward on the GPU kernels)
+    img, lat = g([z], noise=noise, return_latents=True)
+    torch.manual_seed(seed)
+    pl_noise = torch.randn(img.shape, dtype=torch.float64).float().to(DEV)
+    pen, mean, lengths = O.g_path_regularize(img, lat, 0.0, pl_noise=pl_noise)
+    assert max_rel(pen, fx.t(name + '.pl.penalty')) < TOL
+    g.zero_grad()
+    pen.backward()
+    params = dict(g.named_parameters())
+    for k in fx.keys(name + '.pl.g.'):
+        key = k[len(name) + 6:]
+        assert max_rel(reduce_like_golden(params[key].grad), fx.t(k)) < TOL, key
+    g.zero_grad()
+    img, _ = g([z], noise=noise)
+    (img * fx.t(name + '.bw.cot', torch.float32, DEV)).sum().backward()
+    for k in fx.keys(name + '.bw.g.'):
+        key = k[len(name) + 6:]
+        assert max_rel(reduce_like_golden(params[key].grad), fx.t(k)) < TOL, key
+
+
+def test_discriminator_fp32():
+    fx = Fixture('networks')
+    shapes = P.discriminator_shapes(16, 2)
+    d = M.Discriminator(16, channel_multiplier=2)
+    d.load_state_dict(P.seeded_state_dict(shapes, 21))
+    d.to(DEV)
+    x = rnd(210, 8, 3, 16, 16).to(DEV).requires_grad_(True)
+    pred, _ = d(x)
+    assert max_rel(pred, fx.t('d16.f64.pred')) < TOL
+    r1 = O.d_r1_loss(pred, x)
+    assert max_rel(r1, fx.t('d16.r1')) < TOL
+    d.zero_grad()
+    (0.5 * r1 * 16 + 0 * pred[0]).sum().backward()
+    params = dict(d.named_parameters())
+    # R1 gradients of the biases are ~1e-7 (the net is piecewise linear; only minibatch-stddev bends it):
+    # judge them on the scale of the weight gradients of the same layer group, not on their own max
+    scale = max(float(fx.t(k).abs().max()) for k in fx.keys('d16.r1.g.'))
+    for k in fx.keys('d16.r1.g.'):
+        key = k[len('d16.r1.g.'):]
+        got, want = reduce_like_golden(params[key].grad), fx.t(k)
+        assert max_rel(got, want) < TOL or float((got - want).abs().max()) < 1e-6 * scale, key
+    d.zero_grad()
+    loss = O.d_logistic_loss(d(x.detach())[0], d(rnd(211, 8, 3, 16, 16).to(DEV))[0])
+    assert max_rel(loss, fx.t('d16.dloss')) < 1e-4
+    loss.backward()
+    for k in fx.keys('d16.dl.g.'):
+        key = k[len('d16.dl.g.'):]
+        assert max_rel(reduce_like_golden(params[key].grad), fx.t(k)) < TOL, key
+
+
+def test_config1_generator256_fp32():
+    """BASELINE.json configs[0] on the GPU: Generator(256) forward batch 1 vs the reference output."""
+    fx = Fixture('config1_g256')
+    g = M.Generator(256, 512, 8, channel_multiplier=2, conv_transpose=True)
+    g.load_state_dict(P.seeded_state_dict(P.generator_shapes(256, 512, 8, 2), 31))
+    g.to(DEV).eval()
+    with torch.no_grad():
+        img, _ = g([fx.t('z', torch.float32, DEV)], randomize_noise=False)
+    e = max_rel(img[0, :, 128, :], fx.t('img_row'))
+    print(f'config1 G256 fp32: max-rel err of centre row vs reference {e:.2e}')
+    assert e < TOL
+    assert rel_err(img, fx.t('img').float()) < 2e-3      # golden image stored as fp16
+
+
+def test_generator_discriminator_bf16():
+    """bf16 storage (the throughput configuration): bounded deviation from the fp64 reference."""
+    fx = Fixture('networks')
+    name = 'g16'
+    size, sdim, n_mlp, seed = [int(v) for v in fx.np(name + '.cfg')]
+    g = M.Generator(size, sdim, n_mlp, channel_multiplier=2, conv_transpose=True, act_dtype=torch.bfloat16)
+    g.load_state_dict(P.seeded_state_dict(P.generator_shapes(size, sdim, n_mlp, 2), seed))
+    g.to(DEV)
+    z = rnd(seed * 10, 2, sdim).to(DEV)
+    noise = [rnd(seed * 100 + i, 2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)).to(DEV) for i in range(g.num_layers)]
+    img, _ = g([z], noise=noise)
+    assert img.dtype == torch.bfloat16
+    e = rel_err(img, fx.t(f'{name}.f64.img'))
+    print(f'g16 bf16: image rel-L2 err vs fp64 reference {e:.2e}')
+    assert e < 3e-2
+    d = M.Discriminator(16, channel_multiplier=2, act_dtype=torch.bfloat16)
+    d.load_state_dict(P.seeded_state_dict(P.discriminator_shapes(16, 2), 21))
+    d.to(DEV)
+    pred, _ = d(rnd(210, 8, 3, 16, 16).to(DEV))
+    e = rel_err(pred, fx.t('d16.f64.pred'))
+    print(f'd16 bf16: pred rel-L2 err vs fp64 reference {e:.2e}')
+    assert e < 5e-2
+    torch.nn.functional.softplus(-d(img)[0]).mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in g.parameters() if p.grad is not None)

@@ -1,0 +1,178 @@
+"""The training step (gan_control_b200/train_step.py) against a restatement of the reference's step
+functions built from the oracle + torch.optim.Adam, on CPU with the kernel stand-ins: single
+replica, and two gloo replicas vs the same global batch on one."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gan_control_b200 import modules as M
+from gan_control_b200.train_step import GanTrainStep
+from oracle import params as P
+from oracle import stylegan2_oracle as O
+
+SIZE, SDIM, NMLP = 8, 32, 2
+
+
+F64 = torch.float64
+
+
+def rnd(seed, *shape):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape))      # fp64: Adam(beta1=0) amplifies rounding noise
+
+
+class FixedNoiseG(M.Generator):
+    """deterministic per-layer noise so that two implementations see the same draw"""
+    def forward(self, styles, **kw):
+        if kw.get('noise') is None:
+            b = styles[0].shape[0]
+            kw['noise'] = [self.fixed_noise[i][:b] for i in range(self.num_layers)]
+        return super().forward(styles, **kw)
+
+
+def build(batch):
+    g = FixedNoiseG(SIZE, SDIM, NMLP, channel_multiplier=2, conv_transpose=True, act_dtype=F64).double()
+    g.load_state_dict(P.seeded_state_dict(P.generator_shapes(SIZE, SDIM, NMLP, 2), 5, dtype=F64))
+    g.fixed_noise = [rnd(50 + i, batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i in range(g.num_layers)]
+    g_ema = copy.deepcopy(g)
+    d = M.Discriminator(SIZE, channel_multiplier=2, act_dtype=F64).double()
+    d.load_state_dict(P.seeded_state_dict(P.discriminator_shapes(SIZE, 2), 6, dtype=F64))
+    return g, g_ema, d
+
+
+def oracle_run(batch, real, zs, pl_noise, iters):
+    """generator_trainer.py:343-369,407-436,568-599,645-711 restated on the oracle."""
+    sd_g = {k: v.clone().requires_grad_(not k.endswith('kernel') and not k.startswith('noises.'))
+            for k, v in P.seeded_state_dict(P.generator_shapes(SIZE, SDIM, NMLP, 2), 5, dtype=F64).items()}
+    sd_d = {k: v.clone().requires_grad_(not k.endswith('kernel')) for k, v in P.seeded_state_dict(P.discriminator_shapes(SIZE, 2), 6, dtype=F64).items()}
+    ema = {k: v.detach().clone() for k, v in sd_g.items() if v.requires_grad}
+    noise = [rnd(50 + i, batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i in range(2 * (int(np.log2(SIZE)) - 2) + 1)]
+    gp = {k: v for k, v in sd_g.items() if v.requires_grad}
+    dp = {k: v for k, v in sd_d.items() if v.requires_grad}
+    lr_g, b_g = O.lazy_adam_hparams(0.002, 4)
+    lr_d, b_d = O.lazy_adam_hparams(0.002, 16)
+    g_opt = torch.optim.Adam(list(gp.values()), lr=lr_g, betas=b_g)
+    d_opt = torch.optim.Adam(list(dp.values()), lr=lr_d, betas=b_d)
+    accum = 0.5 ** (batch / 10000)
+    mean_pl = torch.zeros((), dtype=F64)
+    for i in iters:
+        z_d, z_g, z_pl = zs[i]
+        with torch.no_grad():
+            fake = O.generator_forward(sd_g, [z_d], SIZE, noise=noise)
+        d_loss = O.d_logistic_loss(O.discriminator_forward(sd_d, real, SIZE), O.discriminator_forward(sd_d, fake, SIZE)) / batch
+        d_opt.zero_grad(set_to_none=True)
+        d_loss.backward(inputs=list(dp.values()))
+        d_opt.step()
+        if i % 16 == 0:
+            x = real.clone().requires_grad_(True)
+            pred = O.discriminator_forward(sd_d, x, SIZE)
+            r1 = O.d_r1_loss(pred, x)
+            d_opt.zero_grad(set_to_none=True)
+            (1.0 / 2 * r1 * 16 + 0 * pred[0]).sum().backward(inputs=list(dp.values()))
+            dp['final_linear.1.bias'].grad = None                       # set_grad_none, gt.py:708
+            d_opt.step()
+        fake = O.generator_forward(sd_g, [z_g], SIZE, noise=noise)
+        g_loss = O.g_nonsaturating_loss(O.discriminator_forward(sd_d, fake, SIZE))
+        g_opt.zero_grad(set_to_none=True)
+        g_loss.backward(inputs=list(gp.values()))
+        g_opt.step()
+        if i % 4 == 0:
+            pb = max(1, batch // 2)
+            fake, lat = O.generator_forward(sd_g, [z_pl], SIZE, noise=[n[:pb] for n in noise], return_latents=True)
+            pen, mean_pl, _ = O.g_path_regularize(fake, lat, mean_pl, pl_noise=pl_noise)
+            g_opt.zero_grad(set_to_none=True)
+            (2.0 * 4 * pen + 0 * fake[0, 0, 0, 0]).backward(inputs=list(gp.values()))
+            for k in gp:
+                if k.startswith('to_rgb') and k.endswith('.bias') and 'modulation' not in k:
+                    gp[k].grad = None                                   # set_grad_none, gt.py:594
+            g_opt.step()
+        O.ema_accumulate(ema, sd_g, accum)
+    return sd_g, sd_d, ema
+
+
+def product_run(batch, real, zs, pl_noise, iters, world=1, rank=0):
+    g, g_ema, d = build(batch * world)
+    if world > 1:   # replica r owns samples r::world of the global batch (strided like minibatch-stddev groups)
+        g.fixed_noise = [n[rank::world] for n in g.fixed_noise]
+        real = real[rank::world]
+    step = GanTrainStep(g, d, g_ema, batch=batch, latent_size=SDIM, world_size=world, bucket_mb=1)
+    for i in iters:
+        z_d, z_g, z_pl = [z[rank::world] if world > 1 else z for z in zs[i]]
+        step.discriminator_step(real, [z_d])
+        if i % 16 == 0:
+            step.discriminator_regularize_step(real)
+        do_reg = i % 4 == 0
+        step.generator_step([z_g], ema=not do_reg)
+        if do_reg:
+            pn = pl_noise[rank::world] if world > 1 else pl_noise
+            step.generator_regularize_step([z_pl], pl_noise=pn)
+            step.ema_arena.data.mul_(step.accum).add_(step.g_arena.data, alpha=1 - step.accum)
+        step.g_arena.check_views()
+        step.d_arena.check_views()
+    return g, d, g_ema
+
+
+def make_inputs(batch):
+    real = rnd(70, batch, 3, SIZE, SIZE).clamp_(-1, 1)
+    zs = {i: (rnd(80 + i, batch, SDIM), rnd(90 + i, batch, SDIM), rnd(100 + i, max(1, batch // 2), SDIM)) for i in range(0, 3)}
+    pl_noise = rnd(110, max(1, batch // 2), 3, SIZE, SIZE)
+    return real, zs, pl_noise
+
+
+def compare(module, sd_ref, tol):
+    worst = 0.0
+    for k, p in module.named_parameters():
+        ref = sd_ref[k].detach()
+        err = float((p.detach() - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+        worst = max(worst, err)
+        assert err < tol, (k, err)
+    return worst
+
+
+def test_single_replica_matches_reference_step(cpu_kernels):
+    batch = 4
+    real, zs, pl_noise = make_inputs(batch)
+    iters = [0, 1]          # iteration 0 runs both regularisers, 1 is a plain step
+    sd_g, sd_d, ema = oracle_run(batch, real, zs, pl_noise, iters)
+    g, d, g_ema = product_run(batch, real, zs, pl_noise, iters)
+    compare(g, sd_g, 1e-7)
+    compare(d, sd_d, 1e-7)
+    compare(g_ema, ema, 1e-7)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from gan_control_b200 import kernels
+    from oracle import kernels_ref
+    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
+                 'gemm_f32', 'adam_ema', 'launch_count']:
+        setattr(kernels, name, getattr(kernels_ref, name))
+    real, zs, pl_noise = make_inputs(4 * world)
+    g, d, g_ema = product_run(4, real, zs, pl_noise, [0, 1], world=world, rank=rank)
+    if rank == 0:
+        torch.save({'g': g.state_dict(), 'd': d.state_dict(), 'ema': g_ema.state_dict()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_replicas_match_one(cpu_kernels, tmp_path):
+    """world_size 2 over gloo: gradient all-reduce out of the flat arenas (+ the path-length mean
+    exchange) reproduces the single-replica run on the same global batch of 8."""
+    world, batch = 2, 4
+    out = str(tmp_path / 'ddp.pt')
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    ddp = torch.load(out)
+    real, zs, pl_noise = make_inputs(batch * world)
+    # single replica on the global batch, samples ordered so that the strided minibatch-stddev groups
+    # (gm.py:1005-1011) coincide with the replicas' local groups
+    g, d, g_ema = product_run(batch * world, real, zs, pl_noise, [0, 1])
+    compare(g, ddp['g'], 1e-5)
+    compare(d, ddp['d'], 1e-5)
+    compare(g_ema, ddp['ema'], 1e-5)
