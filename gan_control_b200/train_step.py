@@ -51,12 +51,19 @@ def g_path_regularize(fake_img, latents, mean_path_length, decay=0.01, pl_noise=
     pl_noise = pl_noise / math.sqrt(fake_img.shape[2] * fake_img.shape[3])
     grad, = torch.autograd.grad(outputs=(fake_img * pl_noise).sum(), inputs=latents, create_graph=True)
     path_lengths = torch.sqrt(grad.pow(2).sum(2).mean(1))
-    batch_mean = path_lengths.mean()
-    if all_reduce_mean is not None:
-        # the reference averages over the gathered full batch (gt.py:579,621-622)
-        batch_mean = batch_mean + (all_reduce_mean(batch_mean.detach()) - batch_mean.detach())
-    path_mean = mean_path_length + decay * (batch_mean - mean_path_length)
-    path_penalty = (path_lengths - path_mean).pow(2).mean()
+    local_mean = path_lengths.mean()
+    if all_reduce_mean is None:
+        path_mean = mean_path_length + decay * (local_mean - mean_path_length)
+        path_penalty = (path_lengths - path_mean).pow(2).mean()
+    else:
+        # The reference computes the running mean AND the penalty on the gathered full batch
+        # (gt.py:579,621-623); path_mean stays attached to the graph there, so every sample's length
+        # also receives d(penalty)/d(path_mean) * decay / B.  With the batch sharded over replicas
+        # that cross-sample term is restored exactly from the all-reduced mean:
+        global_mean = all_reduce_mean(local_mean.detach())
+        path_mean = mean_path_length + decay * (global_mean - mean_path_length)          # a constant here
+        dpen_dmean = -2.0 * (global_mean - path_mean)
+        path_penalty = (path_lengths - path_mean).pow(2).mean() + dpen_dmean * decay * (local_mean - local_mean.detach())
     return path_penalty, path_mean.detach(), path_lengths
 
 

@@ -173,6 +173,6 @@ def test_two_replicas_match_one(cpu_kernels, tmp_path):
     # single replica on the global batch, samples ordered so that the strided minibatch-stddev groups
     # (gm.py:1005-1011) coincide with the replicas' local groups
     g, d, g_ema = product_run(batch * world, real, zs, pl_noise, [0, 1])
-    compare(g, ddp['g'], 1e-5)
-    compare(d, ddp['d'], 1e-5)
-    compare(g_ema, ddp['ema'], 1e-5)
+    compare(g, ddp['g'], 1e-9)
+    compare(d, ddp['d'], 1e-9)
+    compare(g_ema, ddp['ema'], 1e-9)
