@@ -1,5 +1,17 @@
 // extern "C" entry points of the convolution family; picks the engine per call.
+#include <atomic>
+
 #include "conv.cuh"
+
+namespace b200gan {
+// 0 = automatic (tcgen05 when the shape is eligible), 1 = CUDA-core engine only (testing / A-B timing)
+static std::atomic<int> g_conv_engine{0};
+}  // namespace b200gan
+
+extern "C" int b200gan_set_conv_engine(int engine) {
+    int prev = b200gan::g_conv_engine.exchange(engine);
+    return prev;
+}
 
 
 extern "C" int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype, int b, int in_h, int in_w, int ic,
@@ -8,6 +20,8 @@ extern "C" int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype
                                 const float* noise_w, float slope, float gain, void* stream) {
     using namespace b200gan;
     ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    if (g_conv_engine.load() == 0 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
+        return conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
     return conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,406 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+// One persistent, warp-specialised kernel serves every dense convolution on the StyleGAN2 path
+// (include/b200gan.h "convolution family"):
+//     up=1, down=1 : stride-1 3x3 / 1x1        (ModulatedConv2d plain, EqualConv2d, all s1 dgrads)
+//     up=1, down=2 : stride-2 conv              (D downsampling convs; dgrad of the G up-conv)
+//     up=2, down=1 : transposed stride-2 conv   (G up-conv gm.py:304; dgrad of the D s2 convs),
+//                    decomposed into its 4 output phases, each a small stride-1 conv on the
+//                    input grid -- no zero-insertion, no wasted MMA work.
+// GEMM view per tile:  D[128 pixels][BN out-channels] += A[128 pixels][KC in-ch] * B[BN][KC]^T
+// for every (tap, channel chunk).  A tiles are fetched straight from the NHWC activation by a 4-D
+// TMA box {KC, TW, TH, TN} whose start coordinate carries the tap offset (out-of-bounds = zero
+// padding for free; element strides give the stride-2 gather); B tiles come from the K-major
+// weight tensor [wb][tap][OC][IC] (per-sample weights when wb = batch).  Accumulators live in
+// TMEM, double-buffered, so the epilogue of tile i (demod scale, noise, bias, leaky-ReLU, bf16
+// store) overlaps the MMAs of tile i+1.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (thread t <-> TMEM lane t <-> pixel t of the tile).
+#include <cstring>
+
+#include "conv.cuh"
+#include "umma.cuh"
+
+namespace b200gan {
+
+using namespace umma;
+
+constexpr int kMaxTaps = 9;
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+
+struct FwdPhase {
+    int ntaps;
+    int dy[kMaxTaps], dx[kMaxTaps], wtap[kMaxTaps];
+    int py, px;        // output offset of the phase
+    int ph, pw;        // phase-grid extent
+    int tiles_h, tiles_w, tiles_n;
+    int tile_begin;
+};
+
+struct FwdParams {
+    int B, OH, OW, OC, IC;
+    int n_phases;
+    FwdPhase phase[4];
+    int TW, TH, TN, rows;
+    int es, os;
+    int BN, n_oc_tiles;
+    int kchunks, kc, row_bytes, layout;
+    int taps_total, w_per_sample;
+    int total_tiles;
+    int stages, a_stage_bytes, b_stage_bytes, tx_bytes;
+    int tmem_cols;
+    const float* bias;
+    const float* rowscale;
+    const __nv_bfloat16* noise;
+    const float* noise_w;
+    float slope, gain;
+    int has_ep;
+    __nv_bfloat16* y;
+};
+
+struct TileCoord {
+    int phase, n0, h0, w0, ocb;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const FwdParams& p, int tile) {
+    TileCoord t;
+    int ph = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < p.n_phases && tile >= p.phase[i].tile_begin) ph = i;
+    const FwdPhase& P = p.phase[ph];
+    int r = tile - P.tile_begin;
+    t.phase = ph;
+    t.ocb = r % p.n_oc_tiles;
+    r /= p.n_oc_tiles;
+    t.w0 = (r % P.tiles_w) * p.TW;
+    r /= P.tiles_w;
+    t.h0 = (r % P.tiles_h) * p.TH;
+    t.n0 = (r / P.tiles_h) * p.TN;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* a_buf = smem;
+    uint8_t* b_buf = a_buf + p.stages * p.a_stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(b_buf + p.stages * p.b_stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x);
+        prefetch_tensormap(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull + a, 1);
+            mbar_init(tempty + a, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0, par = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const FwdPhase& P = p.phase[t.phase];
+                const int wz0 = (p.w_per_sample ? t.n0 : 0) * p.taps_total;
+                for (int tp = 0; tp < P.ntaps; ++tp) {
+                    const int cx = t.w0 * p.es + P.dx[tp], cy = t.h0 * p.es + P.dy[tp];
+                    for (int c = 0; c < p.kchunks; ++c) {
+                        mbar_wait(empty + stage, par ^ 1);
+                        mbar_arrive_expect_tx(full + stage, (uint32_t)p.tx_bytes);
+                        tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, full + stage, c * p.kc, cx, cy, t.n0);
+                        tma_load_3d(b_buf + stage * p.b_stage_bytes, &map_w, full + stage, c * p.kc, t.ocb * p.BN, wz0 + P.wtap[tp]);
+                        if (++stage == p.stages) { stage = 0; par ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16(kTileM, p.BN, 0, 0);
+            const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
+            const int kk = p.kc / 16;
+            int stage = 0, par = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const TileCoord t = decode_tile(p, tile);
+                const FwdPhase& P = p.phase[t.phase];
+                const int acc = it & 1, acc_par = (it >> 1) & 1;
+                mbar_wait(tempty + acc, acc_par ^ 1);
+                tc_fence_after();
+                const int ksteps = P.ntaps * p.kchunks;
+                if (ksteps == 0) {           // phase without taps: the epilogue writes zeros
+                    mbar_arrive(tfull + acc);
+                    continue;
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(full + stage, par);
+                    tc_fence_after();
+                    const uint64_t a_desc = smem_desc(smem_u32(a_buf + stage * p.a_stage_bytes), 16, sbo, (uint32_t)p.layout);
+                    const uint64_t b_desc = smem_desc(smem_u32(b_buf + stage * p.b_stage_bytes), 16, sbo, (uint32_t)p.layout);
+                    for (int k = 0; k < kk; ++k)   // +32 B per K=16 step inside the swizzled row
+                        mma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((ks | k) != 0));
+                    mma_commit(empty + stage);
+                    if (++stage == p.stages) { stage = 0; par ^= 1; }
+                }
+                mma_commit(tfull + acc);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int q = warp - 4;
+        const int r = q * 32 + lane;
+        const int w_l = r % p.TW, h_l = (r / p.TW) % p.TH, n_l = r / (p.TW * p.TH);
+        const float nw = (p.noise != nullptr && p.noise_w != nullptr) ? *p.noise_w : 0.f;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile(p, tile);
+            const FwdPhase& P = p.phase[t.phase];
+            const int acc = it & 1, acc_par = (it >> 1) & 1;
+            mbar_wait(tfull + acc, acc_par);
+            tc_fence_after();
+            const int n = t.n0 + n_l, j = t.h0 + h_l, i = t.w0 + w_l;
+            const int oy = j * p.os + P.py, ox = i * p.os + P.px;
+            const bool valid = r < p.rows && n < p.B && j < P.ph && i < P.pw && oy < p.OH && ox < p.OW;
+            const bool zero_tile = P.ntaps == 0;
+            const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
+            __nv_bfloat16* dst = p.y + pix * p.OC + t.ocb * p.BN;
+            const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
+            const float* rs = p.rowscale ? p.rowscale + (int64_t)(valid ? n : 0) * p.OC + t.ocb * p.BN : nullptr;
+            const float* bs = p.bias ? p.bias + t.ocb * p.BN : nullptr;
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float v[16];
+                if (!zero_tile) {
+                    tmem_ld_x16(taddr + (uint32_t)c0, v);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                }
+                if (valid) {
+                    if (p.has_ep) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float u = v[e];
+                            if (rs) u *= rs[c0 + e];
+                            u += nz + (bs ? bs[c0 + e] : 0.f);
+                            v[e] = p.gain * (u > 0.f ? u : u * p.slope);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+                    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return B200GAN_ENOSUP;
+    }
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                     (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box,
+                     (const cuuint32_t*)elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return B200GAN_EINVAL;
+    }
+    return 0;
+}
+
+static int floordiv_h(int a, int b) {
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+static int next_pow2(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Does the tcgen05 engine take this convolution?  (Everything else goes to conv_simt.cu.)
+bool conv_fwd_umma_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
+    if (dtype != B200GAN_BF16) return false;
+    if (g.kh * g.kw > kMaxTaps) return false;
+    if (!((g.up == 1 && (g.down == 1 || g.down == 2)) || (g.up == 2 && g.down == 1))) return false;
+    if (g.ic < 32 || g.ic % 8 != 0) return false;
+    if (g.ic < 64 && g.ic != 32) return false;
+    if (g.oc < 16 || g.oc % 16 != 0) return false;
+    if (g.oc > 256 && g.oc % 128 != 0) return false;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) % 16 != 0) return false;
+    if ((int64_t)g.b * g.out_h * g.out_w < 64) return false;          // too small to be worth a launch of this shape
+    return tensor_map_encoder() != nullptr;
+}
+
+int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias,
+                  const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
+                  cudaStream_t st) {
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = g.b; p.OH = g.out_h; p.OW = g.out_w; p.OC = g.oc; p.IC = g.ic;
+    p.es = g.down; p.os = g.up;
+    p.taps_total = g.kh * g.kw;
+    p.w_per_sample = g.w_per_sample;
+    // ---- phases ----
+    int max_ph = 0, max_pw = 0;
+    if (g.up == 1) {
+        p.n_phases = 1;
+        FwdPhase& P = p.phase[0];
+        for (int ky = 0; ky < g.kh; ++ky)
+            for (int kx = 0; kx < g.kw; ++kx) {
+                P.dy[P.ntaps] = ky - g.pad0;
+                P.dx[P.ntaps] = kx - g.pad0;
+                P.wtap[P.ntaps++] = ky * g.kw + kx;
+            }
+        P.ph = g.out_h; P.pw = g.out_w;
+        max_ph = P.ph; max_pw = P.pw;
+    } else {
+        p.n_phases = 0;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                FwdPhase& P = p.phase[p.n_phases];
+                P.py = py; P.px = px;
+                P.ph = (g.out_h - py + 1) / 2;
+                P.pw = (g.out_w - px + 1) / 2;
+                if (P.ph <= 0 || P.pw <= 0) continue;
+                for (int ky = 0; ky < g.kh; ++ky) {
+                    if (((py + ky - g.pad0) % 2 + 2) % 2 != 0) continue;
+                    for (int kx = 0; kx < g.kw; ++kx) {
+                        if (((px + kx - g.pad0) % 2 + 2) % 2 != 0) continue;
+                        P.dy[P.ntaps] = floordiv_h(py + ky - g.pad0, 2);
+                        P.dx[P.ntaps] = floordiv_h(px + kx - g.pad0, 2);
+                        P.wtap[P.ntaps++] = ky * g.kw + kx;
+                    }
+                }
+                max_ph = P.ph > max_ph ? P.ph : max_ph;
+                max_pw = P.pw > max_pw ? P.pw : max_pw;
+                ++p.n_phases;
+            }
+    }
+    // ---- tile geometry ----
+    p.TW = max_pw < 16 ? max_pw : 16;
+    p.TH = max_ph < kTileM / p.TW ? max_ph : kTileM / p.TW;
+    p.TN = g.w_per_sample ? 1 : kTileM / (p.TW * p.TH);
+    if (p.TN < 1) p.TN = 1;
+    if (p.TN > g.b) p.TN = g.b;
+    p.rows = p.TW * p.TH * p.TN;
+    p.BN = g.oc <= 256 ? g.oc : (g.oc % 256 == 0 ? 256 : 128);
+    p.n_oc_tiles = g.oc / p.BN;
+    p.row_bytes = g.ic >= 64 ? 128 : 64;
+    p.layout = p.row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+    p.kc = p.row_bytes / 2;
+    p.kchunks = (g.ic + p.kc - 1) / p.kc;
+    int tiles = 0;
+    for (int i = 0; i < p.n_phases; ++i) {
+        FwdPhase& P = p.phase[i];
+        P.tiles_h = (P.ph + p.TH - 1) / p.TH;
+        P.tiles_w = (P.pw + p.TW - 1) / p.TW;
+        P.tiles_n = (g.b + p.TN - 1) / p.TN;
+        P.tile_begin = tiles;
+        tiles += P.tiles_h * P.tiles_w * P.tiles_n * p.n_oc_tiles;
+    }
+    p.total_tiles = tiles;
+    p.a_stage_bytes = kTileM * p.row_bytes;
+    p.b_stage_bytes = p.BN * p.row_bytes;
+    p.tx_bytes = p.rows * p.row_bytes + p.BN * p.row_bytes;
+    const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) p.stages = 2;
+    p.tmem_cols = next_pow2(2 * p.BN);
+    p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
+    p.slope = slope; p.gain = gain;
+    p.has_ep = (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0;
+    p.y = (__nv_bfloat16*)y;
+
+    // ---- tensor maps ----
+    CUtensorMap map_x, map_w;
+    {
+        uint64_t dims[4] = {(uint64_t)g.ic, (uint64_t)g.in_w, (uint64_t)g.in_h, (uint64_t)g.b};
+        uint64_t strides[3] = {(uint64_t)g.ic * 2, (uint64_t)g.in_w * g.ic * 2, (uint64_t)g.in_h * g.in_w * g.ic * 2};
+        uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.TW * p.es), (uint32_t)(p.TH * p.es), (uint32_t)p.TN};
+        uint32_t es[4] = {1, (uint32_t)p.es, (uint32_t)p.es, 1};
+        if (int e = encode_bf16_map(&map_x, x, 4, dims, strides, box, es, p.row_bytes)) return e;
+    }
+    {
+        const int wb = g.w_per_sample ? g.b : 1;
+        uint64_t dims[3] = {(uint64_t)g.ic, (uint64_t)g.oc, (uint64_t)wb * p.taps_total};
+        uint64_t strides[2] = {(uint64_t)g.ic * 2, (uint64_t)g.oc * g.ic * 2};
+        uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.BN, 1};
+        uint32_t es[3] = {1, 1, 1};
+        if (int e = encode_bf16_map(&map_w, w, 3, dims, strides, box, es, p.row_bytes)) return e;
+    }
+    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16;
+    cudaFuncSetAttribute(conv_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    conv_fwd_umma_kernel<<<grid, kThreads, smem, st>>>(map_x, map_w, p);
+    count_launch();
+    return check_launch("conv_fwd_umma");
+}
+
+}  // namespace b200gan

@@ -35,6 +35,7 @@ _SIGNATURES = {
     'b200gan_bias_act_bwd': ([_vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
     'b200gan_reduce_nhwc': ([_vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
     'b200gan_conv_fwd': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
+    'b200gan_set_conv_engine': ([_i], _i),
     'b200gan_conv_wgrad': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
     'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
     'b200gan_gemm_f32': ([_vp, _vp, _vp] + [_i] * 8 + [_f, _f, _vp], _i),
@@ -61,6 +62,11 @@ def lib():
 
 def exported_symbols():
     return sorted(_SIGNATURES)
+
+
+def set_conv_engine(engine):
+    """0 = auto (tcgen05 when eligible), 1 = CUDA-core engine only. Returns the previous setting."""
+    return int(lib().b200gan_set_conv_engine(int(engine)))
 
 
 def launch_count():

@@ -148,3 +148,45 @@ def test_adam_ema():
         pt.grad = g.cuda()
         opt.step()
     assert float((pt.detach() - dev[0]).abs().max()) < 1e-5
+
+
+# ---- tcgen05 implicit-GEMM engine ----------------------------------------------------------------
+UMMA_CASES = [
+    # b, h, w, ic, oc, k, up, down, pad0, per_sample
+    (2, 16, 16, 64, 64, 3, 1, 1, 1, False), (4, 8, 8, 128, 128, 3, 1, 1, 1, False), (16, 4, 4, 512, 512, 3, 1, 1, 1, False),
+    (2, 32, 32, 32, 32, 3, 1, 1, 1, False), (2, 64, 64, 64, 32, 3, 1, 1, 1, False), (3, 16, 16, 64, 64, 3, 1, 1, 1, True),
+    (2, 32, 32, 32, 32, 3, 1, 1, 1, True), (2, 16, 16, 64, 64, 1, 1, 1, 0, False), (2, 16, 16, 96, 48, 3, 1, 1, 1, False),
+    (4, 8, 8, 512, 512, 3, 1, 1, 1, False), (2, 8, 8, 64, 64, 3, 2, 1, 2, False), (2, 8, 8, 64, 64, 3, 2, 1, 2, True),
+    (2, 4, 4, 128, 64, 3, 2, 1, 2, False), (2, 17, 17, 64, 128, 3, 1, 2, 0, False), (2, 33, 33, 32, 64, 3, 1, 2, 0, False),
+    (2, 15, 15, 64, 128, 1, 1, 2, 0, False), (2, 8, 8, 128, 64, 1, 2, 1, 0, False), (5, 16, 16, 64, 256, 3, 1, 1, 1, False),
+    (1, 128, 128, 64, 64, 3, 1, 1, 1, False), (2, 64, 64, 32, 32, 3, 2, 1, 2, True), (2, 129, 129, 32, 32, 3, 1, 2, 0, True),
+]
+
+
+@pytest.mark.parametrize('case', UMMA_CASES)
+def test_conv_fwd_umma(case):
+    """the tcgen05 engine against the fp64 contract stand-in, and against the CUDA-core engine"""
+    b, h, w, ic, oc, k, up, down, pad0, ps = case
+    dt = torch.bfloat16
+    if up == 2:
+        oh, ow = (h - 1) * 2 + k - 2 * (k - 1 - pad0), (w - 1) * 2 + k - 2 * (k - 1 - pad0)
+    else:
+        oh, ow = conv_out_hw(h, w, k, up, down, pad0)
+    x, xr = prep(rnd(41, b, h, w, ic), dt)
+    wt, wr = prep(rnd(42, b if ps else 1, k, k, oc, ic) / (ic * k * k) ** 0.5, dt)
+    bias, rs, nw = rnd(43, oc).float(), (rnd(44, b, oc).abs() + 0.5).float(), torch.tensor([0.3])
+    noise, noiser = prep(rnd(45, b, oh, ow), dt)
+    ref = R.conv_fwd(xr, wr, oh, ow, up, down, pad0)
+    ref_ep = R.conv_fwd(xr, wr, oh, ow, up, down, pad0, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5)
+    n0 = K.launch_count()
+    y = K.conv_fwd(x, wt, oh, ow, up, down, pad0)
+    y_ep = K.conv_fwd(x, wt, oh, ow, up, down, pad0, bias.cuda(), rs.cuda(), noise, nw.cuda(), 0.2, 2 ** 0.5)
+    torch.cuda.synchronize()
+    prev = K.set_conv_engine(1)
+    try:
+        y_simt = K.conv_fwd(x, wt, oh, ow, up, down, pad0)
+    finally:
+        K.set_conv_engine(prev)
+    close(y, ref, dt, 'umma fwd')
+    close(y_ep, ref_ep, dt, 'umma fwd+epilogue')
+    close(y, y_simt.cpu().double(), dt, 'umma vs simt')
