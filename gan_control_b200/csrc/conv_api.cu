@@ -30,5 +30,7 @@ extern "C" int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int 
                                   int w_per_sample, void* stream) {
     using namespace b200gan;
     ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    if (g_conv_engine.load() == 0 && b > 0 && conv_wgrad_umma_eligible(dtype, g, x, gy))
+        return conv_wgrad_umma(x, gy, gw, g, (cudaStream_t)stream);
     return conv_wgrad_simt(x, gy, gw, dtype, g, (cudaStream_t)stream);
 }

@@ -190,3 +190,35 @@ def test_conv_fwd_umma(case):
     close(y, ref, dt, 'umma fwd')
     close(y_ep, ref_ep, dt, 'umma fwd+epilogue')
     close(y, y_simt.cpu().double(), dt, 'umma vs simt')
+
+
+WGRAD_UMMA_CASES = UMMA_CASES[:8] + UMMA_CASES[9:] + [
+    (2, 16, 16, 256, 128, 3, 1, 1, 1, False), (2, 16, 16, 32, 128, 3, 1, 1, 1, False), (3, 32, 32, 64, 32, 3, 2, 1, 2, False),
+    (2, 65, 65, 64, 64, 3, 1, 2, 0, False), (16, 8, 8, 512, 512, 3, 1, 1, 1, False),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_UMMA_CASES)
+def test_conv_wgrad_umma(case):
+    b, h, w, ic, oc, k, up, down, pad0, ps = case
+    dt = torch.bfloat16
+    if up == 2:
+        oh, ow = (h - 1) * 2 + k - 2 * (k - 1 - pad0), (w - 1) * 2 + k - 2 * (k - 1 - pad0)
+    else:
+        oh, ow = conv_out_hw(h, w, k, up, down, pad0)
+    x, xr = prep(rnd(51, b, h, w, ic), dt)
+    gy, gyr = prep(rnd(52, b, oh, ow, oc), dt)
+    gw = K.conv_wgrad(x, gy, k, k, up, down, pad0, ps)
+    torch.cuda.synchronize()
+    prev = K.set_conv_engine(1)
+    try:
+        gw_simt = K.conv_wgrad(x, gy, k, k, up, down, pad0, ps)
+    finally:
+        K.set_conv_engine(prev)
+    scale = float(gw_simt.abs().max())
+    err_simt = float((gw - gw_simt).abs().max()) / scale
+    assert err_simt < 2e-4, f'umma vs simt wgrad rel err {err_simt:.2e}'
+    if b * oh * ow * ic * oc <= 2 ** 27:
+        gwr = R.conv_wgrad(xr, gyr, k, k, up, down, pad0, ps)
+        err = float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max())
+        assert err < 2e-4, f'wgrad rel err {err:.2e}'
