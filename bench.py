@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--cpu-sample-size', type=int, default=None, help='resolution of the CPU-baseline sample')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-roofline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     return ap.parse_args()
 
 
@@ -205,16 +206,18 @@ def run_b200(args):
     def timed(n_steps, e2e, first_iter):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = K.launch_count()
+        n0 = K.launch_count() + getattr(step, 'replayed_launches', 0)
         e0.record()
         sink = 0.0
         for it in range(n_steps):
             i = first_iter + it
-            if e2e:
+            if e2e and not use_graph:
                 real = host_real.to(dev, non_blocking=True)      # this step's inputs from pinned host memory
+            elif e2e:
+                real = host_real                                 # copied H2D into the graph's static buffer
             else:
                 real = dev_real
-            d_loss, g_loss = step.train_step(i, real, regularize=reg)
+            d_loss, g_loss = run_step(i, real, regularize=reg)
             if e2e:
                 sink += float(torch.stack([d_loss.float(), g_loss.float()]).cpu().sum())   # D2H read of the step's result
         e1.record()
@@ -224,11 +227,15 @@ def run_b200(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms / n_steps, K.launch_count() - n0
+        return ms / n_steps, K.launch_count() + getattr(step, 'replayed_launches', 0) - n0
 
+    use_graph = not args.no_graph
+    if use_graph:
+        step.capture(tuple(dev_real.shape))      # runs every step variant twice on a side stream, then captures
+    run_step = step.train_step_graphed if use_graph else step.train_step
     # warm-up (also runs one of each regulariser so every kernel / allocation exists)
     for it in range(args.warmup):
-        step.train_step(it * 4, dev_real, regularize=reg and it == 0)
+        run_step(it * 4, dev_real, regularize=reg and it == 0)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -252,7 +259,7 @@ def run_b200(args):
         'config': {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]): Generator({size})+Discriminator({size}) '
                                f'channel_multiplier 2, random init, lazy regularisers at real cadence '
                                f'(R1 /16, path-length /4)' + ('' if reg else ' DISABLED'),
-                   'global_batch': global_batch, 'per_gpu_batch': batch, 'parallelism': f'dp{world}',
+                   'global_batch': global_batch, 'per_gpu_batch': batch, 'parallelism': f'dp{world}', 'cuda_graphs': use_graph,
                    'l2': 'inputs larger than L2 (each step streams >10 GB of activations; no explicit flush)'},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,

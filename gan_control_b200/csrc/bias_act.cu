@@ -117,7 +117,85 @@ __global__ void __launch_bounds__(256) reduce_nhwc_kernel(const T* __restrict__ 
     }
 }
 
+// ---- fused backward of the StyledConv / ConvLayer epilogue -----------------------------------------
+// forward was  y = gain*lrelu(z*d[n][c] + nw*noise[n][p] + bias[c]).  One pass over (gy, y) produces
+//   gconv = gy * gain * act'(y) * d          (the gradient entering the convolution's backward)
+//   gb[c]    += gz                            gz = gy * gain * act'(y)
+//   gd[n][c] += gz * z = gz * (u - nw*noise - bias) / d,   u = pre-activation recovered from y
+//   gnw      += gz * noise
+// so the convolution output z never has to be stored (SURVEY.md hard part H4).
+template <typename T>
+__global__ void __launch_bounds__(256) epilogue_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y,
+                                                           T* __restrict__ gconv, const float* __restrict__ rowscale,
+                                                           const T* __restrict__ noise, const float* __restrict__ noise_w,
+                                                           const float* __restrict__ bias, float* __restrict__ gd,
+                                                           float* __restrict__ gb, float* __restrict__ gnw, int64_t hw,
+                                                           int64_t c, int64_t pix_per_block, float slope, float gain) {
+    constexpr int CT = 32, RT = 8;
+    __shared__ float red_b[RT][CT + 1], red_d[RT][CT + 1], red_n[RT][CT + 1];
+    const int tx = threadIdx.x % CT, ty = threadIdx.x / CT;
+    const int64_t sample = blockIdx.z;
+    const int64_t p0 = blockIdx.y * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+    const float nw = (noise && noise_w) ? *noise_w : 0.f;
+    const float inv_gain = 1.f / gain, inv_gs = 1.f / (gain * slope);
+    for (int64_t cb = blockIdx.x * CT; cb < c; cb += (int64_t)gridDim.x * CT) {
+        const int64_t ch = cb + tx;
+        float sb = 0.f, sd = 0.f, sn = 0.f;
+        if (ch < c) {
+            const float d = rowscale ? rowscale[sample * c + ch] : 1.f;
+            const float bv = bias ? bias[ch] : 0.f;
+            const float inv_d = 1.f / d;
+            for (int64_t p = p0 + ty; p < p1; p += RT) {
+                const int64_t e = (sample * hw + p) * c + ch;
+                const float yv = io<T>::ld(y + e);
+                const float gz = io<T>::ld(gy + e) * gain * (yv > 0.f ? 1.f : slope);
+                io<T>::st(gconv + e, gz * d);
+                const float nz = noise ? io<T>::ld(noise + sample * hw + p) : 0.f;
+                const float u = yv > 0.f ? yv * inv_gain : yv * inv_gs;
+                sb += gz;
+                sd += gz * (u - nw * nz - bv) * inv_d;
+                sn += gz * nz;
+            }
+        }
+        red_b[ty][tx] = sb; red_d[ty][tx] = sd; red_n[ty][tx] = sn;
+        __syncthreads();
+        if (ty == 0 && ch < c) {
+            float tb = 0.f, td = 0.f, tn = 0.f;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) { tb += red_b[r][tx]; td += red_d[r][tx]; tn += red_n[r][tx]; }
+            if (gb) atomicAdd(gb + ch, tb);
+            if (gd) atomicAdd(gd + sample * c + ch, td);
+            if (gnw && noise) atomicAdd(gnw, tn);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace b200gan
+
+extern "C" int b200gan_epilogue_bwd(const void* gy, const void* y, void* gconv, const float* rowscale, const void* noise,
+                                    const float* noise_w, const float* bias, float* gd, float* gb, float* gnw, int dtype,
+                                    int64_t n, int64_t hw, int64_t c, float slope, float gain, void* stream) {
+    using namespace b200gan;
+    B200_REQUIRE(n >= 0 && hw >= 1 && c >= 1, "epilogue_bwd: bad shape");
+    if (n == 0) return 0;
+    return B200_DISPATCH(dtype, [&] {
+        int64_t cblocks = cdiv(c, 32);
+        if (cblocks > 64) cblocks = 64;
+        int64_t want = cdiv((int64_t)sm_count() * 8, cblocks * n);
+        int64_t slabs = want < 1 ? 1 : want;
+        int64_t ppb = cdiv(hw, slabs);
+        if (ppb < 64) ppb = 64;
+        slabs = cdiv(hw, ppb);
+        B200_REQUIRE(n <= 65535 && slabs <= 65535, "epilogue_bwd: grid too large");
+        dim3 grid((unsigned)cblocks, (unsigned)slabs, (unsigned)n);
+        epilogue_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)gy, (const T*)y, (T*)gconv, rowscale,
+                                                                       (const T*)noise, noise_w, bias, gd, gb, gnw, hw, c,
+                                                                       ppb, slope, gain);
+        count_launch();
+        return check_launch("epilogue_bwd");
+    });
+}
 
 extern "C" int b200gan_bias_act_fwd(const void* x, void* y, const float* bias, const float* rowscale,
                                     const void* noise, const float* noise_w, int dtype, int64_t n,

@@ -13,6 +13,13 @@ struct ConvGeom {
 int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
                   const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
                   cudaStream_t st);
+// streaming 1x1 kernels for a <= 4-channel side (conv_pointwise.cu)
+bool conv_fwd_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y);
+int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
+                       const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
+                       cudaStream_t st);
+bool conv_wgrad_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy);
+int conv_wgrad_pointwise(const void* x, const void* gy, float* gw, int dtype, const ConvGeom& g, cudaStream_t st);
 // tcgen05 engine (conv_umma.cu)
 bool conv_fwd_umma_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y);
 int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias, const float* rowscale,

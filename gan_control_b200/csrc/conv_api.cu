@@ -20,6 +20,8 @@ extern "C" int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype
                                 const float* noise_w, float slope, float gain, void* stream) {
     using namespace b200gan;
     ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    if (g_conv_engine.load() == 0 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
+        return conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
     if (g_conv_engine.load() == 0 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
         return conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
     return conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
@@ -30,6 +32,8 @@ extern "C" int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int 
                                   int w_per_sample, void* stream) {
     using namespace b200gan;
     ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    if (g_conv_engine.load() == 0 && b > 0 && b <= 65535 && conv_wgrad_pointwise_eligible(dtype, g, x, gy))
+        return conv_wgrad_pointwise(x, gy, gw, dtype, g, (cudaStream_t)stream);
     if (g_conv_engine.load() == 0 && b > 0 && conv_wgrad_umma_eligible(dtype, g, x, gy))
         return conv_wgrad_umma(x, gy, gw, g, (cudaStream_t)stream);
     return conv_wgrad_simt(x, gy, gw, dtype, g, (cudaStream_t)stream);

@@ -1,0 +1,224 @@
+// 1x1 convolutions with a tiny channel count on one side: ToRGB (C -> 3, gan_model.py:421-426), its data
+// gradient (3 -> C), the discriminator's from_rgb ConvLayer (3 -> C, gm.py:943) and their weight
+// gradients.  These are pure streaming passes over a 1024^2 activation (AI ~ 3 FLOP/B, SURVEY.md
+// App. B): no tensor cores, no tiling -- one coalesced 16-byte-vector read of the wide tensor, the
+// narrow tensor and the (per-sample) weights ride in registers / shared memory.
+#include "conv.cuh"
+
+namespace b200gan {
+
+constexpr int kPwMaxSmall = 4;
+
+struct PwEpilogue {
+    const float* bias;
+    const float* rowscale;
+    const void* noise;
+    const float* noise_w;
+    float slope, gain;
+    int on;
+};
+
+template <typename T>
+__device__ __forceinline__ float pw_epilogue(const PwEpilogue& e, float v, int b, int oc_total, int o, int64_t pix, float nz) {
+    if (!e.on) return v;
+    if (e.rowscale) v *= e.rowscale[(int64_t)b * oc_total + o];
+    v += nz + (e.bias ? e.bias[o] : 0.f);
+    return e.gain * (v > 0.f ? v : v * e.slope);
+}
+
+// ---- OC <= 4:  y[p][o] = sum_c x[p][c] * w[wb][o][c] ------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pw_small_oc_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                          T* __restrict__ y, int npix, int ic, int oc,
+                                                          int per_sample, PwEpilogue ep) {
+    extern __shared__ float wsm[];                      // [oc][ic]
+    const int b = blockIdx.y;
+    const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
+    for (int i = threadIdx.x; i < oc * ic; i += blockDim.x) wsm[i] = io<T>::ld(wb + i);
+    __syncthreads();
+    const int nv = ic / VEC;
+    int L = 1;
+    while (L < 32 && L < nv) L <<= 1;                   // lanes cooperating on one pixel
+    const int lane = threadIdx.x & 31, sub = lane % L, pw_ = lane / L, ppw = 32 / L;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const float nw = (ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
+    for (int p0 = warp * ppw; p0 < npix; p0 += warps * ppw) {
+        const int p = p0 + pw_;
+        float acc[kPwMaxSmall] = {0.f, 0.f, 0.f, 0.f};
+        if (p < npix) {
+            const T* xp = x + ((int64_t)b * npix + p) * ic;
+            for (int v = sub; v < nv; v += L) {
+                const Pack<T, VEC> xv = *reinterpret_cast<const Pack<T, VEC>*>(xp + v * VEC);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float xf = io<T>::ld(&xv.v[j]);
+#pragma unroll
+                    for (int o = 0; o < kPwMaxSmall; ++o)
+                        if (o < oc) acc[o] = fmaf(xf, wsm[o * ic + v * VEC + j], acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kPwMaxSmall; ++o)
+            for (int off = L >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+        if (sub == 0 && p < npix) {
+            const int64_t pix = (int64_t)b * npix + p;
+            const float nz = ep.noise ? nw * io<T>::ld((const T*)ep.noise + pix) : 0.f;
+            for (int o = 0; o < oc; ++o) io<T>::st(y + pix * oc + o, pw_epilogue<T>(ep, acc[o], b, oc, o, pix, nz));
+        }
+    }
+}
+
+// ---- IC <= 4:  y[p][o..o+VEC) = sum_c x[p][c] * w[wb][o][c] -----------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pw_small_ic_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                          T* __restrict__ y, int npix, int ic, int oc,
+                                                          int per_sample, PwEpilogue ep) {
+    extern __shared__ float wsm[];                      // [oc][ic]
+    const int b = blockIdx.y;
+    const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
+    for (int i = threadIdx.x; i < oc * ic; i += blockDim.x) wsm[i] = io<T>::ld(wb + i);
+    __syncthreads();
+    const int nv = oc / VEC;
+    const float nw = (ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
+    const int64_t total = (int64_t)npix * nv;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nv);
+        const int p = (int)(idx / nv);
+        const int64_t pix = (int64_t)b * npix + p;
+        float xs[kPwMaxSmall];
+#pragma unroll
+        for (int c = 0; c < kPwMaxSmall; ++c) xs[c] = c < ic ? io<T>::ld(x + pix * ic + c) : 0.f;
+        const float nz = ep.noise ? nw * io<T>::ld((const T*)ep.noise + pix) : 0.f;
+        Pack<T, VEC> out;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int o = v * VEC + j;
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < kPwMaxSmall; ++c)
+                if (c < ic) a = fmaf(xs[c], wsm[o * ic + c], a);
+            io<T>::st(&out.v[j], pw_epilogue<T>(ep, a, b, oc, o, pix, nz));
+        }
+        *reinterpret_cast<Pack<T, VEC>*>(y + pix * oc + v * VEC) = out;
+    }
+}
+
+// ---- weight gradient with one narrow side:  gw[wb][o][c] += sum_p gy[p][o] * x[p][c] ----------------
+// `wide` has wc channels (vectorised), `narrow` has nc <= 4.  narrow_is_oc selects the output indexing.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wide, const T* __restrict__ narrow,
+                                                       float* __restrict__ gw, int npix, int wc, int nc,
+                                                       int narrow_is_oc, int per_sample, int pix_per_block) {
+    extern __shared__ float red[];                      // [nc][wc]
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < nc * wc; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int nv = wc / VEC;                            // vectors per pixel (<= 256)
+    const int v = threadIdx.x % nv, pl = threadIdx.x / nv, npl = blockDim.x / nv;
+    const int p_begin = blockIdx.x * pix_per_block, p_end = min(npix, p_begin + pix_per_block);
+    float acc[kPwMaxSmall][VEC];
+#pragma unroll
+    for (int s = 0; s < kPwMaxSmall; ++s)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[s][j] = 0.f;
+    if (pl < npl) {
+        for (int p = p_begin + pl; p < p_end; p += npl) {
+            const int64_t pix = (int64_t)b * npix + p;
+            const Pack<T, VEC> wv = *reinterpret_cast<const Pack<T, VEC>*>(wide + pix * wc + v * VEC);
+            float ns[kPwMaxSmall];
+#pragma unroll
+            for (int s = 0; s < kPwMaxSmall; ++s) ns[s] = s < nc ? io<T>::ld(narrow + pix * nc + s) : 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float wf = io<T>::ld(&wv.v[j]);
+#pragma unroll
+                for (int s = 0; s < kPwMaxSmall; ++s) acc[s][j] = fmaf(wf, ns[s], acc[s][j]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kPwMaxSmall; ++s)
+            if (s < nc)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) atomicAdd(&red[s * wc + v * VEC + j], acc[s][j]);
+    }
+    __syncthreads();
+    const int oc = narrow_is_oc ? nc : wc, ic = narrow_is_oc ? wc : nc;
+    float* dst = gw + (int64_t)(per_sample ? b : 0) * oc * ic;
+    for (int i = threadIdx.x; i < nc * wc; i += blockDim.x) {
+        const int s = i / wc, cw = i % wc;
+        const int o = narrow_is_oc ? s : cw, c = narrow_is_oc ? cw : s;
+        atomicAdd(dst + (int64_t)o * ic + c, red[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static bool pw_shape(const ConvGeom& g) {
+    return g.kh == 1 && g.kw == 1 && g.up == 1 && g.down == 1 && g.pad0 == 0 && g.out_h == g.in_h && g.out_w == g.in_w;
+}
+
+bool conv_fwd_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
+    if (!pw_shape(g)) return false;
+    const int vec = dtype == B200GAN_BF16 ? 8 : 4;
+    if ((int64_t)g.oc * g.ic * 4 > 40 * 1024) return false;      // weights are staged in (default-limit) shared memory
+    if (g.oc <= kPwMaxSmall && g.ic % vec == 0 && (uintptr_t)x % 16 == 0) return true;
+    if (g.ic <= kPwMaxSmall && g.oc % vec == 0 && (uintptr_t)y % 16 == 0) return true;
+    return false;
+}
+
+int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
+                       const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
+                       cudaStream_t st) {
+    PwEpilogue ep{bias, rowscale, noise, noise_w, slope, gain,
+                  (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0};
+    const int npix = g.out_h * g.out_w;
+    return B200_DISPATCH(dtype, [&] {
+        constexpr int V = 16 / sizeof(T);
+        const size_t smem = (size_t)g.oc * g.ic * sizeof(float);
+        int bx = (int)cdiv((int64_t)sm_count() * 8, g.b);
+        if (g.oc <= kPwMaxSmall) {
+            int need = (int)cdiv(npix, 64);
+            if (bx > need) bx = need;
+            pw_small_oc_kernel<T, V><<<dim3(bx < 1 ? 1 : bx, g.b), 256, smem, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc,
+                                                                                  g.w_per_sample, ep);
+        } else {
+            int need = (int)cdiv((int64_t)npix * (g.oc / V), 256);
+            if (bx > need) bx = need;
+            pw_small_ic_kernel<T, V><<<dim3(bx < 1 ? 1 : bx, g.b), 256, smem, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc,
+                                                                                  g.w_per_sample, ep);
+        }
+        count_launch();
+        return check_launch("conv_fwd_pointwise");
+    });
+}
+
+bool conv_wgrad_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy) {
+    if (!pw_shape(g)) return false;
+    const int vec = dtype == B200GAN_BF16 ? 8 : 4;
+    if (g.oc <= kPwMaxSmall && g.ic % vec == 0 && g.ic / vec <= 256 && (uintptr_t)x % 16 == 0) return true;
+    if (g.ic <= kPwMaxSmall && g.oc % vec == 0 && g.oc / vec <= 256 && (uintptr_t)gy % 16 == 0) return true;
+    return false;
+}
+
+int conv_wgrad_pointwise(const void* x, const void* gy, float* gw, int dtype, const ConvGeom& g, cudaStream_t st) {
+    const int npix = g.out_h * g.out_w;
+    return B200_DISPATCH(dtype, [&] {
+        constexpr int V = 16 / sizeof(T);
+        const bool narrow_oc = g.oc <= kPwMaxSmall;
+        const T* wide = narrow_oc ? (const T*)x : (const T*)gy;
+        const T* narrow = narrow_oc ? (const T*)gy : (const T*)x;
+        const int wc = narrow_oc ? g.ic : g.oc, nc = narrow_oc ? g.oc : g.ic;
+        int blocks = (int)cdiv((int64_t)sm_count() * 4, g.b);
+        int ppb = (int)cdiv(npix, blocks < 1 ? 1 : blocks);
+        if (ppb < 256) ppb = 256;
+        blocks = (int)cdiv(npix, ppb);
+        const size_t smem = (size_t)nc * wc * sizeof(float);
+        pw_wgrad_kernel<T, V><<<dim3(blocks, g.b), 256, smem, st>>>(wide, narrow, gw, npix, wc, nc, narrow_oc ? 1 : 0,
+                                                                 g.w_per_sample, ppb);
+        count_launch();
+        return check_launch("conv_wgrad_pointwise");
+    });
+}
+
+}  // namespace b200gan

@@ -396,7 +396,14 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
         if (int e = encode_bf16_map(&map_w, w, 3, dims, strides, box, es, p.row_bytes)) return e;
     }
     const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16;
-    cudaFuncSetAttribute(conv_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // once per device (not a stream operation; kept out of CUDA-graph capture)
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaFuncSetAttribute(conv_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_dev = cur_dev;
+    }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
     conv_fwd_umma_kernel<<<grid, kThreads, smem, st>>>(map_x, map_w, p);
     count_launch();

@@ -394,7 +394,14 @@ int conv_wgrad_umma(const void* x, const void* gy, float* gw, const ConvGeom& g,
     // so keep one extra slot of slack behind the rings
     const size_t smem = 1024 + (size_t)p.sa_stages * p.a_slot_bytes + (size_t)p.sb_stages * p.b_slot_bytes +
                         (2 * p.sa_stages + 2 * p.sb_stages + 2) * sizeof(uint64_t) + 16;
-    cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // once per device (not a stream operation; kept out of CUDA-graph capture)
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_dev = cur_dev;
+    }
     int grid = p.total_units < sm_count() ? p.total_units : sm_count();
     conv_wgrad_umma_kernel<<<grid, kWgThreads, smem, st>>>(map_x, map_gy, p);
     count_launch();

@@ -33,6 +33,7 @@ _SIGNATURES = {
     'b200gan_upfirdn2d': ([_vp, _vp, _vp, _i] + [_i] * 6 + [_i] * 7 + [_f, _vp], _i),
     'b200gan_bias_act_fwd': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
     'b200gan_bias_act_bwd': ([_vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
+    'b200gan_epilogue_bwd': ([_vp] * 10 + [_i, _i64, _i64, _i64, _f, _f, _vp], _i),
     'b200gan_reduce_nhwc': ([_vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
     'b200gan_conv_fwd': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
     'b200gan_set_conv_engine': ([_i], _i),
@@ -40,7 +41,7 @@ _SIGNATURES = {
     'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
     'b200gan_gemm_f32': ([_vp, _vp, _vp] + [_i] * 8 + [_f, _f, _vp], _i),
     'b200gan_mapping_fwd': ([_vp, _vp, _vp] + [_i] * 6 + [_vp], _i),
-    'b200gan_adam_ema': ([_vp, _vp, _vp, _vp, _vp, _i64] + [_f] * 8 + [_vp], _i),
+    'b200gan_adam_ema': ([_vp, _vp, _vp, _vp, _vp, _i64] + [_f] * 4 + [_vp, _f, _f, _vp], _i),
 }
 
 
@@ -168,6 +169,30 @@ def bias_act_bwd(gy, y, rowscale=None, slope=0.2, gain=2 ** 0.5, planar=False):
     return gx
 
 
+def epilogue_bwd(gy, y, rowscale=None, noise=None, noise_w=None, bias=None, slope=0.2, gain=2 ** 0.5,
+                 want_gd=True, want_gb=True, want_gnw=True):
+    """Fused backward of y = gain*lrelu(z*rowscale + noise_w*noise + bias) from the saved output (NHWC).
+    Returns (gconv, gd (N,C)|None, gb (C,)|None, gnw (1,)|None), reductions in fp32."""
+    _cuda(gy, y, rowscale, noise, noise_w, bias)
+    assert gy.is_contiguous() and y.is_contiguous() and gy.shape == y.shape and gy.dtype == y.dtype
+    n, c = gy.shape[0], gy.shape[-1]
+    hw = max(1, gy.numel() // max(1, n * c))
+    rowscale, noise_w, bias = _f32c(rowscale), _f32c(noise_w), _f32c(bias)
+    if noise is not None:
+        noise = noise.detach().to(gy.dtype).contiguous()
+    gconv = torch.empty_like(gy)
+    dev = gy.device
+    gd = torch.zeros(n, c, dtype=torch.float32, device=dev) if (want_gd and rowscale is not None) else None
+    gb = torch.zeros(c, dtype=torch.float32, device=dev) if want_gb else None
+    gnw = torch.zeros(1, dtype=torch.float32, device=dev) if (want_gnw and noise is not None) else None
+    if gy.numel():
+        with torch.cuda.device(dev):
+            _check(lib().b200gan_epilogue_bwd(_ptr(gy), _ptr(y), _ptr(gconv), _ptr(rowscale), _ptr(noise), _ptr(noise_w),
+                                              _ptr(bias), _ptr(gd), _ptr(gb), _ptr(gnw), _dt(gy), n, hw, c, float(slope),
+                                              float(gain), _stream()), 'epilogue_bwd')
+    return gconv, gd, gb, gnw
+
+
 def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None):
     """sums of a*b*pixw[n,pix] over pixels: (C,) and/or (N,C), fp32.  a, b contiguous (N,...,C)."""
     _cuda(a, b, pixw)
@@ -272,14 +297,14 @@ def mapping_fwd(z, layer_table, n_groups, n_layers, row_width, normalize):
     return acts
 
 
-def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay=0.0, grad_scale=1.0):
-    """In-place Adam step (torch.optim.Adam semantics) on flat fp32 buffers, fused with EMA."""
-    _cuda(p, g, m, v, ema)
+def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, bias_corr, ema_decay=0.0, grad_scale=1.0):
+    """In-place Adam step (torch.optim.Adam semantics) on flat fp32 buffers, fused with EMA.
+    bias_corr: device float32[2] = (1 - beta1**t, 1 - beta2**t)."""
+    _cuda(p, g, m, v, ema, bias_corr)
     for t in (p, g, m, v) + ((ema,) if ema is not None else ()):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
-    bc1 = 1.0 - beta1 ** step
-    bc2 = 1.0 - beta2 ** step
+    assert bias_corr.dtype == torch.float32 and bias_corr.numel() == 2 and bias_corr.is_contiguous()
     with torch.cuda.device(p.device):
         _check(lib().b200gan_adam_ema(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(ema), p.numel(), float(lr), float(beta1),
-                                      float(beta2), float(eps), float(bc1), float(bc2), float(ema_decay),
+                                      float(beta2), float(eps), _ptr(bias_corr), float(ema_decay),
                                       float(grad_scale), _stream()), 'adam_ema')

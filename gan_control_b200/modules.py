@@ -168,9 +168,9 @@ class ModulatedConv2d(nn.Module):                                             # 
         # per-sample weights cost B*OC*IC*k^2 elements, activation scaling costs B*IC*H*W
         return self.out_channel * self.kernel_size ** 2 <= height * width
 
-    def raw(self, input, style):
-        """Un-demodulated convolution and the demodulation coefficients: (z, d) with
-        ModulatedConv2d(x, style) == z * d[:, :, None, None]; d is None when demodulate=False."""
+    def operands(self, input, style):
+        """(x, wk, d): the convolution operands of one of the two equivalent forms (module docstring)
+        and the demodulation coefficients d (None when demodulate=False)."""
         batch, in_channel, height, width = input.shape
         s = self.modulation(style)                                            # (B, IC) fp32, gm.py:284
         w = self.weight[0] * self.scale                                       # (OC, IC, k, k)
@@ -184,6 +184,13 @@ class ModulatedConv2d(nn.Module):                                             # 
         else:
             wk = w.unsqueeze(0)
             x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
+        return x, wk, d
+
+    def raw(self, input, style):
+        """Un-demodulated convolution and the demodulation coefficients: (z, d) with
+        ModulatedConv2d(x, style) == z * d[:, :, None, None]."""
+        height, width = input.shape[2], input.shape[3]
+        x, wk, d = self.operands(input, style)
         k = self.kernel_size
         if self.upsample:
             # conv_transpose2d(stride 2, padding 0) in gather form (gm.py:301-306) ...
@@ -235,12 +242,20 @@ class StyledConv(nn.Module):                                                  # 
         self.activate = FusedLeakyReLU(out_channel)
 
     def forward(self, input, style, noise=None):
-        z, d = self.conv.raw(input, style)
+        conv = self.conv
+        if conv.upsample:
+            # transposed conv -> blur -> [demod scale + noise + bias + leaky-ReLU*sqrt(2)] in one pass
+            z, d = conv.raw(input, style)
+            if noise is None:
+                noise = z.new_empty(z.shape[0], 1, z.shape[2], z.shape[3]).normal_()
+            return ops.mod_epilogue(z, d, noise, self.noise.weight, self.activate.bias,
+                                    self.activate.negative_slope, self.activate.scale)
+        # plain layer: the whole StyledConv is ONE kernel (epilogue fused into the convolution)
+        x, wk, d = conv.operands(input, style)
         if noise is None:
-            noise = z.new_empty(z.shape[0], 1, z.shape[2], z.shape[3]).normal_()
-        # demod scale + noise + bias + leaky-ReLU*sqrt(2) in one pass
-        return ops.mod_epilogue(z, d, noise, self.noise.weight, self.activate.bias,
-                                self.activate.negative_slope, self.activate.scale)
+            noise = input.new_empty(input.shape[0], 1, input.shape[2], input.shape[3]).normal_()
+        return ops.conv_epilogue(x, wk, d, noise, self.noise.weight, self.activate.bias, 1, 1, conv.padding,
+                                 slope=self.activate.negative_slope, gain=self.activate.scale)
 
 
 class ToRGB(nn.Module):                                                       # gm.py:411-435
@@ -458,6 +473,24 @@ class ConvLayer(nn.Sequential):                                               # 
         if activate:
             layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
         super().__init__(*layers)
+
+    def forward(self, input):
+        """[Blur] -> conv (+ bias + leaky-ReLU fused into the convolution's epilogue)."""
+        mods = list(self)
+        x = input
+        if isinstance(mods[0], Blur):
+            x = mods[0](x)
+            mods = mods[1:]
+        conv = mods[0]
+        w = (conv.weight * conv.scale).unsqueeze(0)
+        if len(mods) == 1:                                   # no activation (ResBlock.skip)
+            y = ops.conv_gather(x, w, 1, conv.stride, conv.padding)
+            return y if conv.bias is None else y + conv.bias.view(1, -1, 1, 1).to(y.dtype)
+        act = mods[1]
+        bias = act.bias if isinstance(act, FusedLeakyReLU) else None
+        gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
+        return ops.conv_epilogue(x, w, None, None, None, bias, 1, conv.stride, conv.padding,
+                                 slope=act.negative_slope, gain=gain)
 
 
 class ResBlock(nn.Module):                                                    # gm.py:893-922

@@ -171,17 +171,22 @@ class _ModEpilogue(Function):
             if ctx.bias_dtype is not None and need[4]:
                 gb = gz32.sum((0, 2, 3)).to(ctx.bias_dtype)
         else:
-            gzp = _nhwc(gz)
+            # first-order only: ONE fused pass (kernels.epilogue_bwd) instead of four
+            gconv, gd_, gb_, gnw_ = K.epilogue_bwd(_nhwc(gy), _nhwc(y), d, noise, noise_w if noise is not None else None,
+                                                   None, slope, gain, want_gd=d is not None and need[1],
+                                                   want_gb=ctx.bias_dtype is not None and need[4],
+                                                   want_gnw=noise is not None and need[3])
+            # (bias is not needed to form z*d here because x = z is saved: use the exact product)
             if need[0]:
-                gx = gz if d is None else _nchw(K.bias_act_bwd(_nhwc(gy), _nhwc(y), d, slope, gain))
+                gx = _nchw(gconv)
             if d is not None and need[1]:
-                gd = K.reduce_nhwc(gzp, _nhwc(x), per_channel=False, per_sample_channel=True)[1].to(d.dtype)
+                gd = K.reduce_nhwc(_nhwc(gz), _nhwc(x), per_channel=False, per_sample_channel=True)[1].to(d.dtype)
             if noise is not None and need[2]:
                 gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
-            if noise is not None and need[3]:
-                gnw = K.reduce_nhwc(gzp, None, per_channel=True, pixw=noise)[0].sum().reshape(noise_w.shape).to(noise_w.dtype)
-            if ctx.bias_dtype is not None and need[4]:
-                gb = K.reduce_nhwc(gzp, None, per_channel=True)[0].to(ctx.bias_dtype)
+            if gnw_ is not None:
+                gnw = gnw_.reshape(noise_w.shape).to(noise_w.dtype)
+            if gb_ is not None:
+                gb = gb_.to(ctx.bias_dtype)
         return gx, gd, gnoise, gnw, gb, None, None
 
 
@@ -243,6 +248,72 @@ class _ConvWgrad(Function):
         if ctx.needs_input_grad[1]:
             ggy = _ConvGather.apply(x, ggw, up, down, pad0, oh, ow)
         return gx, ggy, None, None, None, None, None, None
+
+
+class _ConvEpilogue(Function):
+    """y = gain*lrelu(conv(x, w)*d[b,o] + nw*noise + bias[o]) in ONE kernel (the convolution's epilogue;
+    the conv output never reaches HBM).  StyledConv without upsampling (gm.py:402-408) and the
+    discriminator's ConvLayer (EqualConv2d + FusedLeakyReLU, gm.py:872-888).
+    Backward: first order = fused epilogue backward (from the saved output) + the conv gradients;
+    under create_graph the conv output is recomputed and the differentiable formulas are used."""
+
+    @staticmethod
+    def forward(ctx, x, w, d, noise, noise_w, bias, up, down, pad0, out_h, out_w, slope, gain):
+        y = _nchw(K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0, bias, d, noise,
+                             noise_w, slope, gain))
+        ctx.cfg = (up, down, pad0, x.shape[2], x.shape[3], out_h, out_w, slope, gain)
+        ctx.save_for_backward(x, w, d, noise, noise_w, bias, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, d, noise, noise_w, bias, y = ctx.saved_tensors
+        up, down, pad0, h, wd, oh, ow, slope, gain = ctx.cfg
+        need = ctx.needs_input_grad
+        kh, kw = w.shape[3], w.shape[4]
+        gx = gw = gd = gnoise = gnw = gb = None
+        if torch.is_grad_enabled():
+            z = _ConvGather.apply(x, w, up, down, pad0, oh, ow)                  # recompute, differentiable
+            gz = _BiasActGrad.apply(gy, y, slope, gain)
+            gz32 = up32(gz)
+            gconv = gz if d is None else (gz32 * up32(d)[:, :, None, None]).to(gz.dtype)
+            if d is not None and need[2]:
+                gd = (gz32 * up32(z)).sum((2, 3)).to(d.dtype)
+            if noise is not None and need[3]:
+                gnoise = (gz32.sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
+            if noise is not None and need[4]:
+                gnw = (gz32.sum(1, keepdim=True) * up32(noise)).sum().reshape(noise_w.shape).to(noise_w.dtype)
+            if bias is not None and need[5]:
+                gb = gz32.sum((0, 2, 3)).to(bias.dtype)
+        else:
+            gconv, gd_, gb_, gnw_ = K.epilogue_bwd(_nhwc(gy), _nhwc(y), d, noise, noise_w if noise is not None else None,
+                                                   bias, slope, gain, want_gd=d is not None and need[2],
+                                                   want_gb=bias is not None and need[5],
+                                                   want_gnw=noise is not None and need[4])
+            gconv = _nchw(gconv)
+            if gd_ is not None:
+                gd = gd_.to(d.dtype)
+            if gb_ is not None:
+                gb = gb_.to(bias.dtype)
+            if gnw_ is not None:
+                gnw = gnw_.reshape(noise_w.shape).to(noise_w.dtype)
+            if noise is not None and need[3]:
+                gz = _BiasActGrad.apply(gy, y, slope, gain)
+                gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
+        if need[0]:
+            gx = _ConvGather.apply(gconv, w.flip(3, 4).transpose(1, 2), down, up, kh - 1 - pad0, h, wd)
+        if need[1]:
+            gw = _ConvWgrad.apply(x, gconv, up, down, pad0, kh, kw, w.shape[0] > 1).to(w.dtype)
+        return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None
+
+
+def conv_epilogue(x, w, d=None, noise=None, noise_w=None, bias=None, up=1, down=1, pad0=0, out_hw=None,
+                  slope=0.2, gain=SQRT2):
+    """conv_gather fused with the demod-scale / noise / bias / leaky-ReLU epilogue; `w` (Bw,OC,IC,KH,KW)."""
+    if out_hw is None:
+        zh, zw = (x.shape[2] - 1) * up + 1, (x.shape[3] - 1) * up + 1
+        out_hw = ((zh + 2 * pad0 - w.shape[3]) // down + 1, (zw + 2 * pad0 - w.shape[4]) // down + 1)
+    return _ConvEpilogue.apply(x, w, d, noise, noise_w, bias, up, down, pad0, out_hw[0], out_hw[1], slope, gain)
 
 
 def conv_gather(x, w, up=1, down=1, pad0=0, out_hw=None):

@@ -116,13 +116,24 @@ class ParamArena:
 
 
 class ArenaAdam:
-    """torch.optim.Adam semantics (eps 1e-8, no weight decay) on an arena, fused with EMA."""
+    """torch.optim.Adam semantics (eps 1e-8, no weight decay) on an arena, fused with EMA.
+
+    The step counters live on the device (the bias corrections 1 - beta^t are recomputed there), so
+    the optimiser step is safe to capture in a CUDA graph and replay."""
 
     def __init__(self, arena, lr, betas, ema_arena=None):
         self.arena, self.lr, self.betas, self.ema = arena, lr, betas, ema_arena
         self.m = torch.zeros_like(arena.data)
         self.v = torch.zeros_like(arena.data)
-        self.steps = [0, 0]            # [head, tail] ranges step separately (see ParamArena.tail)
+        dev = arena.data.device
+        # [head, tail] ranges step separately (see ParamArena.tail)
+        self.t = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.log_betas = torch.tensor([math.log(b) if b > 0 else -math.inf for b in betas], dtype=torch.float64, device=dev)
+
+    def _bias_corr(self, which):
+        self.t[which] += 1
+        # 1 - beta^t  (beta = 0 -> exp(-inf * t) = 0 -> correction 1, like 0 ** t for t >= 1)
+        return (1.0 - torch.exp(self.log_betas * self.t[which])).to(self.arena.data.dtype)
 
     def step(self, skip_tail=False, ema_decay=None, grad_scale=1.0):
         a = self.arena
@@ -130,12 +141,12 @@ class ArenaAdam:
         for lo, hi, which in ranges:
             if hi <= lo:
                 continue
-            self.steps[which] += 1
+            bias_corr = self._bias_corr(which)
             ema = None
             if self.ema is not None and ema_decay is not None:
                 ema = self.ema.data[lo:hi]
             K.adam_ema(a.data[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], ema, self.lr, self.betas[0],
-                       self.betas[1], 1e-8, self.steps[which], ema_decay if ema is not None else 0.0, grad_scale)
+                       self.betas[1], 1e-8, bias_corr, ema_decay if ema is not None else 0.0, grad_scale)
 
 
 class GradBuckets:
@@ -236,6 +247,7 @@ class GanTrainStep:
         self.g_buckets = GradBuckets(self.g_arena, world_size, bucket_mb)
         self.d_buckets = GradBuckets(self.d_arena, world_size, bucket_mb)
         self.stats = {}
+        self.graphs = None
 
     # -- helpers ------------------------------------------------------------------------------
     @staticmethod
@@ -311,9 +323,10 @@ class GanTrainStep:
         if noise is None:
             noise = self.mixing_noise(path_batch)
         fake_img, latents = self.g(noise, return_latents=True)
-        path_loss, self.mean_path_length, path_lengths = g_path_regularize(
+        path_loss, new_mean, path_lengths = g_path_regularize(
             fake_img, latents, self.mean_path_length, pl_noise=pl_noise,
             all_reduce_mean=self._mean_over_ranks if self.world > 1 else None)
+        self.mean_path_length.copy_(new_mean)          # in place: the tensor is static under CUDA graphs
         weighted = self.path_regularize * self.g_reg_every * path_loss                     # gt.py:587-590
         if self.path_batch_shrink:
             weighted = weighted + 0 * up32(fake_img[0, 0, 0, 0])
@@ -339,3 +352,59 @@ class GanTrainStep:
             if self.ema_arena is not None:
                 self.ema_arena.data.mul_(self.accum).add_(self.g_arena.data, alpha=1 - self.accum)
         return d_loss, g_loss
+
+
+    # -- CUDA graphs: the whole step is launch-bound on the host (thousands of small kernels), so the
+    #    four step variants are captured once and replayed --------------------------------------------
+    def capture(self, real_shape, warmup=2):
+        """Capture discriminator_step / generator_step (+ their regularised variants) into CUDA graphs
+        reading from a static image buffer.  Requires mixing == 0 (style mixing draws host-side
+        randomness per step, tu:19-23)."""
+        assert self.mixing == 0, 'graph capture needs mixing=0 (host-side random control flow)'
+        self.static_real = torch.zeros(real_shape, device=self.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._variant('d')
+                self._variant('d_reg')
+                self._variant('g')
+                self._variant('g_reg')
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs, self.graph_launches, self.replayed_launches = {}, {}, 0
+        pool = None
+        for name in ('d', 'd_reg', 'g', 'g_reg'):
+            graph = torch.cuda.CUDAGraph()
+            n0 = K.launch_count()
+            with torch.cuda.graph(graph, pool=pool):
+                self._variant(name)
+            self.graph_launches[name] = K.launch_count() - n0      # libb200gan kernels inside this graph
+            pool = graph.pool()
+            self.graphs[name] = graph
+        return self
+
+    def _replay(self, name):
+        self.graphs[name].replay()
+        self.replayed_launches += self.graph_launches[name]
+
+    def _variant(self, name):
+        if name == 'd':
+            self.discriminator_step(self.static_real, self.mixing_noise(self.batch))
+        elif name == 'd_reg':
+            self.discriminator_regularize_step(self.static_real)
+        elif name == 'g':
+            self.generator_step(self.mixing_noise(self.batch), ema=True)
+        else:   # generator step without EMA, path-length step, then the iteration's single EMA update
+            self.generator_step(self.mixing_noise(self.batch), ema=False)
+            self.generator_regularize_step()
+            if self.ema_arena is not None:
+                self.ema_arena.data.mul_(self.accum).add_(self.g_arena.data, alpha=1 - self.accum)
+
+    def train_step_graphed(self, i, real_img, regularize=True):
+        self.static_real.copy_(real_img, non_blocking=True)
+        self._replay('d')
+        if regularize and i % self.d_reg_every == 0:
+            self._replay('d_reg')
+        self._replay('g_reg' if regularize and i % self.g_reg_every == 0 else 'g')
+        return self.stats['d_loss'], self.stats['g_loss']

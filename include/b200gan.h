@@ -76,6 +76,13 @@ int b200gan_bias_act_fwd(const void* x, void* y, const float* bias, const float*
 int b200gan_bias_act_bwd(const void* gy, const void* y, void* gx, const float* rowscale, int dtype,
                          int64_t n, int64_t hw, int64_t c, int64_t inner,
                          float slope, float gain, void* stream);
+/* Fused backward of the epilogue  y = gain*lrelu(z*rowscale + noise_w*noise + bias)  from the saved
+ * OUTPUT y (NHWC): writes gconv = gy*gain*act'(y)*rowscale (the gradient entering the conv backward)
+ * and accumulates gb[c] (bias), gd[n][c] (rowscale; z recovered from y), gnw[1] (noise strength).
+ * rowscale / noise / bias / gd / gb / gnw may be NULL; fp32 outputs zero-initialised by the caller. */
+int b200gan_epilogue_bwd(const void* gy, const void* y, void* gconv, const float* rowscale, const void* noise,
+                         const float* noise_w, const float* bias, float* gd, float* gb, float* gnw, int dtype,
+                         int64_t n, int64_t hw, int64_t c, float slope, float gain, void* stream);
 /* Pixel reductions of  a[n][p][c] * b[n][p][c] * pixw[n][p]  (b, pixw may be NULL):
  * out_c[c] = sum over n,p (bias / noise-strength grads), out_nc[n][c] = sum over p
  * (demod-scale grads); either may be NULL.  NHWC; fp32 outputs must be zero-initialised by
@@ -152,10 +159,12 @@ int b200gan_mapping_fwd(const float* z, float* acts, const b200gan_fc_layer* lay
                         int normalize, void* stream);
 
 /* ---- optimiser ------------------------------------------------------------------
- * Adam step as `torch.optim.Adam` (gt.py:161-173) fused with the generator EMA
- * `accumulate` (trainers/utils.py:8-12; ema may be NULL).  fp32, in place.      */
+ * Adam step as `torch.optim.Adam` (gt.py:161-173; eps added after the bias-corrected sqrt) fused with
+ * the generator EMA `accumulate` (trainers/utils.py:8-12; ema may be NULL).  fp32, in place.
+ * bias_corr: DEVICE float[2] = {1 - beta1^t, 1 - beta2^t} (on the device so that a captured CUDA
+ * graph replays with the current step count).                                          */
 int b200gan_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t numel,
-                     float lr, float beta1, float beta2, float eps, float bias_c1, float bias_c2,
+                     float lr, float beta1, float beta2, float eps, const float* bias_corr,
                      float ema_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus

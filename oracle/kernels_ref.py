@@ -79,6 +79,26 @@ def bias_act_bwd(gy, y, rowscale=None, slope=0.2, gain=2 ** 0.5, planar=False):
     return g.contiguous()
 
 
+def epilogue_bwd(gy, y, rowscale=None, noise=None, noise_w=None, bias=None, slope=0.2, gain=2 ** 0.5,
+                 want_gd=True, want_gb=True, want_gnw=True):
+    hi = torch.float64
+    n, c = gy.shape[0], gy.shape[-1]
+    g = gy.to(hi) * gain * torch.where(y > 0, 1.0, slope).to(hi)
+    d = _bcast(rowscale.to(hi), gy, False, 'nc') if rowscale is not None else torch.ones((), dtype=hi)
+    u = torch.where(y > 0, y.to(hi) / gain, y.to(hi) / (gain * slope))
+    nz = noise_w.to(hi).reshape(()) * _bcast(noise.to(hi).contiguous(), gy, False, 'pix') if noise is not None else 0.0
+    bv = _bcast(bias.to(hi), gy, False, 'c') if bias is not None else 0.0
+    z = (u - nz - bv) / d
+    out_t = torch.float64 if gy.dtype == torch.float64 else torch.float32
+    gconv = (g * d).to(gy.dtype).contiguous()
+    gd = (g * z).reshape(n, -1, c).sum(1).to(out_t) if (want_gd and rowscale is not None) else None
+    gb = g.reshape(-1, c).sum(0).to(out_t) if want_gb else None
+    gnw = None
+    if want_gnw and noise is not None:
+        gnw = (g * _bcast(noise.to(hi).contiguous(), gy, False, 'pix')).sum().reshape(1).to(out_t)
+    return gconv, gd, gb, gnw
+
+
 def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None):
     v = a.double() if a.dtype != torch.float64 else a
     if b is not None:
@@ -134,11 +154,11 @@ def gemm_f32(a, b, trans_a, trans_b, alpha=1.0):
     return (alpha * (a2 @ b2)).contiguous()
 
 
-def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, step, ema_decay=0.0, grad_scale=1.0):
+def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, bias_corr, ema_decay=0.0, grad_scale=1.0):
     gi = g * grad_scale
     m.mul_(beta1).add_(gi, alpha=1 - beta1)
     v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
-    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    bc1, bc2 = float(bias_corr[0]), float(bias_corr[1])
     p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)
     if ema is not None:
         ema.mul_(ema_decay).add_(p, alpha=1 - ema_decay)

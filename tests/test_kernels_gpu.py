@@ -79,7 +79,41 @@ def test_reduce_nhwc(shape, dt):
     assert float((oc2.cpu().double() - rc2).abs().max()) < 1e-4 * float(rc2.abs().max() + 1)
 
 
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('shape', [(3, 9, 9, 16), (2, 32, 32, 64), (16, 4, 4, 512)])
+def test_epilogue_bwd(shape, dt):
+    n, h, w, c = shape
+    gy, gyr = prep(rnd(60, *shape), dt)
+    y, yr = prep(rnd(61, *shape), dt)
+    d, bias, nw = (rnd(62, n, c).abs() + 0.5).float(), rnd(63, c).float(), torch.tensor([0.4])
+    noise, noiser = prep(rnd(64, n, h, w), dt)
+    out = K.epilogue_bwd(gy, y, d.cuda(), noise, nw.cuda(), bias.cuda(), 0.2, 2 ** 0.5)
+    ref = R.epilogue_bwd(gyr, yr, d.double(), noiser, nw.double(), bias.double(), 0.2, 2 ** 0.5)
+    close(out[0], ref[0].double(), dt, 'gconv')
+    for o, r_, name in zip(out[1:], ref[1:], ['gd', 'gb', 'gnw']):
+        err = float((o.cpu().double() - r_.double()).abs().max() / r_.double().abs().max().clamp_min(1e-12))
+        assert err < 2e-4, f'{name}: {err:.2e}'
+    out2 = K.epilogue_bwd(gy, y, None, None, None, bias.cuda(), 0.2, 2 ** 0.5)
+    ref2 = R.epilogue_bwd(gyr, yr, None, None, None, bias.double(), 0.2, 2 ** 0.5)
+    close(out2[0], ref2[0].double(), dt, 'gconv (bias only)')
+    assert out2[1] is None and out2[3] is None
+    assert float((out2[2].cpu().double() - ref2[2].double()).abs().max() / ref2[2].double().abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+def test_blur_separable_taps(dt):
+    x, xr = prep(rnd(70, 2, 40, 40, 32), dt)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    taps = torch.outer(k1, k1) / 64 * 4
+    y = K.upfirdn2d(x, taps.cuda(), 1, 1, 1, 1, 39, 39, True)
+    close(y, R.upfirdn2d(xr, taps.double(), 1, 1, 1, 1, 39, 39, True), dt)
+    y = K.upfirdn2d(x, taps.cuda(), 1, 1, 2, 2, 41, 41, False)
+    close(y, R.upfirdn2d(xr, taps.double(), 1, 1, 2, 2, 41, 41, False), dt)
+
+
 CONV_CASES = [
+    (2, 32, 32, 32, 3, 1, 1, 1, 0, True), (2, 16, 16, 3, 64, 1, 1, 1, 0, False), (3, 8, 8, 512, 3, 1, 1, 1, 0, True),
+    (2, 16, 16, 3, 512, 1, 1, 1, 0, True), (2, 9, 9, 40, 2, 1, 1, 1, 0, False),
     # b, h, w, ic, oc, k, up, down, pad0, per_sample
     (2, 8, 8, 16, 32, 3, 1, 1, 1, False), (3, 7, 9, 8, 12, 3, 1, 1, 1, True), (2, 6, 6, 8, 6, 3, 2, 1, 2, True),
     (2, 9, 9, 16, 8, 3, 1, 2, 0, False), (2, 8, 8, 3, 32, 1, 1, 1, 0, False), (2, 4, 4, 513, 64, 3, 1, 1, 1, False),
@@ -137,8 +171,9 @@ def test_adam_ema():
     dev = [t.clone().cuda() for t in (p, g, m, v, ema)]
     ref = [t.clone().double() for t in (p, g, m, v, ema)]
     for step in (1, 2, 3):
-        K.adam_ema(*dev, lr=0.002, beta1=0.0, beta2=0.99, eps=1e-8, step=step, ema_decay=0.998)
-        R.adam_ema(*ref, lr=0.002, beta1=0.0, beta2=0.99, eps=1e-8, step=step, ema_decay=0.998)
+        bc = torch.tensor([1 - 0.0 ** step, 1 - 0.99 ** step], dtype=torch.float32)
+        K.adam_ema(*dev, lr=0.002, beta1=0.0, beta2=0.99, eps=1e-8, bias_corr=bc.cuda(), ema_decay=0.998)
+        R.adam_ema(*ref, lr=0.002, beta1=0.0, beta2=0.99, eps=1e-8, bias_corr=bc.double(), ema_decay=0.998)
     for d, r in zip(dev, ref):
         assert float((d.cpu().double() - r).abs().max()) < 1e-5
     # agrees with torch.optim.Adam

@@ -150,7 +150,7 @@ def _worker(rank, world, port, out):
     torch.set_num_threads(2)
     from gan_control_b200 import kernels
     from oracle import kernels_ref
-    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
+    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
                  'gemm_f32', 'adam_ema', 'launch_count']:
         setattr(kernels, name, getattr(kernels_ref, name))
     real, zs, pl_noise = make_inputs(4 * world)
