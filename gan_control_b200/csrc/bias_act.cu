@@ -171,6 +171,73 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(const T* __restrict__
     }
 }
 
+// 16-byte vectorised variant: thread = (channel vector, pixel lane); per-thread partial sums, one
+// shared-memory reduction per block, one global atomic per (block, channel).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) epilogue_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ y,
+                                                               T* __restrict__ gconv, const float* __restrict__ rowscale,
+                                                               const T* __restrict__ noise, const float* __restrict__ noise_w,
+                                                               const float* __restrict__ bias, float* __restrict__ gd,
+                                                               float* __restrict__ gb, float* __restrict__ gnw, int64_t hw,
+                                                               int c, int64_t pix_per_block, float slope, float gain) {
+    extern __shared__ float sred[];                   // [2][c] + 1
+    float* red_b = sred;
+    float* red_d = sred + c;
+    float* red_n = sred + 2 * c;
+    for (int i = threadIdx.x; i < 2 * c + 1; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+    const int nv = c / VEC;
+    const int v = threadIdx.x % nv, pl = threadIdx.x / nv, npl = blockDim.x / nv;
+    const int64_t sample = blockIdx.y;
+    const int64_t p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+    const float nw = (noise && noise_w) ? *noise_w : 0.f;
+    const float inv_gain = 1.f / gain, inv_gs = 1.f / (gain * slope);
+    float dv[VEC], bv[VEC], idv[VEC], sb[VEC], sd[VEC];
+    float sn = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        dv[j] = rowscale ? rowscale[sample * c + v * VEC + j] : 1.f;
+        idv[j] = 1.f / dv[j];
+        bv[j] = bias ? bias[v * VEC + j] : 0.f;
+        sb[j] = 0.f;
+        sd[j] = 0.f;
+    }
+    if (pl < npl) {
+        for (int64_t p = p0 + pl; p < p1; p += npl) {
+            const int64_t e = (sample * hw + p) * c + (int64_t)v * VEC;
+            const Pack<T, VEC> yv = *reinterpret_cast<const Pack<T, VEC>*>(y + e);
+            const Pack<T, VEC> gv = *reinterpret_cast<const Pack<T, VEC>*>(gy + e);
+            const float nz = noise ? io<T>::ld(noise + sample * hw + p) : 0.f;
+            Pack<T, VEC> out;
+            float gsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float yy = io<T>::ld(&yv.v[j]);
+                const float gz = io<T>::ld(&gv.v[j]) * gain * (yy > 0.f ? 1.f : slope);
+                io<T>::st(&out.v[j], gz * dv[j]);
+                const float u = yy > 0.f ? yy * inv_gain : yy * inv_gs;
+                sb[j] += gz;
+                sd[j] += gz * (u - nw * nz - bv[j]) * idv[j];
+                gsum += gz;
+            }
+            sn += gsum * nz;
+            *reinterpret_cast<Pack<T, VEC>*>(gconv + e) = out;
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            atomicAdd(&red_b[v * VEC + j], sb[j]);
+            atomicAdd(&red_d[v * VEC + j], sd[j]);
+        }
+        atomicAdd(red_n, sn);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        if (gb) atomicAdd(gb + i, red_b[i]);
+        if (gd) atomicAdd(gd + sample * c + i, red_d[i]);
+    }
+    if (threadIdx.x == 0 && gnw && noise) atomicAdd(gnw, red_n[0]);
+}
+
 }  // namespace b200gan
 
 extern "C" int b200gan_epilogue_bwd(const void* gy, const void* y, void* gconv, const float* rowscale, const void* noise,
@@ -180,6 +247,21 @@ extern "C" int b200gan_epilogue_bwd(const void* gy, const void* y, void* gconv, 
     B200_REQUIRE(n >= 0 && hw >= 1 && c >= 1, "epilogue_bwd: bad shape");
     if (n == 0) return 0;
     return B200_DISPATCH(dtype, [&] {
+        constexpr int V = 16 / sizeof(T);
+        const bool vec = c % V == 0 && c / V <= 256 && c <= 4096 && n <= 65535 &&
+                         (((uintptr_t)gy | (uintptr_t)y | (uintptr_t)gconv) % 16 == 0);
+        if (vec) {
+            int64_t slabs = cdiv((int64_t)sm_count() * 8, n);
+            int64_t ppb = cdiv(hw, slabs < 1 ? 1 : slabs);
+            if (ppb < 128) ppb = 128;
+            slabs = cdiv(hw, ppb);
+            const size_t smem = (2 * (size_t)c + 1) * sizeof(float);
+            epilogue_bwd_vec_kernel<T, V><<<dim3((unsigned)slabs, (unsigned)n), 256, smem, (cudaStream_t)stream>>>(
+                (const T*)gy, (const T*)y, (T*)gconv, rowscale, (const T*)noise, noise_w, bias, gd, gb, gnw, hw, (int)c, ppb,
+                slope, gain);
+            count_launch();
+            return check_launch("epilogue_bwd");
+        }
         int64_t cblocks = cdiv(c, 32);
         if (cblocks > 64) cblocks = 64;
         int64_t want = cdiv((int64_t)sm_count() * 8, cblocks * n);

@@ -119,56 +119,70 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Role loops are executed by the WHOLE warp with warp-uniform control flow; only the TMA / MMA /
+    // commit instructions sit under elect_one().  (Running the loop under `if (lane == 0)` makes every
+    // descriptor a per-thread value that has to be moved to uniform registers around each UTCHMMA:
+    // measured ~200 clk per MMA, profiles/r01_conv_issue_bound.md.)
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            int stage = 0, par = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
-                const FwdPhase& P = p.phase[t.phase];
-                const int wz0 = (p.w_per_sample ? t.n0 : 0) * p.taps_total;
-                for (int tp = 0; tp < P.ntaps; ++tp) {
-                    const int cx = t.w0 * p.es + P.dx[tp], cy = t.h0 * p.es + P.dy[tp];
-                    for (int c = 0; c < p.kchunks; ++c) {
-                        mbar_wait(empty + stage, par ^ 1);
+        int stage = 0, par = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const FwdPhase& P = p.phase[t.phase];
+            const int wz0 = (p.w_per_sample ? t.n0 : 0) * p.taps_total;
+            for (int tp = 0; tp < P.ntaps; ++tp) {
+                const int cx = t.w0 * p.es + P.dx[tp], cy = t.h0 * p.es + P.dy[tp];
+                for (int c = 0; c < p.kchunks; ++c) {
+                    mbar_wait(empty + stage, par ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(full + stage, (uint32_t)p.tx_bytes);
                         tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, full + stage, c * p.kc, cx, cy, t.n0);
                         tma_load_3d(b_buf + stage * p.b_stage_bytes, &map_w, full + stage, c * p.kc, t.ocb * p.BN, wz0 + P.wtap[tp]);
-                        if (++stage == p.stages) { stage = 0; par ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == p.stages) { stage = 0; par ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(kTileM, p.BN, 0, 0);
-            const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
-            const int kk = p.kc / 16;
-            int stage = 0, par = 0, it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const TileCoord t = decode_tile(p, tile);
-                const FwdPhase& P = p.phase[t.phase];
-                const int acc = it & 1, acc_par = (it >> 1) & 1;
-                mbar_wait(tempty + acc, acc_par ^ 1);
+        const uint32_t idesc = instr_desc_bf16(kTileM, p.BN, 0, 0);
+        const uint32_t hi = desc_hi(8u * (uint32_t)p.row_bytes, (uint32_t)p.layout);
+        const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), 16), b_lo0 = desc_lo(smem_u32(b_buf), 16);
+        const uint32_t a_inc = (uint32_t)p.a_stage_bytes >> 4, b_inc = (uint32_t)p.b_stage_bytes >> 4;
+        const int nstages = p.stages, kchunks = p.kchunks, bn = p.BN, total = p.total_tiles;
+        const bool k4 = p.kc == 64;
+        int stage = 0, par = 0, it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const TileCoord t = decode_tile(p, tile);
+            const int acc = it & 1, acc_par = (it >> 1) & 1;
+            mbar_wait(tempty + acc, acc_par ^ 1);
+            tc_fence_after();
+            const int ksteps = p.phase[t.phase].ntaps * kchunks;
+            if (ksteps == 0) {           // phase without taps: the epilogue writes zeros
+                if (elect_one()) mbar_arrive(tfull + acc);
+                __syncwarp();
+                continue;
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * bn);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait(full + stage, par);
                 tc_fence_after();
-                const int ksteps = P.ntaps * p.kchunks;
-                if (ksteps == 0) {           // phase without taps: the epilogue writes zeros
-                    mbar_arrive(tfull + acc);
-                    continue;
-                }
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(full + stage, par);
-                    tc_fence_after();
-                    const uint64_t a_desc = smem_desc(smem_u32(a_buf + stage * p.a_stage_bytes), 16, sbo, (uint32_t)p.layout);
-                    const uint64_t b_desc = smem_desc(smem_u32(b_buf + stage * p.b_stage_bytes), 16, sbo, (uint32_t)p.layout);
-                    for (int k = 0; k < kk; ++k)   // +32 B per K=16 step inside the swizzled row
-                        mma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((ks | k) != 0));
+                if (elect_one()) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * a_inc, b_lo = b_lo0 + (uint32_t)stage * b_inc;
+                    // +32 B (= 2 descriptor units) per K = 16 step inside the swizzled row
+                    if (ks == 0) mma_issue<false>(d_tmem, a_lo, hi, b_lo, hi, idesc);
+                    else         mma_issue<true>(d_tmem, a_lo, hi, b_lo, hi, idesc);
+                    mma_issue<true>(d_tmem, a_lo + 2, hi, b_lo + 2, hi, idesc);
+                    if (k4) {
+                        mma_issue<true>(d_tmem, a_lo + 4, hi, b_lo + 4, hi, idesc);
+                        mma_issue<true>(d_tmem, a_lo + 6, hi, b_lo + 6, hi, idesc);
+                    }
                     mma_commit(empty + stage);
-                    if (++stage == p.stages) { stage = 0; par ^= 1; }
+                    if (ks == ksteps - 1) mma_commit(tfull + acc);
                 }
-                mma_commit(tfull + acc);
+                __syncwarp();
+                if (++stage == nstages) { stage = 0; par ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -370,7 +384,7 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.tx_bytes = p.rows * p.row_bytes + p.BN * p.row_bytes;
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     p.stages = (200 * 1024) / stage_bytes;
-    if (p.stages > 8) p.stages = 8;
+    if (p.stages > 12) p.stages = 12;
     if (p.stages < 2) p.stages = 2;
     p.tmem_cols = next_pow2(2 * p.BN);
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
@@ -395,7 +409,7 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
         uint32_t es[3] = {1, 1, 1};
         if (int e = encode_bf16_map(&map_w, w, 3, dims, strides, box, es, p.row_bytes)) return e;
     }
-    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * sizeof(uint64_t) + 64;
     // once per device (not a stream operation; kept out of CUDA-graph capture)
     static thread_local int attr_dev = -1;
     int cur_dev = 0;

@@ -1,0 +1,295 @@
+// tcgen05 implicit-GEMM convolution, "halo" variant for the small-channel / high-resolution layers
+// (3x3 or 1x1, stride 1, IC and OC <= 64: the 1024^2 and 512^2 StyledConv / ResBlock convs and their
+// data gradients).  The general kernel (conv_umma.cu) fetches one shifted A tile per tap -- 9x the
+// activation traffic from L2 and 9 TMA round trips per tile; at 32..64 channels that, not the tensor
+// pipe, bounds it (profiles/: 7 % of bf16 peak, 13 % of HBM at 32->32 @1024^2).  Here:
+//   * the input region of a 16x8-pixel output tile, (16+k-1) x 16 pixels, is fetched ONCE per channel
+//     chunk; the 9 tap operands are descriptors into that one buffer, shifted by whole pixel rows
+//     (ky * 2048 B) and by kx pixels (kx * 128 B), 8-pixel swizzle atoms = one tile row, stride between atoms = the buffer's
+//     16-pixel row pitch (measured on B200: the hardware swizzles on absolute address bits, the
+//     descriptor's base-offset field must stay 0 -- tests/test_kernels_gpu.py::test_conv_fwd_halo);
+//   * all taps of the (per-sample) weights stay resident in shared memory while consecutive tiles use
+//     the same sample, so steady-state traffic per tile is the activation halo only.
+#include <atomic>
+#include <cstring>
+
+#include "conv.cuh"
+#include "umma.cuh"
+
+namespace b200gan {
+
+using namespace umma;
+
+constexpr int kHaloThreads = 256;
+constexpr int kHTW = 8, kHTH = 16;
+
+struct HaloParams {
+    int B, H, W, OC, IC;                 // stride-1 conv: output extent == (H + 2*pad - k + 1) passed as OH/OW
+    int OH, OW, k, pad0;
+    int tiles_h, tiles_w, total_tiles;
+    int BN, kchunks, kc, row_bytes, layout;
+    int PW, RH;                          // buffer row pitch (pixels) and rows
+    int w_per_sample;
+    int a_stages, a_stage_bytes, w_tile_bytes, w_bytes;
+    int tmem_cols;
+    const float* bias;
+    const float* rowscale;
+    const __nv_bfloat16* noise;
+    const float* noise_w;
+    float slope, gain;
+    int has_ep;
+    __nv_bfloat16* y;
+};
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* w_buf = smem;                                             // [tap][chunk][BN][row_bytes]
+    uint8_t* a_buf = w_buf + ((p.w_bytes + 1023) & ~1023);
+    uint64_t* afull = reinterpret_cast<uint64_t*>(a_buf + p.a_stages * p.a_stage_bytes);
+    uint64_t* aempty = afull + p.a_stages;
+    uint64_t* wfull = aempty + p.a_stages;
+    uint64_t* tfull = wfull + 1;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_x);
+        prefetch_tensormap(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
+        mbar_init(wfull, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int taps = p.k * p.k;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        // ================= TMA producer (whole warp, elected lane issues) =================
+        int stage = 0, par = 0, key = -1;
+        int last_stage = -1, last_par = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int n = tile / tiles_per_img, t = tile % tiles_per_img;
+            const int h0 = (t / p.tiles_w) * kHTH, w0 = (t % p.tiles_w) * kHTW;
+            const int wkey = p.w_per_sample ? n : 0;
+            if (wkey != key) {
+                // drain: every MMA that reads the resident weights has completed once the most recently
+                // filled activation stage has been released
+                if (last_stage >= 0) mbar_wait(aempty + last_stage, last_par);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(wfull, (uint32_t)p.w_bytes);
+                    for (int tp = 0; tp < taps; ++tp)
+                        for (int c = 0; c < p.kchunks; ++c)
+                            tma_load_3d(w_buf + (tp * p.kchunks + c) * p.w_tile_bytes, &map_w, wfull, c * p.kc, 0, wkey * taps + tp);
+                }
+                __syncwarp();
+                key = wkey;
+            }
+            for (int c = 0; c < p.kchunks; ++c) {
+                mbar_wait(aempty + stage, par ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(afull + stage, (uint32_t)p.a_stage_bytes);
+                    tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, c * p.kc, w0 - p.pad0, h0 - p.pad0, n);
+                }
+                __syncwarp();
+                last_stage = stage; last_par = par;
+                if (++stage == p.a_stages) { stage = 0; par ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp, elected lane issues) =================
+        const uint32_t idesc = instr_desc_bf16(128, p.BN, 0, 0);
+        // A: one 8-pixel swizzle atom per tile row, atoms PW pixels apart; the swizzle is a function of the
+        // absolute shared-memory address, so tap-shifted start addresses need no base-offset field
+        const uint32_t a_hi = desc_hi((uint32_t)(p.PW * p.row_bytes), (uint32_t)p.layout);
+        const uint32_t b_hi = desc_hi(8u * (uint32_t)p.row_bytes, (uint32_t)p.layout);
+        const uint32_t w_lo0 = desc_lo(smem_u32(w_buf), 16), w_inc = (uint32_t)p.w_tile_bytes >> 4;
+        const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), 16), a_inc = (uint32_t)p.a_stage_bytes >> 4;
+        const uint32_t row_units = (uint32_t)p.row_bytes >> 4, pw = (uint32_t)p.PW;
+        const bool k4 = p.kc == 64;
+        const int nstages = p.a_stages, kchunks = p.kchunks, bn = p.BN, total = p.total_tiles, kdim = p.k;
+        int stage = 0, par = 0, it = 0, key = -1, wpar = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+            const int n = tile / tiles_per_img;
+            const int wkey = p.w_per_sample ? n : 0;
+            if (wkey != key) {
+                mbar_wait(wfull, wpar);
+                wpar ^= 1;
+                key = wkey;
+            }
+            const int acc = it & 1, acc_par = (it >> 1) & 1;
+            mbar_wait(tempty + acc, acc_par ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * bn);
+            for (int c = 0; c < kchunks; ++c) {
+                mbar_wait(afull + stage, par);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_stage_lo = a_lo0 + (uint32_t)stage * a_inc;
+                    uint32_t w_lo = w_lo0 + (uint32_t)c * w_inc;
+                    bool first = c == 0;
+                    for (int ky = 0; ky < kdim; ++ky) {
+                        for (int kx = 0; kx < kdim; ++kx) {
+                            const uint32_t a_lo = a_stage_lo + ((uint32_t)ky * pw + (uint32_t)kx) * row_units;
+                            if (first) mma_issue<false>(d_tmem, a_lo, a_hi, w_lo, b_hi, idesc);
+                            else       mma_issue<true>(d_tmem, a_lo, a_hi, w_lo, b_hi, idesc);
+                            first = false;
+                            mma_issue<true>(d_tmem, a_lo + 2, a_hi, w_lo + 2, b_hi, idesc);
+                            if (k4) {
+                                mma_issue<true>(d_tmem, a_lo + 4, a_hi, w_lo + 4, b_hi, idesc);
+                                mma_issue<true>(d_tmem, a_lo + 6, a_hi, w_lo + 6, b_hi, idesc);
+                            }
+                            w_lo += w_inc * (uint32_t)kchunks;          // next tap (tiles are [tap][chunk])
+                        }
+                    }
+                    mma_commit(aempty + stage);
+                    if (c == kchunks - 1) mma_commit(tfull + acc);
+                }
+                __syncwarp();
+                if (++stage == nstages) { stage = 0; par ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int q = warp - 4;
+        const int r = q * 32 + lane;
+        const int w_l = r % kHTW, h_l = r / kHTW;
+        const float nw = (p.noise != nullptr && p.noise_w != nullptr) ? *p.noise_w : 0.f;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int n = tile / tiles_per_img, t = tile % tiles_per_img;
+            const int oy = (t / p.tiles_w) * kHTH + h_l, ox = (t % p.tiles_w) * kHTW + w_l;
+            const int acc = it & 1, acc_par = (it >> 1) & 1;
+            mbar_wait(tfull + acc, acc_par);
+            tc_fence_after();
+            const bool valid = oy < p.OH && ox < p.OW;
+            const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
+            __nv_bfloat16* dst = p.y + pix * p.OC;
+            const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
+            const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                float v[16];
+                tmem_ld_x16(taddr + (uint32_t)c0, v);
+                if (valid) {
+                    if (p.has_ep) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float u = v[e];
+                            if (rs) u *= rs[c0 + e];
+                            u += nz + (p.bias ? p.bias[c0 + e] : 0.f);
+                            v[e] = p.gain * (u > 0.f ? u : u * p.slope);
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+                    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+bool conv_fwd_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
+    if (dtype != B200GAN_BF16) return false;
+    if (g.up != 1 || g.down != 1 || g.kh != g.kw || (g.kh != 1 && g.kh != 3)) return false;
+    if (!(g.ic == 32 || g.ic == 64) || !(g.oc == 16 || g.oc == 32 || g.oc == 64)) return false;
+    if (g.out_h < kHTH || g.out_w < kHTW) return false;
+    if (g.out_h != g.in_h + 2 * g.pad0 - g.kh + 1 || g.out_w != g.in_w + 2 * g.pad0 - g.kw + 1) return false;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) % 16 != 0) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias, const float* rowscale,
+                  const void* noise, const float* noise_w, float slope, float gain, cudaStream_t st) {
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = g.b; p.H = g.in_h; p.W = g.in_w; p.OC = g.oc; p.IC = g.ic; p.OH = g.out_h; p.OW = g.out_w;
+    p.k = g.kh; p.pad0 = g.pad0; p.w_per_sample = g.w_per_sample;
+    p.tiles_h = (g.out_h + kHTH - 1) / kHTH;
+    p.tiles_w = (g.out_w + kHTW - 1) / kHTW;
+    p.total_tiles = g.b * p.tiles_h * p.tiles_w;
+    p.BN = g.oc;
+    p.row_bytes = g.ic >= 64 ? 128 : 64;
+    p.layout = p.row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+    p.kc = p.row_bytes / 2;
+    p.kchunks = g.ic / p.kc;
+    p.PW = g.kw == 1 ? 8 : 16;
+    p.RH = kHTH + g.kh - 1;
+    p.a_stage_bytes = p.RH * p.PW * p.row_bytes;
+    p.a_stage_bytes = (p.a_stage_bytes + 1023) & ~1023;
+    p.w_tile_bytes = p.BN * p.row_bytes;
+    p.w_bytes = g.kh * g.kw * p.kchunks * p.w_tile_bytes;
+    p.a_stages = (int)((190 * 1024 - p.w_bytes) / p.a_stage_bytes);
+    if (p.a_stages > 6) p.a_stages = 6;
+    if (p.a_stages < 2) return B200GAN_ENOSUP;
+    int cols = 32;
+    while (cols < 2 * p.BN) cols <<= 1;
+    p.tmem_cols = cols;
+    p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
+    p.slope = slope; p.gain = gain;
+    p.has_ep = (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0;
+    p.y = (__nv_bfloat16*)y;
+
+    CUtensorMap map_x, map_w;
+    {
+        uint64_t dims[4] = {(uint64_t)g.ic, (uint64_t)g.in_w, (uint64_t)g.in_h, (uint64_t)g.b};
+        uint64_t strides[3] = {(uint64_t)g.ic * 2, (uint64_t)g.in_w * g.ic * 2, (uint64_t)g.in_h * g.in_w * g.ic * 2};
+        uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.PW, (uint32_t)p.RH, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        if (int e = encode_bf16_map(&map_x, x, 4, dims, strides, box, es, p.row_bytes)) return e;
+    }
+    {
+        const int wb = g.w_per_sample ? g.b : 1;
+        uint64_t dims[3] = {(uint64_t)g.ic, (uint64_t)g.oc, (uint64_t)wb * g.kh * g.kw};
+        uint64_t strides[2] = {(uint64_t)g.ic * 2, (uint64_t)g.oc * g.ic * 2};
+        uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.BN, 1};
+        uint32_t es[3] = {1, 1, 1};
+        if (int e = encode_bf16_map(&map_w, w, 3, dims, strides, box, es, p.row_bytes)) return e;
+    }
+    if (p.a_stage_bytes != p.RH * p.PW * p.row_bytes) {      // expect_tx counts exactly one box per stage
+        set_error("conv_fwd_halo: stage/box size mismatch");
+        return B200GAN_ENOSUP;
+    }
+    const size_t smem = 1024 + ((size_t)(p.w_bytes + 1023) & ~(size_t)1023) + (size_t)p.a_stages * p.a_stage_bytes +
+                        (2 * p.a_stages + 5) * sizeof(uint64_t) + 16;
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaFuncSetAttribute(conv_fwd_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_dev = cur_dev;
+    }
+    int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    conv_fwd_halo_kernel<<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
+    count_launch();
+    return check_launch("conv_fwd_halo");
+}
+
+}  // namespace b200gan

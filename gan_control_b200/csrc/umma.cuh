@@ -36,6 +36,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // of a hung GPU.  try_wait itself suspends for a hardware time slice, so the bound is seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
+    {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
     for (uint32_t spins = 0;; ++spins) {
         uint32_t done;
         asm volatile(
@@ -85,6 +94,37 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Lean issue path: the single MMA-issuing thread is instruction-bound (profiles/r01: ~200 clk per
+// tcgen05.mma when the descriptors are rebuilt every time), so the 64-bit descriptors are kept as a
+// constant high word plus a 32-bit low word (start address >> 4 | LBO << 16) that is advanced by adds.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout, uint32_t base_offset = 0) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((base_offset & 7u) << 17) | (layout << 29);
+}
+template <bool ACC>
+__device__ __forceinline__ void mma_issue(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if (ACC)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+}
+__device__ __forceinline__ void mma_issue_dyn(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
 // arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed

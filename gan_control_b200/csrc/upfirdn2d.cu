@@ -36,16 +36,18 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
         const int zy0 = oy * down - pad0_y, zx0 = ox * down - pad0_x;
-        for (int ky = 0; ky < kh; ++ky) {
-            int zy = zy0 + ky;
-            if (zy < 0 || zy % up != 0) continue;
-            int iy = zy / up;
-            if (iy >= in_h) continue;
-            for (int kx = 0; kx < kw; ++kx) {
-                int zx = zx0 + kx;
-                if (zx < 0 || zx % up != 0) continue;
-                int ix = zx / up;
-                if (ix >= in_w) continue;
+        // polyphase: only taps that land on a real (non-inserted) sample, i.e. (z0 + k) % up == 0
+        const int ky0 = ((-zy0 % up) + up) % up, kx0 = ((-zx0 % up) + up) % up;
+        for (int ky = ky0; ky < kh; ky += up) {
+            const int zy = zy0 + ky;
+            if (zy < 0) continue;
+            const int iy = zy / up;
+            if (iy >= in_h) break;
+            for (int kx = kx0; kx < kw; kx += up) {
+                const int zx = zx0 + kx;
+                if (zx < 0) continue;
+                const int ix = zx / up;
+                if (ix >= in_w) break;
                 float f = taps[ky * kw + kx];
                 const T* src = x + (((int64_t)b * in_h + iy) * in_w + ix) * c + (int64_t)ci * VEC;
                 Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(src);

@@ -128,67 +128,81 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int as = 0, apar = 0, bs = 0, bpar = 0;
-            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-                const WgUnit u = wg_decode(p, unit);
-                const WgPhase& P = p.phase[u.phase];
-                for (int kt = u.kt0; kt < u.kt1; ++kt) {
-                    int n0, h0, w0;
-                    wg_ktile(p, P, u, kt, n0, h0, w0);
-                    mbar_wait(bempty + bs, bpar ^ 1);
+        // ================= TMA producer (whole warp, elected lane issues) =================
+        int as = 0, apar = 0, bs = 0, bpar = 0;
+        for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+            const WgUnit u = wg_decode(p, unit);
+            const WgPhase& P = p.phase[u.phase];
+            for (int kt = u.kt0; kt < u.kt1; ++kt) {
+                int n0, h0, w0;
+                wg_ktile(p, P, u, kt, n0, h0, w0);
+                mbar_wait(bempty + bs, bpar ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(bfull + bs, (uint32_t)(p.nslabs_n * p.slab_n));
                     for (int s = 0; s < p.nslabs_n; ++s)
                         tma_load_4d(b_buf + bs * p.b_slot_bytes + s * p.slab_n, &map_gy, bfull + bs,
                                     u.ocb * p.N + s * p.atom_n, w0 * p.sa + P.px, h0 * p.sa + P.py, n0);
-                    if (++bs == p.sb_stages) { bs = 0; bpar ^= 1; }
-                    for (int g = u.g0; g < u.g0 + u.ng; ++g) {
-                        const WgGroup& G = P.group[g];
-                        mbar_wait(aempty + as, apar ^ 1);
+                }
+                __syncwarp();
+                if (++bs == p.sb_stages) { bs = 0; bpar ^= 1; }
+                for (int g = u.g0; g < u.g0 + u.ng; ++g) {
+                    const WgGroup& G = P.group[g];
+                    mbar_wait(aempty + as, apar ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(afull + as, (uint32_t)(G.natoms * p.slab_m));
                         for (int a = 0; a < G.natoms; ++a) {
                             const int tp = G.tap[a];
                             tma_load_4d(a_buf + as * p.a_slot_bytes + a * p.slab_m, &map_x, afull + as,
                                         u.icb * 128 + G.choff[a], w0 * p.sb + P.dx[tp], h0 * p.sb + P.dy[tp], n0);
                         }
-                        if (++as == p.sa_stages) { as = 0; apar ^= 1; }
                     }
+                    __syncwarp();
+                    if (++as == p.sa_stages) { as = 0; apar ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1);        // both operands MN-major
-            const int ksteps = p.rows / 16;
-            int as = 0, apar = 0, bs = 0, bpar = 0, it = 0;
-            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++it) {
-                const WgUnit u = wg_decode(p, unit);
-                mbar_wait(tempty, (it & 1) ^ 1);
-                tc_fence_after();
-                for (int kt = u.kt0; kt < u.kt1; ++kt) {
-                    mbar_wait(bfull + bs, bpar);
-                    const uint32_t b_addr = smem_u32(b_buf + bs * p.b_slot_bytes);
-                    for (int gl = 0; gl < u.ng; ++gl) {
-                        mbar_wait(afull + as, apar);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(a_buf + as * p.a_slot_bytes);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(gl * p.N);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t a_desc = smem_desc(a_addr + (uint32_t)(ks * 16 * p.rowb_m), (uint32_t)p.slab_m,
-                                                              8u * (uint32_t)p.rowb_m, (uint32_t)p.layout_m);
-                            const uint64_t b_desc = smem_desc(b_addr + (uint32_t)(ks * 16 * p.rowb_n), (uint32_t)p.slab_n,
-                                                              8u * (uint32_t)p.rowb_n, (uint32_t)p.layout_n);
-                            mma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kt != u.kt0 || ks != 0));
-                        }
+        // ================= MMA issuer (whole warp, elected lane issues) =================
+        const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1);        // both operands MN-major
+        const int ksteps = p.rows / 16;
+        const uint32_t a_hi = desc_hi(8u * (uint32_t)p.rowb_m, (uint32_t)p.layout_m);
+        const uint32_t b_hi = desc_hi(8u * (uint32_t)p.rowb_n, (uint32_t)p.layout_n);
+        const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), (uint32_t)p.slab_m), b_lo0 = desc_lo(smem_u32(b_buf), (uint32_t)p.slab_n);
+        const uint32_t a_inc = (uint32_t)p.a_slot_bytes >> 4, b_inc = (uint32_t)p.b_slot_bytes >> 4;
+        const uint32_t a_kstep = (uint32_t)p.rowb_m, b_kstep = (uint32_t)p.rowb_n;     // 16 rows * row_bytes >> 4
+        const int sa_stages = p.sa_stages, sb_stages = p.sb_stages, nn = p.N, total = p.total_units;
+        int as = 0, apar = 0, bs = 0, bpar = 0, it = 0;
+        for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++it) {
+            const WgUnit u = wg_decode(p, unit);
+            mbar_wait(tempty, (it & 1) ^ 1);
+            tc_fence_after();
+            for (int kt = u.kt0; kt < u.kt1; ++kt) {
+                mbar_wait(bfull + bs, bpar);
+                const uint32_t b_lo = b_lo0 + (uint32_t)bs * b_inc;
+                const uint32_t first = kt != u.kt0;
+                for (int gl = 0; gl < u.ng; ++gl) {
+                    mbar_wait(afull + as, apar);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)as * a_inc;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(gl * nn);
+                        mma_issue_dyn(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                        for (int ks = 1; ks < ksteps; ++ks)
+                            mma_issue<true>(d_tmem, a_lo + (uint32_t)ks * a_kstep, a_hi, b_lo + (uint32_t)ks * b_kstep, b_hi, idesc);
                         mma_commit(aempty + as);
-                        if (++as == p.sa_stages) { as = 0; apar ^= 1; }
+                        if (gl == u.ng - 1) {
+                            mma_commit(bempty + bs);
+                            if (kt == u.kt1 - 1) mma_commit(tfull);
+                        }
                     }
-                    mma_commit(bempty + bs);
-                    if (++bs == p.sb_stages) { bs = 0; bpar ^= 1; }
+                    __syncwarp();
+                    if (++as == sa_stages) { as = 0; apar ^= 1; }
                 }
-                if (u.kt1 > u.kt0) mma_commit(tfull); else mbar_arrive(tfull);
+                if (++bs == sb_stages) { bs = 0; bpar ^= 1; }
+            }
+            if (u.kt1 <= u.kt0) {
+                if (elect_one()) mbar_arrive(tfull);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {

@@ -113,7 +113,8 @@ int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype,
                      float slope, float gain, void* stream);
 /* Engine selection for the convolution family: 0 (default) = tcgen05/TMEM implicit GEMM whenever the
  * shape qualifies (bf16, IC = 32 or a multiple of 8 >= 64, OC a multiple of 16, k <= 3x3), CUDA-core
- * gather kernel otherwise; 1 = CUDA-core kernel only (tests, A/B timing).  Returns the previous value. */
+ * gather kernel otherwise; 1 = CUDA-core kernel only; 2 = automatic but without the halo-reuse variant
+ * (tests, A/B timing).  Returns the previous value. */
 int b200gan_set_conv_engine(int engine);
 /* Weight gradient of the form above:
  *   gw[wb][ky][kx][o][i] += sum_{b,oy,ox} gy[b][oy][ox][o] * z[b][oy*down+ky-pad0][..][i]

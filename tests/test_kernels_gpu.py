@@ -257,3 +257,34 @@ def test_conv_wgrad_umma(case):
         gwr = R.conv_wgrad(xr, gyr, k, k, up, down, pad0, ps)
         err = float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max())
         assert err < 2e-4, f'wgrad rel err {err:.2e}'
+
+
+HALO_CASES = [
+    # b, h, w, ic, oc, k, per_sample       (3x3 pad 1 / 1x1 pad 0, stride 1, <= 64 channels)
+    (2, 32, 32, 64, 64, 3, False), (3, 64, 64, 64, 64, 3, True), (2, 32, 32, 32, 32, 3, True), (2, 48, 40, 32, 64, 3, False),
+    (2, 32, 32, 64, 32, 3, True), (2, 64, 64, 64, 64, 1, False), (2, 40, 24, 32, 32, 1, True), (1, 128, 128, 64, 64, 3, False),
+    (5, 17, 9, 64, 16, 3, True),
+]
+
+
+@pytest.mark.parametrize('case', HALO_CASES)
+def test_conv_fwd_halo(case):
+    """halo-reuse tcgen05 variant vs the general tcgen05 kernel (engine 2) and the fp64 stand-in"""
+    b, h, w, ic, oc, k, ps = case
+    dt = torch.bfloat16
+    pad0 = k // 2
+    x, xr = prep(rnd(81, b, h, w, ic), dt)
+    wt, wr = prep(rnd(82, b if ps else 1, k, k, oc, ic) / (ic * k * k) ** 0.5, dt)
+    bias, rs, nw = rnd(83, oc).float(), (rnd(84, b, oc).abs() + 0.5).float(), torch.tensor([0.3])
+    noise, noiser = prep(rnd(85, b, h, w), dt)
+    y = K.conv_fwd(x, wt, h, w, 1, 1, pad0)
+    y_ep = K.conv_fwd(x, wt, h, w, 1, 1, pad0, bias.cuda(), rs.cuda(), noise, nw.cuda(), 0.2, 2 ** 0.5)
+    torch.cuda.synchronize()
+    prev = K.set_conv_engine(2)
+    try:
+        y_gen = K.conv_fwd(x, wt, h, w, 1, 1, pad0)
+    finally:
+        K.set_conv_engine(prev)
+    assert float((y.float() - y_gen.float()).abs().max()) <= 2e-2 * float(y_gen.float().abs().max()), 'halo vs general'
+    close(y, R.conv_fwd(xr, wr, h, w, 1, 1, pad0), dt, 'halo fwd')
+    close(y_ep, R.conv_fwd(xr, wr, h, w, 1, 1, pad0, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5), dt, 'halo fwd+ep')
