@@ -489,8 +489,17 @@ class ConvLayer(nn.Sequential):                                               # 
         act = mods[1]
         bias = act.bias if isinstance(act, FusedLeakyReLU) else None
         gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
-        return ops.conv_epilogue(x, w, None, None, None, bias, 1, conv.stride, conv.padding,
-                                 slope=act.negative_slope, gain=gain)
+        y = ops.conv_epilogue(x, w, None, None, None, bias, 1, conv.stride, conv.padding,
+                              slope=act.negative_slope, gain=gain)
+        return _plain_if_tiny(y)
+
+
+def _plain_if_tiny(y):
+    """The reference Discriminator `.view()`s its last (4x4) feature maps (gm.py:1006,1014), which needs the
+    default NCHW-contiguous layout; at <= 16 pixels the copy is free."""
+    if y.shape[2] * y.shape[3] <= 16 and not y.is_contiguous():
+        return y.contiguous()
+    return y
 
 
 class ResBlock(nn.Module):                                                    # gm.py:893-922
@@ -504,7 +513,7 @@ class ResBlock(nn.Module):                                                    # 
 
     def forward(self, input):
         out = self.conv2(self.conv1(input))
-        return (out + self.skip(input)) * (1 / SQRT2)
+        return _plain_if_tiny((out + self.skip(input)) * (1 / SQRT2))
 
 
 class Discriminator(nn.Module):                                               # gm.py:925-1016

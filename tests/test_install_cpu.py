@@ -1,0 +1,48 @@
+"""`gan_control_b200.install()` on the UNMODIFIED reference (build container only: needs /root/reference):
+the reference's own Generator / Discriminator classes, built after install(), run on the new operators and
+reproduce the goldens; state_dict layout unchanged."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import params as P
+from oracle.ref_import import available, import_reference
+from golden_io import Fixture, max_rel
+
+pytestmark = pytest.mark.skipif(not available(), reason='reference tree not present on this machine')
+
+
+def rnd(seed, *shape):
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal(shape))
+
+
+def test_install_patches_reference(cpu_kernels):
+    import sys
+    gm, _ = import_reference()
+    saved = {k: getattr(gm, k) for k in dir(gm) if not k.startswith('__')}
+    try:
+        import gan_control_b200
+        from gan_control_b200 import modules as M
+        gan_control_b200.install(gm)
+        assert gm.StyledConv is M.StyledConv and 'gan_control.models.op' in sys.modules
+        assert sys.modules['gan_control.models.op'].upfirdn2d is gm.upfirdn2d
+        fx = Fixture('networks')
+        size, sdim, n_mlp, seed = [int(v) for v in fx.np('g16.cfg')]
+        g = gm.Generator(size, sdim, n_mlp, channel_multiplier=2, conv_transpose=True).double()   # the REFERENCE class
+        assert isinstance(g.conv1, M.StyledConv) and isinstance(g.style[1], M.EqualLinear)
+        shapes = P.generator_shapes(size, sdim, n_mlp, 2)
+        assert {k: tuple(v.shape) for k, v in g.state_dict().items()} == {k: tuple(v) for k, v in shapes.items()}
+        g.load_state_dict(P.seeded_state_dict(shapes, seed, dtype=torch.float64))
+        z = rnd(seed * 10, 2, sdim)
+        noise = [rnd(seed * 100 + i, 2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)) for i in range(g.num_layers)]
+        img, _ = g([z], noise=noise)
+        assert max_rel(img, fx.t('g16.f64.img')) < 1e-10
+        d = gm.Discriminator(16, channel_multiplier=2).double()
+        d.load_state_dict(P.seeded_state_dict(P.discriminator_shapes(16, 2), 21, dtype=torch.float64))
+        pred, _ = d(rnd(210, 8, 3, 16, 16))
+        assert max_rel(pred, fx.t('d16.f64.pred')) < 1e-10
+    finally:
+        for k, v in saved.items():
+            setattr(gm, k, v)
+        sys.modules.pop('gan_control.models.op', None)
+        sys.modules.pop('gan_control.models.op.conv2d_gradfix', None)
