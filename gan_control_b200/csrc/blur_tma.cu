@@ -1,0 +1,220 @@
+// Blur (upfirdn2d with up = down = 1, <= 4x4 taps) as a TMA-fed shared-memory stencil, bf16 NHWC.
+//
+// The register-only kernel (upfirdn2d.cu::blur_rows_kernel) is latency-bound: ncu shows 64 % of the
+// stall samples on long_scoreboard at 26 % of HBM bandwidth (profiles/r01_blur.md) -- every thread
+// waits for its own loads.  Here the loads are decoupled from the threads: an elected thread streams
+// (16+kh-1) x (TW+kw-1)-pixel input tiles through a double-buffered TMA pipeline (out-of-bounds =
+// the zero padding), 128 threads run the separable FIR out of shared memory with rolling row
+// accumulators (swizzle-aware, conflict-free 16-byte reads) and write 16-byte vectors.
+#include <cstring>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b200gan {
+
+using namespace umma;
+
+constexpr int kBlurThreads = 128;
+constexpr int kBlurRows = 16;          // output rows per tile
+constexpr int kBlurStages = 2;
+
+struct BlurParams {
+    int n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip;
+    float gain;
+    int ch;            // channels per tile: 64 (128-B rows, SW128) or 32 (64-B rows, SW64)
+    int tw;            // output columns per tile: 16 or 32  (tw * ch/8 = 128 threads)
+    int box_w, box_h, stage_bytes;
+    int tiles_x, tiles_y, chunks, total_tiles;
+    const float* taps;
+    __nv_bfloat16* y;
+};
+
+__global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                const __grid_constant__ BlurParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    __shared__ uint64_t full[kBlurStages];
+    __shared__ float taps[16], tap_v[4], tap_h[4];
+    __shared__ int separable;
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+        const int ky = tid / 4, kx = tid % 4;
+        float v = 0.f;
+        if (ky < p.kh && kx < p.kw) {
+            const int sy = p.flip ? p.kh - 1 - ky : ky, sx = p.flip ? p.kw - 1 - kx : kx;
+            v = p.taps[sy * p.kw + sx] * p.gain;
+        }
+        taps[tid] = v;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kBlurStages; ++s) mbar_init(full + s, 1);
+        fence_barrier_init();
+        prefetch_tensormap(&map_x);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const float f00 = taps[0];
+        int sep = fabsf(f00) > 1e-20f;
+        for (int ky = 0; ky < 4 && sep; ++ky)
+            for (int kx = 0; kx < 4; ++kx)
+                if (fabsf(taps[ky * 4] * taps[kx] / f00 - taps[ky * 4 + kx]) > 1e-6f * fabsf(f00)) sep = 0;
+        separable = sep;
+        for (int k = 0; k < 4; ++k) {
+            tap_v[k] = sep ? taps[k * 4] / f00 : 0.f;
+            tap_h[k] = sep ? taps[k] : 0.f;
+        }
+    }
+    __syncthreads();
+    const bool sep = separable != 0;
+    const int ncg = p.ch / 8;                              // 16-byte channel groups per pixel in the tile
+    const int cg = tid % ncg, tx = tid / ncg;
+    const bool sw128 = p.ch == 64;
+    const int rowb = p.ch * 2;
+
+    auto issue = [&](int tile, int stage) {
+        int t = tile;
+        const int chunk = t % p.chunks; t /= p.chunks;
+        const int bx = t % p.tiles_x; t /= p.tiles_x;
+        const int by = t % p.tiles_y;
+        const int b = t / p.tiles_y;
+        mbar_arrive_expect_tx(full + stage, (uint32_t)(p.box_w * p.box_h * rowb));
+        tma_load_4d(smem + stage * p.stage_bytes, &map_x, full + stage, chunk * p.ch, bx * p.tw - p.pad0_x,
+                    by * kBlurRows - p.pad0_y, b);
+    };
+
+    int it = 0;
+    if (tid == 0 && (int)blockIdx.x < p.total_tiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < p.total_tiles) issue(next, stage ^ 1);      // stage^1 was released by the barrier below
+        mbar_wait(full + stage, (it >> 1) & 1);
+        int t = tile;
+        const int chunk = t % p.chunks; t /= p.chunks;
+        const int bx = t % p.tiles_x; t /= p.tiles_x;
+        const int by = t % p.tiles_y;
+        const int b = t / p.tiles_y;
+        const uint8_t* buf = smem + stage * p.stage_bytes;
+        const int ox = bx * p.tw + tx, oy0 = by * kBlurRows;
+        float acc[4][8];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[s][j] = 0.f;
+        __nv_bfloat16* yb = p.y + (((int64_t)b * p.out_h) * p.out_w + ox) * p.c + chunk * p.ch + cg * 8;
+        // taps are zero-padded to 4x4, so every tile reads kBlurRows + 3 input rows; fully unrolled: the rolling
+        // accumulator slots are compile-time
+#pragma unroll
+        for (int r = 0; r < kBlurRows + 3; ++r) {
+            float in[4][8];
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                {
+                    const int pix = r * p.box_w + tx + kx;
+                    const int swz = sw128 ? (cg ^ (pix & 7)) : (cg ^ ((pix >> 1) & 3));
+                    const uint4 v = *reinterpret_cast<const uint4*>(buf + (int64_t)pix * rowb + swz * 16);
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        in[kx][2 * j] = __uint_as_float(w4[j] << 16);
+                        in[kx][2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u);
+                    }
+                }
+            }
+            if (sep) {
+                float h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    h[j] = tap_h[0] * in[0][j] + tap_h[1] * in[1][j] + tap_h[2] * in[2][j] + tap_h[3] * in[3][j];
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky) {
+                    if (r - ky >= 0 && r - ky < kBlurRows) {
+                        const float f = tap_v[ky];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[(r - ky) & 3][j] = fmaf(f, h[j], acc[(r - ky) & 3][j]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky) {
+                    if (r - ky >= 0 && r - ky < kBlurRows) {
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) {
+                            const float f = taps[ky * 4 + kx];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[(r - ky) & 3][j] = fmaf(f, in[kx][j], acc[(r - ky) & 3][j]);
+                        }
+                    }
+                }
+            }
+            if (r >= 3) {                                  // output row r - 3 is complete
+                const int orow = r - 3;
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { o[j] = acc[orow & 3][j]; acc[orow & 3][j] = 0.f; }
+                if (oy0 + orow < p.out_h && ox < p.out_w) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(yb + (int64_t)(oy0 + orow) * p.out_w * p.c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+        __syncthreads();          // everyone is done reading `stage`: it may be refilled two iterations on
+    }
+}
+
+bool blur_tma_eligible(int dtype, int c, int kh, int kw, int up, int down, int out_h, int out_w, const void* x, const void* y) {
+    if (dtype != B200GAN_BF16 || up != 1 || down != 1 || kh > 4 || kw > 4) return false;
+    if (c % 32 != 0) return false;
+    if (out_h < 8 || out_w < 16) return false;
+    if (((uintptr_t)x | (uintptr_t)y) % 16 != 0) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+int blur_tma(const void* x, void* y, const float* taps, int n, int in_h, int in_w, int c, int out_h, int out_w, int kh,
+             int kw, int pad0_y, int pad0_x, int flip, float gain, cudaStream_t st) {
+    BlurParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.in_h = in_h; p.in_w = in_w; p.c = c; p.out_h = out_h; p.out_w = out_w; p.kh = kh; p.kw = kw;
+    p.pad0_y = pad0_y; p.pad0_x = pad0_x; p.flip = flip; p.gain = gain; p.taps = taps; p.y = (__nv_bfloat16*)y;
+    p.ch = c % 64 == 0 ? 64 : 32;
+    p.tw = p.ch == 64 ? 16 : 32;
+    p.box_w = p.tw + 3;            // taps are zero-padded to 4x4
+    p.box_h = kBlurRows + 3;
+    p.stage_bytes = ((p.box_w * p.box_h * p.ch * 2) + 1023) & ~1023;
+    p.tiles_x = (out_w + p.tw - 1) / p.tw;
+    p.tiles_y = (out_h + kBlurRows - 1) / kBlurRows;
+    p.chunks = c / p.ch;
+    p.total_tiles = n * p.tiles_y * p.tiles_x * p.chunks;
+    if (p.total_tiles == 0) return 0;
+    CUtensorMap map_x;
+    uint64_t dims[4] = {(uint64_t)c, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)n};
+    uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)in_w * c * 2, (uint64_t)in_h * in_w * c * 2};
+    uint32_t box[4] = {(uint32_t)p.ch, (uint32_t)p.box_w, (uint32_t)p.box_h, 1};
+    uint32_t es[4] = {1, 1, 1, 1};
+    if (int e = encode_bf16_map(&map_x, x, 4, dims, strides, box, es, p.ch * 2)) return e;
+    const size_t smem = 1024 + (size_t)kBlurStages * p.stage_bytes;
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        cudaFuncSetAttribute(blur_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_dev = cur_dev;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int grid = sm_count() * per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    blur_tma_kernel<<<grid, kBlurThreads, smem, st>>>(map_x, p);
+    count_launch();
+    return check_launch("blur_tma");
+}
+
+}  // namespace b200gan

@@ -210,6 +210,10 @@ static int launch_upfirdn(const void* x, void* y, const float* kernel, int n, in
     return check_launch("upfirdn2d");
 }
 
+bool blur_tma_eligible(int dtype, int c, int kh, int kw, int up, int down, int out_h, int out_w, const void* x, const void* y);
+int blur_tma(const void* x, void* y, const float* taps, int n, int in_h, int in_w, int c, int out_h, int out_w, int kh,
+             int kw, int pad0_y, int pad0_x, int flip, float gain, cudaStream_t st);
+
 }  // namespace b200gan
 
 extern "C" int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, int dtype, int n, int in_h,
@@ -221,6 +225,8 @@ extern "C" int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, in
     B200_REQUIRE(up >= 1 && down >= 1, "upfirdn2d: up/down must be >= 1");
     B200_REQUIRE(n >= 0 && c >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 0 && out_w >= 0, "upfirdn2d: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0 && blur_tma_eligible(dtype, c, kh, kw, up, down, out_h, out_w, x, y))
+        return blur_tma(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip_kernel, gain, st);
     return B200_DISPATCH(dtype, [&] {
         constexpr int V = 16 / sizeof(T);
         bool aligned = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);

@@ -36,6 +36,8 @@ def close(out, ref, dt, what=''):
     (2, 9, 9, 8, 4, 1, 1, 1, 8, 8, True), (2, 6, 7, 3, 4, 2, 1, 2, 12, 14, True), (3, 8, 8, 16, 4, 1, 1, 2, 9, 9, False),
     (2, 21, 21, 1, 12, 1, 2, 0, 5, 5, True), (1, 10, 10, 4, 12, 2, 1, 0, 9, 9, True), (2, 9, 7, 5, 4, 1, 1, -1, 7, 5, True),
     (2, 33, 33, 32, 4, 1, 1, 1, 32, 32, True), (2, 5, 5, 24, 4, 1, 2, 1, 2, 2, False),
+    (2, 37, 41, 64, 4, 1, 1, 2, 38, 42, False), (1, 20, 50, 128, 3, 1, 1, 1, 20, 50, True), (2, 65, 65, 96, 4, 1, 1, 1, 64, 64, True),
+    (1, 130, 70, 32, 4, 1, 1, 1, 129, 69, True),
 ])
 def test_upfirdn2d(cfg, dt):
     n, h, w, c, k, up, down, pad0, oh, ow, flip = cfg
