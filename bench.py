@@ -86,58 +86,49 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(size, batch, threads, steps=1, warmup=0):
-    """The reference's own CPU implementation of the step (oracle port of gan_model.py +
-    generator_trainer.py step functions, fp32, FUSED=False arithmetic) on `batch` images."""
+def cpu_reference_sample(size, threads, reps=1):
+    """Bounded sample of the reference's CPU path (oracle port of gan_model.py, fp32, FUSED=False arithmetic):
+    ONE generator forward + ONE discriminator forward on 1 image at `size`.  The full plain G+D step costs
+    (4*G_f + 8*D_f) / (G_f + D_f) times the FLOPs of this sample (forward, data-gradient
+    and weight-gradient passes cost one forward each), so images/s = 1 / (t_sample * that ratio).  A whole
+    1024^2 step on the box's host cores takes minutes (measured: 259 s on 128 cores), hence the sample."""
     import torch
     from oracle import params as P, stylegan2_oracle as O
     torch.set_num_threads(threads)
-    sd_g = {k: v.requires_grad_(not k.endswith('kernel') and not k.startswith('noises.'))
-            for k, v in P.seeded_state_dict(P.generator_shapes(size, 512, 8, 2), 1).items()}
-    sd_d = {k: v.requires_grad_(not k.endswith('kernel')) for k, v in P.seeded_state_dict(P.discriminator_shapes(size, 2), 2).items()}
-    gp = [v for v in sd_g.values() if v.requires_grad]
-    dp = [v for v in sd_d.values() if v.requires_grad]
-    lr_g, b_g = O.lazy_adam_hparams(0.002, 4)
-    lr_d, b_d = O.lazy_adam_hparams(0.002, 16)
-    g_opt = torch.optim.Adam(gp, lr=lr_g, betas=b_g)
-    d_opt = torch.optim.Adam(dp, lr=lr_d, betas=b_d)
-    real = torch.randn(batch, 3, size, size).clamp_(-1, 1)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        # discriminator_step (gt.py:645-667)
-        with torch.no_grad():
-            fake = O.generator_forward(sd_g, [torch.randn(batch, 512)], size)
-        d_loss = O.d_logistic_loss(O.discriminator_forward(sd_d, real, size), O.discriminator_forward(sd_d, fake, size)) / batch
-        d_opt.zero_grad()
-        d_loss.backward(inputs=dp)
-        d_opt.step()
-        # generator_step (gt.py:407-436)
-        fake = O.generator_forward(sd_g, [torch.randn(batch, 512)], size)
-        g_loss = O.g_nonsaturating_loss(O.discriminator_forward(sd_d, fake, size))
-        g_opt.zero_grad()
-        g_loss.backward(inputs=gp)
-        g_opt.step()
-        times.append(time.perf_counter() - t0)
-    t = sum(times[warmup:]) / steps
-    return batch / t, t
+    sd_g = P.seeded_state_dict(P.generator_shapes(size, 512, 8, 2), 1)
+    sd_d = P.seeded_state_dict(P.discriminator_shapes(size, 2), 2)
+    z = torch.randn(1, 512)
+    ts = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            img = O.generator_forward(sd_g, [z], size)
+            O.discriminator_forward(sd_d, img, size)
+            ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    g_f, d_f = {1024: (148.5, 153.3), 512: (119.3, 123.2), 256: (90.2, 93.1)}.get(size, (148.5, 153.3))
+    ratio = (4 * g_f + 8 * d_f) / (g_f + d_f)
+    return 1.0 / (t * ratio), t, ratio
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path on this box's host cores (see module docstring)."""
+    """--impl reference: the reference's CPU path on this box's host cores (oracle port; a Python reference
+    cannot travel to the GPU box).  Each of the K steps is one bounded sample (see cpu_reference_sample)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     size = args.cpu_sample_size or args.size
-    v, t = cpu_reference_step(size, 1, threads, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+    reps = max(1, min(args.steps, 2))
+    v, t, ratio = cpu_reference_sample(size, threads, reps=reps)
+    sample = (f'G forward + D forward on 1 image at {size}x{size}, fp32, {t:.1f} s (best of {reps}); scaled to the plain '
+              f'G+D step by its FLOP ratio {ratio:.2f}')
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'FFHQ-{size} G+D plain train step, reference FUSED=False arithmetic on host CPU',
-                       'global_batch': 1, 'note': 'bounded sample: 1 image per step, <=2 timed steps'},
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                             'sample': f'{max(1, min(args.steps, 2))} plain G+D step(s) on 1 image at {size}x{size}, fp32'},
+            'warmup': args.warmup, 'ms_per_step': t * ratio * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]), reference FUSED=False arithmetic '
+                                   f'on the host CPU, bounded sample', 'global_batch': 1},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
@@ -247,9 +238,7 @@ def run_b200(args):
     value = global_batch / (ms_step * 1e-3)
     e2e_value = global_batch / (ms_e2e * 1e-3)
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _finish(world)
         return
     peaks, peak_kind = measured_peaks()
     line = {
@@ -275,13 +264,23 @@ def run_b200(args):
     if not args.skip_cpu_baseline:
         threads = os.cpu_count() or 1
         csize = args.cpu_sample_size or size
-        v, t = cpu_reference_step(csize, 1, threads)
+        v, t, ratio = cpu_reference_sample(csize, threads)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                'sample': f'1 plain G+D step on 1 image at {csize}x{csize}, fp32, {t:.1f} s'}
+                                'sample': f'G forward + D forward on 1 image at {csize}x{csize}, fp32, {t:.1f} s; scaled to the '
+                                          f'plain G+D step by its FLOP ratio {ratio:.2f}'}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank runs leave through os._exit: tearing NCCL communicators down while captured CUDA graphs still
+    reference them can hang interpreter shutdown (observed on 2x B200: JSON printed, process never exited)."""
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
