@@ -30,6 +30,8 @@ int conv_wgrad_umma(const void* x, const void* gy, float* gw, const ConvGeom& g,
 bool conv_fwd_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y);
 int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias, const float* rowscale,
                   const void* noise, const float* noise_w, float slope, float gain, cudaStream_t st);
+bool conv_wgrad_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy);
+int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g, cudaStream_t st);
 int conv_wgrad_simt(const void* x, const void* gy, float* gw, int dtype, const ConvGeom& g, cudaStream_t st);
 
 }  // namespace b200gan

@@ -37,6 +37,8 @@ extern "C" int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int 
     ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
     if (g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_wgrad_pointwise_eligible(dtype, g, x, gy))
         return conv_wgrad_pointwise(x, gy, gw, dtype, g, (cudaStream_t)stream);
+    if (g_conv_engine.load() == 0 && b > 0 && conv_wgrad_halo_eligible(dtype, g, x, gy))
+        return conv_wgrad_halo(x, gy, gw, g, (cudaStream_t)stream);
     if (g_conv_engine.load() != 1 && b > 0 && conv_wgrad_umma_eligible(dtype, g, x, gy))
         return conv_wgrad_umma(x, gy, gw, g, (cudaStream_t)stream);
     return conv_wgrad_simt(x, gy, gw, dtype, g, (cudaStream_t)stream);

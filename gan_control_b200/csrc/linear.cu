@@ -94,11 +94,25 @@ __global__ void __launch_bounds__(256) linear_skinny_kernel(const T* __restrict_
             float acc[MB];
 #pragma unroll
             for (int i = 0; i < MB; ++i) acc[i] = 0.f;
-            for (int kk = lane; kk < k; kk += 32) {
-                const float wv = wrow[kk];
+            if (sizeof(T) == 4 && (k & 127) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0) {
+                // fp32 activations: 16-byte loads, 4 k's per lane per step
+                const float* xf = reinterpret_cast<const float*>(x);
+                for (int kk = lane * 4; kk < k; kk += 128) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wrow + kk);
 #pragma unroll
-                for (int i = 0; i < MB; ++i)
-                    if (m0 + i < m) acc[i] = fmaf(wv, io<T>::ld(x + (int64_t)(m0 + i) * k + kk), acc[i]);
+                    for (int i = 0; i < MB; ++i)
+                        if (m0 + i < m) {
+                            const float4 xv = *reinterpret_cast<const float4*>(xf + (int64_t)(m0 + i) * k + kk);
+                            acc[i] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[i]))));
+                        }
+                }
+            } else {
+                for (int kk = lane; kk < k; kk += 32) {
+                    const float wv = wrow[kk];
+#pragma unroll
+                    for (int i = 0; i < MB; ++i)
+                        if (m0 + i < m) acc[i] = fmaf(wv, io<T>::ld(x + (int64_t)(m0 + i) * k + kk), acc[i]);
+                }
             }
 #pragma unroll
             for (int i = 0; i < MB; ++i)

@@ -62,6 +62,53 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(
     }
 }
 
+// RGB-sized tensors (C <= 4: the ToRGB skip path, gm.py:429, and images): one thread per output PIXEL,
+// all channels in registers, polyphase tap skipping.
+template <typename T>
+__global__ void __launch_bounds__(256) upfirdn2d_smallc_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                               const float* __restrict__ kernel, int n, int in_h,
+                                                               int in_w, int c, int out_h, int out_w, int kh, int kw,
+                                                               int up, int down, int pad0_y, int pad0_x, int flip,
+                                                               float gain, int64_t total) {
+    __shared__ float taps[kMaxTaps * kMaxTaps];
+    for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) {
+        int ky = i / kw, kx = i % kw;
+        int sy = flip ? kh - 1 - ky : ky, sx = flip ? kw - 1 - kx : kx;
+        taps[i] = kernel[sy * kw + sx] * gain;
+    }
+    __syncthreads();
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % out_w);
+        int64_t q = idx / out_w;
+        const int oy = (int)(q % out_h);
+        const int b = (int)(q / out_h);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int zy0 = oy * down - pad0_y, zx0 = ox * down - pad0_x;
+        const int ky0 = ((-zy0 % up) + up) % up, kx0 = ((-zx0 % up) + up) % up;
+        for (int ky = ky0; ky < kh; ky += up) {
+            const int zy = zy0 + ky;
+            if (zy < 0) continue;
+            const int iy = zy / up;
+            if (iy >= in_h) break;
+            for (int kx = kx0; kx < kw; kx += up) {
+                const int zx = zx0 + kx;
+                if (zx < 0) continue;
+                const int ix = zx / up;
+                if (ix >= in_w) break;
+                const float f = taps[ky * kw + kx];
+                const T* src = x + (((int64_t)b * in_h + iy) * in_w + ix) * c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < c) acc[j] = fmaf(f, io<T>::ld(src + j), acc[j]);
+            }
+        }
+        T* dst = y + idx * c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < c) io<T>::st(dst + j, acc[j]);
+    }
+}
+
 // Fast path for the blur call sites (up = down = 1, <= 4x4 taps, vectorisable channel count): one
 // thread owns an (x, 8-channel) column and walks ROWS output rows with a rolling set of KH row
 // accumulators, so every input vector is loaded KW times (from L1) instead of KH*KW times, and a
@@ -229,6 +276,17 @@ extern "C" int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, in
         return blur_tma(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip_kernel, gain, st);
     return B200_DISPATCH(dtype, [&] {
         constexpr int V = 16 / sizeof(T);
+        if (c <= 4 && c > 1) {
+            int64_t total = (int64_t)n * out_h * out_w;
+            if (total == 0) return 0;
+            int64_t blocks = cdiv(total, 256);
+            int64_t cap = (int64_t)sm_count() * 32;
+            if (blocks > cap) blocks = cap;
+            upfirdn2d_smallc_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (T*)y, kernel, n, in_h, in_w, c, out_h, out_w,
+                                                                      kh, kw, up, down, pad0_y, pad0_x, flip_kernel, gain, total);
+            count_launch();
+            return check_launch("upfirdn2d(small c)");
+        }
         bool aligned = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
         if (aligned && up == 1 && down == 1 && kh <= 4 && kw <= 4 && out_h >= 8)
             return launch_blur_rows<T, V>(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x,

@@ -474,23 +474,25 @@ class ConvLayer(nn.Sequential):                                               # 
             layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
         super().__init__(*layers)
 
-    def forward(self, input):
-        """[Blur] -> conv (+ bias + leaky-ReLU fused into the convolution's epilogue)."""
+    def forward(self, input, out_scale=1.0):
+        """[Blur] -> conv (+ bias + leaky-ReLU fused into the convolution's epilogue).  `out_scale`
+        multiplies the result (ResBlock folds its 1/sqrt(2) into both branches this way)."""
         mods = list(self)
         x = input
         if isinstance(mods[0], Blur):
             x = mods[0](x)
             mods = mods[1:]
         conv = mods[0]
-        w = (conv.weight * conv.scale).unsqueeze(0)
-        if len(mods) == 1:                                   # no activation (ResBlock.skip)
+        if len(mods) == 1:                                   # no activation (ResBlock.skip): scale the weights
+            w = (conv.weight * (conv.scale * out_scale)).unsqueeze(0)
             y = ops.conv_gather(x, w, 1, conv.stride, conv.padding)
-            return y if conv.bias is None else y + conv.bias.view(1, -1, 1, 1).to(y.dtype)
+            return y if conv.bias is None else y + (conv.bias * out_scale).view(1, -1, 1, 1).to(y.dtype)
+        w = (conv.weight * conv.scale).unsqueeze(0)
         act = mods[1]
         bias = act.bias if isinstance(act, FusedLeakyReLU) else None
         gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
         y = ops.conv_epilogue(x, w, None, None, None, bias, 1, conv.stride, conv.padding,
-                              slope=act.negative_slope, gain=gain)
+                              slope=act.negative_slope, gain=gain * out_scale)
         return _plain_if_tiny(y)
 
 
@@ -512,8 +514,10 @@ class ResBlock(nn.Module):                                                    # 
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
     def forward(self, input):
-        out = self.conv2(self.conv1(input))
-        return _plain_if_tiny((out + self.skip(input)) * (1 / SQRT2))
+        # (conv2(conv1(x)) + skip(x)) / sqrt(2) (gm.py:920) with the scale folded into both branches:
+        # one elementwise pass instead of two
+        out = self.conv2(self.conv1(input), out_scale=1 / SQRT2)
+        return _plain_if_tiny(out + self.skip(input, out_scale=1 / SQRT2))
 
 
 class Discriminator(nn.Module):                                               # gm.py:925-1016

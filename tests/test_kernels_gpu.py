@@ -290,3 +290,24 @@ def test_conv_fwd_halo(case):
     assert float((y.float() - y_gen.float()).abs().max()) <= 2e-2 * float(y_gen.float().abs().max()), 'halo vs general'
     close(y, R.conv_fwd(xr, wr, h, w, 1, 1, pad0), dt, 'halo fwd')
     close(y_ep, R.conv_fwd(xr, wr, h, w, 1, 1, pad0, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5), dt, 'halo fwd+ep')
+
+
+@pytest.mark.parametrize('case', [c for c in HALO_CASES if c[4] in (32, 64)] + [(16, 64, 64, 32, 32, 3, False)])
+def test_conv_wgrad_halo(case):
+    """halo-reuse weight-gradient kernel vs the general tcgen05 wgrad (engine 2) and the fp64 stand-in"""
+    b, h, w, ic, oc, k, ps = case
+    dt = torch.bfloat16
+    pad0 = k // 2
+    x, xr = prep(rnd(91, b, h, w, ic), dt)
+    gy, gyr = prep(rnd(92, b, h, w, oc), dt)
+    gw = K.conv_wgrad(x, gy, k, k, 1, 1, pad0, ps)
+    torch.cuda.synchronize()
+    prev = K.set_conv_engine(2)
+    try:
+        gw_gen = K.conv_wgrad(x, gy, k, k, 1, 1, pad0, ps)
+    finally:
+        K.set_conv_engine(prev)
+    scale = float(gw_gen.abs().max())
+    assert float((gw - gw_gen).abs().max()) / scale < 2e-4, 'halo vs general wgrad'
+    gwr = R.conv_wgrad(xr, gyr, k, k, 1, 1, pad0, ps)
+    assert float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max()) < 2e-4
