@@ -309,6 +309,18 @@ class FcConfig:                                    # utils/mini_batch_multi_spli
         return cls(names, groups)
 
 
+def _cached_fc_table(module, groups_fn, device):
+    """The kernel's layer table holds raw parameter pointers: rebuild only when a parameter moved (the H2D
+    copy of a fresh table must not happen inside CUDA-graph capture; warm-up builds it)."""
+    groups = groups_fn()
+    key = tuple(p.data_ptr() for _, _, layers in groups for lin in layers for p in (lin.weight, lin.bias))
+    tbl = module.__dict__.get('_fc_table')
+    if tbl is None or tbl['key'] != key or tbl['table'].device != device:
+        tbl = ops.build_fc_table(groups, device)
+        module.__dict__['_fc_table'] = tbl
+    return tbl
+
+
 def _channels(channel_multiplier):
     return {4: 512, 8: 512, 16: 512, 32: 512, 64: int(256 * channel_multiplier),
             128: int(128 * channel_multiplier), 256: int(64 * channel_multiplier),
@@ -402,12 +414,27 @@ class Generator(nn.Module):                                                   # 
         return self.style(latent_in).mean(0, keepdim=True)
 
     def get_latent(self, input):
-        return self.style(input)
+        return self.map_styles(input)
+
+    def _mapping_groups(self):
+        """[(lo, hi, [EqualLinear...])] of the mapping network in latent order (vanilla: one group)."""
+        if isinstance(self.style, MultiFcStack):
+            cfg = self.style.fc_config
+            return [(cfg.groups[n]['latent_place'][0], cfg.groups[n]['latent_place'][1],
+                     [m for m in getattr(self.style, n) if isinstance(m, EqualLinear)]) for n in cfg.in_order_group_names]
+        return [(0, self.style_dim, [m for m in self.style if isinstance(m, EqualLinear)])]
+
+    def map_styles(self, z):
+        """z -> w.  Without autograd (inference, the discriminator step's generator pass) the whole mapping
+        network is ONE persistent kernel; with autograd the per-layer differentiable path runs."""
+        if z.is_cuda and z.ndim == 2 and not torch.is_grad_enabled() and z.dtype == torch.float32:
+            return ops.mapping_forward(_cached_fc_table(self, self._mapping_groups, z.device), z.contiguous(), normalize=True)
+        return self.style(z)
 
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=True, return_grad=False):   # gm.py:709-801
         if not input_is_latent:
-            styles = [self.style(s) for s in styles]
+            styles = [self.map_styles(s) for s in styles]
         if noise is None:
             if randomize_noise:
                 noise = [None] * self.num_layers
@@ -577,4 +604,7 @@ class FcStack(nn.Module):                                    # models/controller
         self.fc_stack = nn.Sequential(*layers)
 
     def forward(self, x):
+        if x.is_cuda and x.ndim == 2 and not torch.is_grad_enabled() and x.dtype == torch.float32:
+            tbl = _cached_fc_table(self, lambda: [(0, self.in_dim, list(self.fc_stack))], x.device)
+            return ops.mapping_forward(tbl, x.contiguous(), normalize=False)
         return self.fc_stack(x)

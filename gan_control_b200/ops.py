@@ -403,3 +403,43 @@ class _EqualLinear(Function):
 def equal_linear(x, weight, bias, scale, lr_mul=1.0, activation=False):
     """``EqualLinear.forward`` (gm.py:189-197) on a 2-D input."""
     return _EqualLinear.apply(x, weight, bias, scale, lr_mul, bool(activation))
+
+
+# ---------------------------------------------------------------------------------------------
+# mapping network in one persistent kernel (forward / no-grad)       (gan_model.py:633-642, 489-502)
+# ---------------------------------------------------------------------------------------------
+def build_fc_table(groups, device):
+    """groups: [(lo, hi, [EqualLinear, ...]), ...] in latent order.  Returns the device-resident layer table
+    of `b200gan_mapping_fwd` (layer-major FcLayer structs) plus its geometry.  Layer 0 reads its slice
+    [lo, hi) of z, the last layer writes its slice of w, hidden activations are packed group after group."""
+    n_groups, n_layers = len(groups), len(groups[0][2])
+    assert n_layers >= 1 and all(len(g[2]) == n_layers for g in groups)
+    table = (K.FcLayer * (n_groups * n_layers))()
+    keep, row_width, out_width, in_offs = [], 0, 0, None
+    for l in range(n_layers):
+        off = 0
+        for gi, (lo, hi, layers) in enumerate(groups):
+            lin = layers[l]
+            w, b = lin.weight.detach(), lin.bias.detach()
+            assert w.is_contiguous() and b.is_contiguous() and w.dtype == torch.float32
+            keep += [w, b]
+            e = table[l * n_groups + gi]
+            e.w, e.bias = w.data_ptr(), b.data_ptr()
+            e.in_dim, e.out_dim = w.shape[1], w.shape[0]
+            e.in_off = lo if l == 0 else in_offs[gi]
+            e.out_off = lo if l == n_layers - 1 else off
+            e.scale, e.bias_mul = float(lin.scale), float(lin.lr_mul)
+            off += w.shape[0]
+            row_width = max(row_width, e.in_off + e.in_dim, e.out_off + e.out_dim)
+            if l == n_layers - 1:
+                out_width = max(out_width, e.out_off + e.out_dim)
+        in_offs = [table[l * n_groups + gi].out_off for gi in range(n_groups)]
+    raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(device)
+    return {'table': raw, 'n_groups': n_groups, 'n_layers': n_layers, 'row_width': row_width, 'out_width': out_width,
+            'key': tuple(t.data_ptr() for t in keep), 'keep': keep}
+
+
+def mapping_forward(tbl, z, normalize=True):
+    """Whole mapping network / MultiFcStack / FcStack forward in ONE cooperative kernel (no autograd)."""
+    acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize)
+    return acts[tbl['n_layers'], :, :tbl['out_width']]

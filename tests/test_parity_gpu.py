@@ -222,3 +222,57 @@ def test_generator_discriminator_bf16():
     assert e < 5e-2
     torch.nn.functional.softplus(-d(img)[0]).mean().backward()
     assert all(torch.isfinite(p.grad).all() for p in g.parameters() if p.grad is not None)
+
+
+def test_mapping_persistent_kernel():
+    """`b200gan_mapping_fwd` (one cooperative kernel for the whole mapping network) against the per-layer path and
+    the goldens: vanilla stack, split-FC MultiFcStack, controller FcStack."""
+    fx = Fixture('networks')
+    for name, fcg in [('g16', None), ('g16split', GROUPS)]:
+        size, sdim, n_mlp, seed = [int(v) for v in fx.np(name + '.cfg')]
+        g = M.Generator(size, sdim, n_mlp, channel_multiplier=2, conv_transpose=True, split_fc=fcg is not None,
+                        fc_config=_fc_config(fcg) if fcg else None)
+        g.load_state_dict(P.seeded_state_dict(P.generator_shapes(size, sdim, n_mlp, 2, fcg), seed))
+        g.to(DEV)
+        zs = rnd(seed * 10 + 2, 16, sdim).to(DEV)
+        with torch.no_grad():
+            w_fast = g.map_styles(zs)
+        w_ref = g.style(zs)
+        assert max_rel(w_fast, w_ref) < 1e-5
+        assert max_rel(w_fast.mean(0, keepdim=True), fx.t(f'{name}.f64.mean_w')) < 1e-4
+    fxs = Fixture('fcstack')
+    n_mlp, din, mid, dout, seed = [int(v) for v in fxs.np('cfg')]
+    m = M.FcStack(0.01, n_mlp, din, mid, dout)
+    m.load_state_dict(P.seeded_state_dict(P.fc_stack_shapes(n_mlp, din, mid, dout), seed))
+    m.to(DEV)
+    with torch.no_grad():
+        y = m(fxs.t('x', torch.float32, DEV))
+    assert max_rel(y, fxs.t('y')) < 1e-5
+
+
+def test_graph_replay_runs_and_counts_launches():
+    """The four step variants captured into CUDA graphs replay, keep the parameters finite, advance the
+    device-side Adam step counters and account for their kernel launches."""
+    from gan_control_b200.train_step import GanTrainStep
+    import copy
+    torch.manual_seed(7)
+    g = M.Generator(16, 64, 3, channel_multiplier=2, conv_transpose=True, act_dtype=torch.bfloat16).to(DEV)
+    d = M.Discriminator(16, channel_multiplier=2, act_dtype=torch.bfloat16).to(DEV)
+    step = GanTrainStep(g, d, copy.deepcopy(g), batch=4, latent_size=64)
+    real = torch.randn(4, 3, 16, 16, device=DEV).clamp_(-1, 1)
+    step.capture(tuple(real.shape), warmup=1)
+    t0 = step.d_optim.t.clone()
+    p0 = step.g_arena.data.clone()
+    losses = []
+    for i in (1, 2, 3, 4, 16):
+        d_loss, g_loss = step.train_step_graphed(i, real)
+        losses.append((float(d_loss), float(g_loss)))
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for pair in losses for v in pair)
+    assert len({round(p[1], 6) for p in losses}) > 1                      # new latents each replay
+    assert torch.isfinite(step.g_arena.data).all() and torch.isfinite(step.d_arena.data).all()
+    assert float((step.g_arena.data - p0).abs().max()) > 0
+    assert float(step.d_optim.t[0] - t0[0]) == 6.0                       # 5 D steps + 1 R1 step (i = 16)
+    assert step.replayed_launches > 5 * step.graph_launches['d'] > 0
+    step.g_arena.check_views()
+    step.d_arena.check_views()
