@@ -16,7 +16,7 @@ namespace b200gan {
 using namespace umma;
 
 constexpr int kBlurThreads = 128;
-constexpr int kBlurRows = 16;          // output rows per tile
+constexpr int kBlurRows = 8;           // output rows per tile (26 KB stages -> 4 CTAs per SM)
 constexpr int kBlurStages = 2;
 
 struct BlurParams {
@@ -104,10 +104,15 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[s][j] = 0.f;
         __nv_bfloat16* yb = p.y + (((int64_t)b * p.out_h) * p.out_w + ox) * p.c + chunk * p.ch + cg * 8;
-        // taps are zero-padded to 4x4, so every tile reads kBlurRows + 3 input rows; fully unrolled: the rolling
-        // accumulator slots are compile-time
+        // taps are zero-padded to 4x4, so every tile reads kBlurRows + 3 input rows.  The row loop is rolled in
+        // groups of 4 (the rolling accumulator slots stay compile-time, the body stays inside the instruction
+        // cache: the fully unrolled version stalled on instruction fetch, profiles/r01_blur.md)
+#pragma unroll 1
+        for (int r0 = 0; r0 < kBlurRows + 4; r0 += 4)
 #pragma unroll
-        for (int r = 0; r < kBlurRows + 3; ++r) {
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = r0 + rr;
+            if (r >= kBlurRows + 3) break;
             float in[4][8];
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx) {
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_con
                     if (r - ky >= 0 && r - ky < kBlurRows) {
                         const float f = tap_v[ky];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[(r - ky) & 3][j] = fmaf(f, h[j], acc[(r - ky) & 3][j]);
+                        for (int j = 0; j < 8; ++j) acc[(rr - ky) & 3][j] = fmaf(f, h[j], acc[(rr - ky) & 3][j]);
                     }
                 }
             } else {
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_con
                         for (int kx = 0; kx < 4; ++kx) {
                             const float f = taps[ky * 4 + kx];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[(r - ky) & 3][j] = fmaf(f, in[kx][j], acc[(r - ky) & 3][j]);
+                            for (int j = 0; j < 8; ++j) acc[(rr - ky) & 3][j] = fmaf(f, in[kx][j], acc[(rr - ky) & 3][j]);
                         }
                     }
                 }
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_con
                 const int orow = r - 3;
                 float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { o[j] = acc[orow & 3][j]; acc[orow & 3][j] = 0.f; }
+                for (int j = 0; j < 8; ++j) { o[j] = acc[(rr - 3) & 3][j]; acc[(rr - 3) & 3][j] = 0.f; }
                 if (oy0 + orow < p.out_h && ox < p.out_w) {
                     uint32_t pk[4];
 #pragma unroll

@@ -315,3 +315,13 @@ if __name__ == '__main__':
     gen_fcstack(gm)
     gen_networks(gm, trainer)
     gen_config1(gm)
+
+
+def gen_config5_controls():
+    """BASELINE.json configs[4] inputs: the 1000 `orientation` control vectors and `latents_w` rows of the
+    reference's data fixture resources/ffhq_1K_attributes_samples_df.pkl (derived arrays only)."""
+    import pandas as pd
+    df = pd.read_pickle('/root/reference/resources/ffhq_1K_attributes_samples_df.pkl')
+    ori = np.stack(df['orientation'].values).astype(np.float32)
+    lw = np.stack(df['latents_w'].values).astype(np.float16)
+    np.savez_compressed(os.path.join(OUT, 'config5_controls.npz'), orientation=ori, latents_w=lw)
