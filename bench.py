@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-roofline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
+    ap.add_argument('--ncu-range', action='store_true',
+                    help='bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)')
     return ap.parse_args()
 
 
@@ -230,7 +232,12 @@ def run_b200(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    if args.ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms_step, launches = timed(args.steps, False, 1)
+    if args.ncu_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.summary() if sampler else None
     ms_e2e, _ = timed(max(1, args.steps // 2), True, 1)
     ms_plain, _ = timed(max(1, min(args.steps, 4)), False, 1) if False else (None, None)

@@ -506,19 +506,29 @@ class ConvLayer(nn.Sequential):                                               # 
         multiplies the result (ResBlock folds its 1/sqrt(2) into both branches this way)."""
         mods = list(self)
         x = input
+        stride = None
         if isinstance(mods[0], Blur):
-            x = mods[0](x)
+            blur, conv = mods[0], mods[1]
+            if conv.weight.shape[2] == 1 and conv.stride == 2 and conv.padding == 0:
+                # Blur -> 1x1 stride-2 conv (ResBlock.skip, gm.py:907-909) only ever reads the blur at even
+                # positions: decimate inside the FIR (upfirdn2d down=2, a quarter of the outputs) and run the
+                # 1x1 conv at stride 1 on the small map.  Same arithmetic, same taps, same result.
+                x = ops.upfirdn2d(x, blur.kernel, up=1, down=2, pad=blur.pad)
+                stride = 1
+            else:
+                x = blur(x)
             mods = mods[1:]
         conv = mods[0]
+        stride = conv.stride if stride is None else stride
         if len(mods) == 1:                                   # no activation (ResBlock.skip): scale the weights
             w = (conv.weight * (conv.scale * out_scale)).unsqueeze(0)
-            y = ops.conv_gather(x, w, 1, conv.stride, conv.padding)
+            y = ops.conv_gather(x, w, 1, stride, conv.padding)
             return y if conv.bias is None else y + (conv.bias * out_scale).view(1, -1, 1, 1).to(y.dtype)
         w = (conv.weight * conv.scale).unsqueeze(0)
         act = mods[1]
         bias = act.bias if isinstance(act, FusedLeakyReLU) else None
         gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
-        y = ops.conv_epilogue(x, w, None, None, None, bias, 1, conv.stride, conv.padding,
+        y = ops.conv_epilogue(x, w, None, None, None, bias, 1, stride, conv.padding,
                               slope=act.negative_slope, gain=gain * out_scale)
         return _plain_if_tiny(y)
 
@@ -586,10 +596,24 @@ class Discriminator(nn.Module):                                               # 
         stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
         stddev = stddev.mean([2, 3, 4], keepdim=True).squeeze(2)
         stddev = stddev.repeat(group, 1, height, width).to(out.dtype)
-        out = torch.cat([out, stddev], 1).contiguous(memory_format=torch.channels_last)
-        out = final_conv(out)
+        out = self._final_conv_split(out, stddev, final_conv)
         out = out.reshape(batch, -1)
         return final_linear(out)
+
+    @staticmethod
+    def _final_conv_split(out, stddev, final_conv):
+        """final_conv(cat([out, stddev], 1)) (gm.py:1013-1014) without the concatenation: a convolution is a sum over
+        input channels, so the 512 feature channels go through the tensor-core engine (513 channels are not a
+        multiple of its 8-channel vectors) and the single stddev channel is added as its own 9-tap convolution;
+        bias + leaky-ReLU run on the sum.  The parameter keeps the reference shape (512, 513, 3, 3)."""
+        mods = list(final_conv)
+        conv, act = mods[0], mods[1]
+        channel = out.shape[1]
+        w = conv.weight * conv.scale
+        z = ops.conv_gather(out, w[:, :channel].unsqueeze(0), 1, conv.stride, conv.padding)
+        z = z + ops.conv_gather(stddev, w[:, channel:].unsqueeze(0), 1, conv.stride, conv.padding)
+        y = ops.fused_leaky_relu(z, act.bias, act.negative_slope, act.scale)
+        return _plain_if_tiny(y)
 
 
 class FcStack(nn.Module):                                    # models/controller_model.py:13-52

@@ -118,7 +118,7 @@ def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None,
     bw, kh, kw, oc, ic = w.shape
     xn = x.permute(0, 3, 1, 2)
     z = _gather_pad(_zero_upsample(xn, up), pad0, pad0, (out_h - 1) * down + kh, (out_w - 1) * down + kw)
-    wt = w.permute(0, 3, 4, 1, 2)                                      # (Bw, OC, IC, KH, KW)
+    wt = w.permute(0, 3, 4, 1, 2).contiguous()                         # (Bw, OC, IC, KH, KW)
     if bw == 1:
         y = F.conv2d(z, wt[0], stride=down)
     else:
