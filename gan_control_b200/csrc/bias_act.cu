@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(const T* __restrict__
 // 16-byte vectorised variant: thread = (channel vector, pixel lane); per-thread partial sums, one
 // shared-memory reduction per block, one global atomic per (block, channel).
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) epilogue_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ y,
-                                                               T* __restrict__ gconv, const float* __restrict__ rowscale,
-                                                               const T* __restrict__ noise, const float* __restrict__ noise_w,
-                                                               const float* __restrict__ bias, float* __restrict__ gd,
-                                                               float* __restrict__ gb, float* __restrict__ gnw, int64_t hw,
-                                                               int c, int64_t pix_per_block, float slope, float gain) {
+__global__ void __launch_bounds__(256, 4) epilogue_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ y,
+                                                                  T* __restrict__ gconv, const float* __restrict__ rowscale,
+                                                                  const T* __restrict__ noise, const float* __restrict__ noise_w,
+                                                                  const float* __restrict__ bias, float* __restrict__ gd,
+                                                                  float* __restrict__ gb, float* __restrict__ gnw, int64_t hw,
+                                                                  int c, int64_t pix_per_block, float slope, float gain) {
     extern __shared__ float sred[];                   // [2][c] + 1
     float* red_b = sred;
     float* red_d = sred + c;
@@ -192,24 +192,24 @@ __global__ void __launch_bounds__(256) epilogue_bwd_vec_kernel(const T* __restri
     const int64_t p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
     const float nw = (noise && noise_w) ? *noise_w : 0.f;
     const float inv_gain = 1.f / gain, inv_gs = 1.f / (gain * slope);
-    float dv[VEC], bv[VEC], idv[VEC], sb[VEC], sd[VEC];
+    // Per-thread state is kept small (<= 64 registers, 4 blocks per SM) and two pixels' loads are issued before
+    // any use: the first version (76 registers, one vector pair in flight) was latency-bound -- ncu: 8.3
+    // long-scoreboard stalls per issue, 34 % warps active, 51 % of HBM (profiles/r01_streaming_kernels.md).
+    // sd accumulates gz*(u - nw*noise); the bias term and 1/d are applied once at the end:
+    //   sum gz*z = (sum gz*(u - nw*noise) - bias*sum gz) / d
+    float dv[VEC], sb[VEC], sd[VEC];
     float sn = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         dv[j] = rowscale ? rowscale[sample * c + v * VEC + j] : 1.f;
-        idv[j] = 1.f / dv[j];
-        bv[j] = bias ? bias[v * VEC + j] : 0.f;
         sb[j] = 0.f;
         sd[j] = 0.f;
     }
     if (pl < npl) {
-        for (int64_t p = p0 + pl; p < p1; p += npl) {
-            const int64_t e = (sample * hw + p) * c + (int64_t)v * VEC;
-            const Pack<T, VEC> yv = *reinterpret_cast<const Pack<T, VEC>*>(y + e);
-            const Pack<T, VEC> gv = *reinterpret_cast<const Pack<T, VEC>*>(gy + e);
-            const float nz = noise ? io<T>::ld(noise + sample * hw + p) : 0.f;
+        auto one = [&](const Pack<T, VEC>& yv, const Pack<T, VEC>& gv, float nz, int64_t e) {
             Pack<T, VEC> out;
             float gsum = 0.f;
+            const float nzw = nw * nz;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const float yy = io<T>::ld(&yv.v[j]);
@@ -217,16 +217,37 @@ __global__ void __launch_bounds__(256) epilogue_bwd_vec_kernel(const T* __restri
                 io<T>::st(&out.v[j], gz * dv[j]);
                 const float u = yy > 0.f ? yy * inv_gain : yy * inv_gs;
                 sb[j] += gz;
-                sd[j] += gz * (u - nw * nz - bv[j]) * idv[j];
+                sd[j] = fmaf(gz, u - nzw, sd[j]);
                 gsum += gz;
             }
-            sn += gsum * nz;
+            sn = fmaf(gsum, nz, sn);
             *reinterpret_cast<Pack<T, VEC>*>(gconv + e) = out;
+        };
+        const T* yb = y + sample * hw * c + (int64_t)v * VEC;
+        const T* gb_ = gy + sample * hw * c + (int64_t)v * VEC;
+        const T* nb = noise ? noise + sample * hw : nullptr;
+        const int64_t ebase = sample * hw * c + (int64_t)v * VEC;
+        int64_t p = p0 + pl;
+        for (; p + npl < p1; p += 2 * (int64_t)npl) {
+            const Pack<T, VEC> y0 = *reinterpret_cast<const Pack<T, VEC>*>(yb + p * c);
+            const Pack<T, VEC> g0 = *reinterpret_cast<const Pack<T, VEC>*>(gb_ + p * c);
+            const Pack<T, VEC> y1 = *reinterpret_cast<const Pack<T, VEC>*>(yb + (p + npl) * c);
+            const Pack<T, VEC> g1 = *reinterpret_cast<const Pack<T, VEC>*>(gb_ + (p + npl) * c);
+            const float n0 = nb ? io<T>::ld(nb + p) : 0.f;
+            const float n1 = nb ? io<T>::ld(nb + p + npl) : 0.f;
+            one(y0, g0, n0, ebase + p * c);
+            one(y1, g1, n1, ebase + (p + npl) * c);
+        }
+        for (; p < p1; p += npl) {
+            const Pack<T, VEC> y0 = *reinterpret_cast<const Pack<T, VEC>*>(yb + p * c);
+            const Pack<T, VEC> g0 = *reinterpret_cast<const Pack<T, VEC>*>(gb_ + p * c);
+            one(y0, g0, nb ? io<T>::ld(nb + p) : 0.f, ebase + p * c);
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
+            const float bvj = bias ? bias[v * VEC + j] : 0.f;
             atomicAdd(&red_b[v * VEC + j], sb[j]);
-            atomicAdd(&red_d[v * VEC + j], sd[j]);
+            atomicAdd(&red_d[v * VEC + j], (sd[j] - bvj * sb[j]) / dv[j]);
         }
         atomicAdd(red_n, sn);
     }

@@ -4,18 +4,24 @@
 // 16-byte vectorised along the contiguous channel axis, taps broadcast from shared memory.
 // The same kernel serves the adjoint (flip_kernel = 0, up <-> down), so it is closed under
 // differentiation.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace b200gan {
 
 constexpr int kMaxTaps = 16;
 
+}  // namespace b200gan
+#include "fir_epilogue.cuh"
+namespace b200gan {
+
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) upfirdn2d_kernel(
     const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ kernel, int n, int in_h,
     int in_w, int c, int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y, int pad0_x,
-    int flip, float gain, int64_t total_vec) {
+    int flip, float gain, int64_t total_vec, FirEpilogue ep) {
     __shared__ float taps[kMaxTaps * kMaxTaps];
     for (int i = threadIdx.x; i < kh * kw; i += blockDim.x) {
         int ky = i / kw, kx = i % kw;
@@ -55,6 +61,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(
                 for (int j = 0; j < VEC; ++j) acc[j] = fmaf(f, io<T>::ld(&v.v[j]), acc[j]);
             }
         }
+        if (ep.enabled) fir_epilogue<T, VEC>(ep, acc, b, ((int64_t)b * out_h + oy) * out_w + ox, c, ci * VEC);
         Pack<T, VEC> o;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) io<T>::st(&o.v[j], acc[j]);
@@ -117,7 +124,8 @@ template <typename T, int VEC, int KH, int KW, int ROWS>
 __global__ void __launch_bounds__(256) blur_rows_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                         const float* __restrict__ kernel, int n, int in_h, int in_w,
                                                         int c, int out_h, int out_w, int kh, int kw, int pad0_y,
-                                                        int pad0_x, int flip, float gain, int64_t total) {
+                                                        int pad0_x, int flip, float gain, int64_t total,
+                                                        FirEpilogue ep) {
     __shared__ float taps[KH * KW];
     __shared__ float tap_v[KH], tap_h[KW];
     __shared__ int separable;
@@ -214,6 +222,8 @@ __global__ void __launch_bounds__(256) blur_rows_kernel(const T* __restrict__ x,
             if (r >= KH - 1) {
                 const int orow = r - (KH - 1);
                 if (y0 + orow < out_h) {
+                    if (ep.enabled)
+                        fir_epilogue<T, VEC>(ep, acc[orow % KH], b, ((int64_t)b * out_h + y0 + orow) * out_w + ox, c, ci * VEC);
                     Pack<T, VEC> o;
 #pragma unroll
                     for (int j = 0; j < VEC; ++j) io<T>::st(&o.v[j], acc[orow % KH][j]);
@@ -228,7 +238,8 @@ __global__ void __launch_bounds__(256) blur_rows_kernel(const T* __restrict__ x,
 
 template <typename T, int VEC>
 static int launch_blur_rows(const void* x, void* y, const float* kernel, int n, int in_h, int in_w, int c, int out_h,
-                            int out_w, int kh, int kw, int pad0_y, int pad0_x, int flip, float gain, cudaStream_t st) {
+                            int out_w, int kh, int kw, int pad0_y, int pad0_x, int flip, float gain, const FirEpilogue& ep,
+                            cudaStream_t st) {
     constexpr int ROWS = 8;
     int64_t total = (int64_t)n * ((out_h + ROWS - 1) / ROWS) * out_w * (c / VEC);
     if (total == 0) return 0;
@@ -236,7 +247,7 @@ static int launch_blur_rows(const void* x, void* y, const float* kernel, int n, 
     int64_t cap = (int64_t)sm_count() * 64;
     if (blocks > cap) blocks = cap;
     blur_rows_kernel<T, VEC, 4, 4, ROWS><<<(unsigned)blocks, 256, 0, st>>>(
-        (const T*)x, (T*)y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip, gain, total);
+        (const T*)x, (T*)y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip, gain, total, ep);
     count_launch();
     return check_launch("upfirdn2d(blur)");
 }
@@ -244,7 +255,7 @@ static int launch_blur_rows(const void* x, void* y, const float* kernel, int n, 
 template <typename T, int VEC>
 static int launch_upfirdn(const void* x, void* y, const float* kernel, int n, int in_h, int in_w, int c,
                           int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y,
-                          int pad0_x, int flip, float gain, cudaStream_t st) {
+                          int pad0_x, int flip, float gain, const FirEpilogue& ep, cudaStream_t st) {
     int64_t total = (int64_t)n * out_h * out_w * (c / VEC);
     if (total == 0) return 0;
     int64_t blocks = cdiv(total, 256);
@@ -252,14 +263,18 @@ static int launch_upfirdn(const void* x, void* y, const float* kernel, int n, in
     if (blocks > cap) blocks = cap;
     upfirdn2d_kernel<T, VEC><<<(unsigned)blocks, 256, 0, st>>>(
         (const T*)x, (T*)y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down, pad0_y, pad0_x,
-        flip, gain, total);
+        flip, gain, total, ep);
     count_launch();
     return check_launch("upfirdn2d");
 }
 
 bool blur_tma_eligible(int dtype, int c, int kh, int kw, int up, int down, int out_h, int out_w, const void* x, const void* y);
 int blur_tma(const void* x, void* y, const float* taps, int n, int in_h, int in_w, int c, int out_h, int out_w, int kh,
-             int kw, int pad0_y, int pad0_x, int flip, float gain, cudaStream_t st);
+             int kw, int pad0_y, int pad0_x, int flip, float gain, const FirEpilogue& ep, cudaStream_t st);
+
+static int upfirdn2d_dispatch(const void* x, void* y, const float* kernel, int dtype, int n, int in_h, int in_w, int c,
+                              int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y, int pad0_x,
+                              int flip_kernel, float gain, const FirEpilogue& ep, cudaStream_t st);
 
 }  // namespace b200gan
 
@@ -267,16 +282,37 @@ extern "C" int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, in
                                  int in_w, int c, int out_h, int out_w, int kh, int kw, int up,
                                  int down, int pad0_y, int pad0_x, int flip_kernel, float gain,
                                  void* stream) {
-    using namespace b200gan;
+    b200gan::FirEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    return b200gan::upfirdn2d_dispatch(x, y, kernel, dtype, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down, pad0_y,
+                                       pad0_x, flip_kernel, gain, ep, (cudaStream_t)stream);
+}
+
+extern "C" int b200gan_upfirdn2d_act(const void* x, void* y, const float* kernel, int dtype, int n, int in_h, int in_w,
+                                     int c, int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y,
+                                     int pad0_x, int flip_kernel, float gain, const float* bias,
+                                     const float* rowscale, const void* noise, const float* noise_w, float slope,
+                                     float act_gain, void* stream) {
+    b200gan::FirEpilogue ep;
+    ep.bias = bias; ep.rowscale = rowscale; ep.noise = noise; ep.noise_w = noise_w;
+    ep.slope = slope; ep.gain = act_gain; ep.enabled = 1;
+    return b200gan::upfirdn2d_dispatch(x, y, kernel, dtype, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down, pad0_y,
+                                       pad0_x, flip_kernel, gain, ep, (cudaStream_t)stream);
+}
+
+namespace b200gan {
+static int upfirdn2d_dispatch(const void* x, void* y, const float* kernel, int dtype, int n, int in_h, int in_w, int c,
+                              int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y, int pad0_x,
+                              int flip_kernel, float gain, const FirEpilogue& ep, cudaStream_t st) {
     B200_REQUIRE(kh >= 1 && kw >= 1 && kh <= kMaxTaps && kw <= kMaxTaps, "upfirdn2d: kernel %dx%d not in 1..16", kh, kw);
     B200_REQUIRE(up >= 1 && down >= 1, "upfirdn2d: up/down must be >= 1");
     B200_REQUIRE(n >= 0 && c >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 0 && out_w >= 0, "upfirdn2d: bad shape");
-    cudaStream_t st = (cudaStream_t)stream;
     if (n > 0 && blur_tma_eligible(dtype, c, kh, kw, up, down, out_h, out_w, x, y))
-        return blur_tma(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip_kernel, gain, st);
+        return blur_tma(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip_kernel, gain, ep, st);
     return B200_DISPATCH(dtype, [&] {
         constexpr int V = 16 / sizeof(T);
-        if (c <= 4 && c > 1) {
+        bool aligned = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+        if (c <= 4 && c > 1 && !ep.enabled) {
             int64_t total = (int64_t)n * out_h * out_w;
             if (total == 0) return 0;
             int64_t blocks = cdiv(total, 256);
@@ -287,14 +323,14 @@ extern "C" int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, in
             count_launch();
             return check_launch("upfirdn2d(small c)");
         }
-        bool aligned = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
         if (aligned && up == 1 && down == 1 && kh <= 4 && kw <= 4 && out_h >= 8)
             return launch_blur_rows<T, V>(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x,
-                                          flip_kernel, gain, st);
+                                          flip_kernel, gain, ep, st);
         if (aligned)
             return launch_upfirdn<T, V>(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down,
-                                        pad0_y, pad0_x, flip_kernel, gain, st);
+                                        pad0_y, pad0_x, flip_kernel, gain, ep, st);
         return launch_upfirdn<T, 1>(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down,
-                                    pad0_y, pad0_x, flip_kernel, gain, st);
+                                    pad0_y, pad0_x, flip_kernel, gain, ep, st);
     });
 }
+}  // namespace b200gan

@@ -31,6 +31,7 @@ _SIGNATURES = {
     'b200gan_last_error': ([], _c.c_char_p),
     'b200gan_launch_count': ([], _c.c_uint64),
     'b200gan_upfirdn2d': ([_vp, _vp, _vp, _i] + [_i] * 6 + [_i] * 7 + [_f, _vp], _i),
+    'b200gan_upfirdn2d_act': ([_vp, _vp, _vp, _i] + [_i] * 6 + [_i] * 7 + [_f, _vp, _vp, _vp, _vp, _f, _f, _vp], _i),
     'b200gan_bias_act_fwd': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
     'b200gan_bias_act_bwd': ([_vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i64, _f, _f, _vp], _i),
     'b200gan_epilogue_bwd': ([_vp] * 10 + [_i, _i64, _i64, _i64, _f, _f, _vp], _i),
@@ -110,8 +111,9 @@ def _f32c(t):
 
 
 # ---------------------------------------------------------------------------------------------
-def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0):
-    """x: contiguous (N,H,W,C).  Returns contiguous (N,out_h,out_w,C)."""
+def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0, epilogue=None):
+    """x: contiguous (N,H,W,C).  Returns contiguous (N,out_h,out_w,C).
+    epilogue = (bias, rowscale, noise, noise_w, slope, act_gain): the StyledConv tail fused on the filter output."""
     _cuda(x, taps)
     assert x.ndim == 4 and x.is_contiguous()
     n, h, w, c = x.shape
@@ -120,9 +122,21 @@ def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0):
     if y.numel() == 0:
         return y
     with torch.cuda.device(x.device):
-        _check(lib().b200gan_upfirdn2d(_ptr(x), _ptr(y), _ptr(taps), _dt(x), n, h, w, c, out_h, out_w,
-                                       taps.shape[0], taps.shape[1], up, down, pad0_y, pad0_x, int(flip),
-                                       float(gain), _stream()), 'upfirdn2d')
+        if epilogue is None:
+            _check(lib().b200gan_upfirdn2d(_ptr(x), _ptr(y), _ptr(taps), _dt(x), n, h, w, c, out_h, out_w,
+                                           taps.shape[0], taps.shape[1], up, down, pad0_y, pad0_x, int(flip),
+                                           float(gain), _stream()), 'upfirdn2d')
+        else:
+            bias, rowscale, noise, noise_w, slope, act_gain = epilogue
+            _cuda(bias, rowscale, noise, noise_w)
+            bias, rowscale, noise_w = _f32c(bias), _f32c(rowscale), _f32c(noise_w)
+            if noise is not None:
+                noise = noise.detach().to(x.dtype).contiguous()
+                assert noise.numel() == n * out_h * out_w
+            _check(lib().b200gan_upfirdn2d_act(_ptr(x), _ptr(y), _ptr(taps), _dt(x), n, h, w, c, out_h, out_w,
+                                               taps.shape[0], taps.shape[1], up, down, pad0_y, pad0_x, int(flip),
+                                               float(gain), _ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w),
+                                               float(slope), float(act_gain), _stream()), 'upfirdn2d_act')
     return y
 
 

@@ -186,9 +186,10 @@ class ModulatedConv2d(nn.Module):                                             # 
             x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
         return x, wk, d
 
-    def raw(self, input, style):
+    def raw(self, input, style, blur=True):
         """Un-demodulated convolution and the demodulation coefficients: (z, d) with
-        ModulatedConv2d(x, style) == z * d[:, :, None, None]."""
+        ModulatedConv2d(x, style) == z * d[:, :, None, None].  blur=False leaves the upsampling layer's Blur
+        (gm.py:307) to the caller (StyledConv fuses it with its epilogue)."""
         height, width = input.shape[2], input.shape[3]
         x, wk, d = self.operands(input, style)
         k = self.kernel_size
@@ -196,7 +197,8 @@ class ModulatedConv2d(nn.Module):                                             # 
             # conv_transpose2d(stride 2, padding 0) in gather form (gm.py:301-306) ...
             z = ops.conv_gather(x, wk.flip(3, 4), up=2, down=1, pad0=k - 1,
                                 out_hw=((height - 1) * 2 + k, (width - 1) * 2 + k))
-            z = self.blur(z)                                                  # ... then Blur (gm.py:307)
+            if blur:
+                z = self.blur(z)                                              # ... then Blur (gm.py:307)
         else:
             z = ops.conv_gather(x, wk, 1, 1, self.padding)
         return z, d
@@ -244,12 +246,13 @@ class StyledConv(nn.Module):                                                  # 
     def forward(self, input, style, noise=None):
         conv = self.conv
         if conv.upsample:
-            # transposed conv -> blur -> [demod scale + noise + bias + leaky-ReLU*sqrt(2)] in one pass
-            z, d = conv.raw(input, style)
+            # transposed conv -> [blur + demod scale + noise + bias + leaky-ReLU*sqrt(2)] in one pass
+            z, d = conv.raw(input, style, blur=False)
+            oh, ow = input.shape[2] * 2, input.shape[3] * 2
             if noise is None:
-                noise = z.new_empty(z.shape[0], 1, z.shape[2], z.shape[3]).normal_()
-            return ops.mod_epilogue(z, d, noise, self.noise.weight, self.activate.bias,
-                                    self.activate.negative_slope, self.activate.scale)
+                noise = z.new_empty(z.shape[0], 1, oh, ow).normal_()
+            return ops.fir_epilogue(z, conv.blur.kernel, conv.blur.pad, d, noise, self.noise.weight, self.activate.bias,
+                                    slope=self.activate.negative_slope, gain=self.activate.scale)
         # plain layer: the whole StyledConv is ONE kernel (epilogue fused into the convolution)
         x, wk, d = conv.operands(input, style)
         if noise is None:
@@ -480,7 +483,8 @@ class Generator(nn.Module):                                                   # 
     @staticmethod
     def g_path_regularize_grad(fake_img, latents, dim_1_shape=1):                             # gm.py:803-811
         noise = torch.randn_like(fake_img) / math.sqrt(fake_img.shape[2] * fake_img.shape[3] * dim_1_shape)
-        grad, = torch.autograd.grad(outputs=(fake_img * noise).sum(), inputs=latents, create_graph=True)
+        with ops.data_grads_only():
+            grad, = torch.autograd.grad(outputs=(fake_img * noise).sum(), inputs=latents, create_graph=True)
         return grad
 
 

@@ -50,6 +50,90 @@ def _is_nhwc(x):
 
 
 # ---------------------------------------------------------------------------------------------
+# regulariser backward mode
+# ---------------------------------------------------------------------------------------------
+_DATA_GRADS_ONLY = False
+
+
+class data_grads_only:
+    """Context for the regularisers' INNER backward: `autograd.grad(pred.sum(), real_img, create_graph=True)`
+    (R1, generator_trainer.py:713-716) and `autograd.grad((img*noise).sum(), latents, create_graph=True)`
+    (path length, :606-608) only ask for the gradient w.r.t. an INPUT, but a custom Function cannot see that: its
+    needs_input_grad is fixed at forward time, so it would also compute (and record for double backward) every
+    parameter gradient -- a full set of weight-gradient convolutions and bias / noise reductions that autograd.grad
+    then throws away.  Inside this context the Functions skip gradients of quantities that depend on parameters
+    only (shared convolution weights, biases, noise strengths); gradients that can reach the input -- activations,
+    per-sample (style-modulated) weights, demodulation coefficients, styles -- are computed as usual.  The result
+    of the enclosed autograd.grad call is unchanged.  A module-level flag: backward runs on autograd's own thread."""
+
+    def __enter__(self):
+        global _DATA_GRADS_ONLY
+        self.prev, _DATA_GRADS_ONLY = _DATA_GRADS_ONLY, True
+
+    def __exit__(self, *exc):
+        global _DATA_GRADS_ONLY
+        _DATA_GRADS_ONLY = self.prev
+
+
+def _param_grads():
+    return not _DATA_GRADS_ONLY
+
+
+# ---------------------------------------------------------------------------------------------
+# per-(sample, channel) scale and dot product: the differentiable pieces of the epilogue backward
+# ---------------------------------------------------------------------------------------------
+class _RowScale(Function):
+    """y[n,c,h,w] = x[n,c,h,w] * d[n,c] in one pass (d fp32); closed under differentiation with _RowDot."""
+
+    @staticmethod
+    def forward(ctx, x, d):
+        ctx.save_for_backward(x, d)
+        return _nchw(K.bias_act_fwd(_nhwc(x), None, d, None, None, 1.0, 1.0))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, d = ctx.saved_tensors
+        gx = _RowScale.apply(g, d) if ctx.needs_input_grad[0] else None
+        gd = _RowDot.apply(g, x).to(d.dtype) if ctx.needs_input_grad[1] else None
+        return gx, gd
+
+
+class _RowDot(Function):
+    """out[n,c] = sum_{h,w} a[n,c,h,w] * b[n,c,h,w], accumulated and returned in fp32 (one pass over a and b)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return K.reduce_nhwc(_nhwc(a), _nhwc(b), per_channel=False, per_sample_channel=True)[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = _RowScale.apply(b, g).to(a.dtype) if ctx.needs_input_grad[0] else None
+        gb = _RowScale.apply(a, g).to(b.dtype) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def _epilogue_grads_graph(gy, y, z, d, noise, noise_w, bias, need_d, need_noise, need_nw, need_b, slope, gain):
+    """Differentiable (create_graph) backward of y = gain*lrelu(z*d + nw*noise + bias) given the recomputed z:
+    returns (gconv, gd, gnoise, gnw, gb).  Full-size work goes through _BiasActGrad / _RowScale / _RowDot (one
+    kernel each); parameter-only gradients are skipped inside `data_grads_only`."""
+    gz = _BiasActGrad.apply(gy, y, slope, gain)
+    gconv = gz if d is None else _RowScale.apply(gz, d)
+    gd = gnoise = gnw = gb = None
+    if d is not None and need_d:
+        gd = _RowDot.apply(gz, z).to(d.dtype)
+    if noise is not None and need_noise:
+        gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
+    if _param_grads():
+        if noise is not None and need_nw:
+            gnw = (up32(gz).sum(1, keepdim=True) * up32(noise)).sum().reshape(noise_w.shape).to(noise_w.dtype)
+        if bias is not None and need_b:
+            gb = up32(gz).sum((0, 2, 3)).to(bias.dtype)
+    return gconv, gd, gnoise, gnw, gb
+
+
+# ---------------------------------------------------------------------------------------------
 # upfirdn2d                                  (gan_model.py:45-50 / pytorch_upfirdn2d.py:9-51)
 # ---------------------------------------------------------------------------------------------
 class _UpFirDn2d(Function):
@@ -126,7 +210,7 @@ class _BiasAct(Function):
         y, = ctx.saved_tensors
         gx = _BiasActGrad.apply(gy, y, *ctx.cfg)
         gb = None
-        if ctx.bias_dtype is not None and ctx.needs_input_grad[1]:
+        if ctx.bias_dtype is not None and ctx.needs_input_grad[1] and _param_grads():
             dims = [d for d in range(gx.ndim) if d != 1]
             gb = up32(gx).sum(dims).to(ctx.bias_dtype)
         return gx, gb, None, None
@@ -155,22 +239,14 @@ class _ModEpilogue(Function):
         x, d, noise, noise_w, y = ctx.saved_tensors
         slope, gain = ctx.cfg
         need = ctx.needs_input_grad
-        gz = _BiasActGrad.apply(gy, y, slope, gain)          # d loss / d (pre-activation)
         gx = gd = gnoise = gnw = gb = None
         if torch.is_grad_enabled():
-            # create_graph=True (R1 / path-length): plain differentiable torch arithmetic on gz
-            gz32 = up32(gz)
-            if need[0]:
-                gx = gz if d is None else (gz32 * up32(d[:, :, None, None])).to(gz.dtype)
-            if d is not None and need[1]:
-                gd = (gz32 * up32(x)).sum((2, 3)).to(d.dtype)
-            if noise is not None and need[2]:
-                gnoise = (gz32.sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
-            if noise is not None and need[3]:
-                gnw = (gz32.sum(1, keepdim=True) * up32(noise)).sum().reshape(noise_w.shape).to(noise_w.dtype)
-            if ctx.bias_dtype is not None and need[4]:
-                gb = gz32.sum((0, 2, 3)).to(ctx.bias_dtype)
+            # create_graph=True (R1 / path-length): differentiable kernels
+            bias_like = None if ctx.bias_dtype is None else torch.empty(0, dtype=ctx.bias_dtype, device=gy.device)
+            gx, gd, gnoise, gnw, gb = _epilogue_grads_graph(gy, y, x, d, noise, noise_w, bias_like, need[1], need[2],
+                                                            need[3], need[4], slope, gain)
         else:
+            gz = _BiasActGrad.apply(gy, y, slope, gain)          # d loss / d (pre-activation)
             # first-order only: ONE fused pass (kernels.epilogue_bwd) instead of four
             gconv, gd_, gb_, gnw_ = K.epilogue_bwd(_nhwc(gy), _nhwc(y), d, noise, noise_w if noise is not None else None,
                                                    None, slope, gain, want_gd=d is not None and need[1],
@@ -192,6 +268,63 @@ class _ModEpilogue(Function):
 
 def mod_epilogue(x, d=None, noise=None, noise_w=None, bias=None, slope=0.2, gain=SQRT2):
     return _ModEpilogue.apply(x, d, noise, noise_w, bias, slope, gain)
+
+
+class _FirEpilogue(Function):
+    """y = gain*lrelu(upfirdn2d(x)*d[b,c] + nw*noise + bias[c]) in ONE kernel: the upsampling StyledConv's
+    Blur (gm.py:307) with its demodulation scale / NoiseInjection / FusedLeakyReLU tail applied to the filter
+    output in registers, so the blurred tensor never reaches HBM before its activation.
+    Backward: first order = fused epilogue backward (from the saved output) + the FIR adjoint; under
+    create_graph the filter output is recomputed and the differentiable formulas are used."""
+
+    @staticmethod
+    def forward(ctx, x, taps, d, noise, noise_w, bias, up, down, pad0, out_h, out_w, slope, gain):
+        y = _nchw(K.upfirdn2d(_nhwc(x), taps, up, down, pad0, pad0, out_h, out_w, True,
+                              epilogue=(bias, d, noise, noise_w, slope, gain)))
+        ctx.cfg = (up, down, pad0, x.shape[2], x.shape[3], out_h, out_w, slope, gain)
+        ctx.save_for_backward(x, taps, d, noise, noise_w, bias, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, taps, d, noise, noise_w, bias, y = ctx.saved_tensors
+        up, down, pad0, h, wd, oh, ow, slope, gain = ctx.cfg
+        need = ctx.needs_input_grad
+        kh, kw = taps.shape
+        gx = gd = gnoise = gnw = gb = None
+        if torch.is_grad_enabled():
+            z = None
+            if d is not None and need[2]:
+                z = _UpFirDn2d.apply(x, taps, up, down, pad0, pad0, oh, ow, True)      # recompute, differentiable
+            gfir, gd, gnoise, gnw, gb = _epilogue_grads_graph(gy, y, z, d, noise, noise_w, bias, need[2], need[3],
+                                                              need[4], need[5], slope, gain)
+        else:
+            gfir, gd_, gb_, gnw_ = K.epilogue_bwd(_nhwc(gy), _nhwc(y), d, noise, noise_w if noise is not None else None,
+                                                  bias, slope, gain, want_gd=d is not None and need[2],
+                                                  want_gb=bias is not None and need[5],
+                                                  want_gnw=noise is not None and need[4])
+            gfir = _nchw(gfir)
+            if gd_ is not None:
+                gd = gd_.to(d.dtype)
+            if gb_ is not None:
+                gb = gb_.to(bias.dtype)
+            if gnw_ is not None:
+                gnw = gnw_.reshape(noise_w.shape).to(noise_w.dtype)
+            if noise is not None and need[3]:
+                gz = _BiasActGrad.apply(gy, y, slope, gain)
+                gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
+        if need[0]:
+            gx = _UpFirDn2d.apply(gfir, taps, down, up, kh - 1 - pad0, kw - 1 - pad0, h, wd, False)
+        return gx, None, gd, gnoise, gnw, gb, None, None, None, None, None, None, None
+
+
+def fir_epilogue(x, kernel, pad, d=None, noise=None, noise_w=None, bias=None, up=1, down=1, slope=0.2, gain=SQRT2):
+    """upfirdn2d(x, kernel, up, down, pad) followed by the StyledConv tail, fused (see _FirEpilogue)."""
+    n, c, h, w = x.shape
+    kh, kw = kernel.shape
+    out_h = (h * up + pad[0] + pad[1] - kh) // down + 1
+    out_w = (w * up + pad[0] + pad[1] - kw) // down + 1
+    return _FirEpilogue.apply(x, kernel, d, noise, noise_w, bias, up, down, pad[0], out_h, out_w, slope, gain)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -222,7 +355,7 @@ class _ConvGather(Function):
         if ctx.needs_input_grad[0]:
             wt = w.flip(3, 4).transpose(1, 2)                  # taps reversed, OC <-> IC
             gx = _ConvGather.apply(gy, wt, down, up, kh - 1 - pad0, h, wd)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and (w.shape[0] > 1 or _param_grads()):
             gw = _ConvWgrad.apply(x, gy, up, down, pad0, kh, kw, w.shape[0] > 1).to(w.dtype)
         return gx, gw, None, None, None, None, None
 
@@ -273,18 +406,11 @@ class _ConvEpilogue(Function):
         kh, kw = w.shape[3], w.shape[4]
         gx = gw = gd = gnoise = gnw = gb = None
         if torch.is_grad_enabled():
-            z = _ConvGather.apply(x, w, up, down, pad0, oh, ow)                  # recompute, differentiable
-            gz = _BiasActGrad.apply(gy, y, slope, gain)
-            gz32 = up32(gz)
-            gconv = gz if d is None else (gz32 * up32(d)[:, :, None, None]).to(gz.dtype)
+            z = None
             if d is not None and need[2]:
-                gd = (gz32 * up32(z)).sum((2, 3)).to(d.dtype)
-            if noise is not None and need[3]:
-                gnoise = (gz32.sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
-            if noise is not None and need[4]:
-                gnw = (gz32.sum(1, keepdim=True) * up32(noise)).sum().reshape(noise_w.shape).to(noise_w.dtype)
-            if bias is not None and need[5]:
-                gb = gz32.sum((0, 2, 3)).to(bias.dtype)
+                z = _ConvGather.apply(x, w, up, down, pad0, oh, ow)              # recompute, differentiable
+            gconv, gd, gnoise, gnw, gb = _epilogue_grads_graph(gy, y, z, d, noise, noise_w, bias, need[2], need[3],
+                                                               need[4], need[5], slope, gain)
         else:
             gconv, gd_, gb_, gnw_ = K.epilogue_bwd(_nhwc(gy), _nhwc(y), d, noise, noise_w if noise is not None else None,
                                                    bias, slope, gain, want_gd=d is not None and need[2],
@@ -302,7 +428,7 @@ class _ConvEpilogue(Function):
                 gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
         if need[0]:
             gx = _ConvGather.apply(gconv, w.flip(3, 4).transpose(1, 2), down, up, kh - 1 - pad0, h, wd)
-        if need[1]:
+        if need[1] and (w.shape[0] > 1 or _param_grads()):        # a shared weight depends on parameters only
             gw = _ConvWgrad.apply(x, gconv, up, down, pad0, kh, kw, w.shape[0] > 1).to(w.dtype)
         return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None
 
@@ -393,9 +519,9 @@ class _EqualLinear(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = _Gemm.apply(gz32, w, False, False, scale).to(x.dtype)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _param_grads():
             gw = _Gemm.apply(gz32, up32(x), True, False, scale).to(w.dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and _param_grads():
             gb = gz32.sum(0) * bias_mul
         return gx, gw, gb, None, None, None
 

@@ -26,7 +26,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import kernels as K
-from .ops import up32
+from .ops import data_grads_only, up32
 
 
 # ---------------------------------------------------------------------------------------------
@@ -41,7 +41,8 @@ def d_logistic_loss(real_pred, fake_pred):
 
 
 def d_r1_loss(real_pred, real_img):
-    grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    with data_grads_only():
+        grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
     return up32(grad_real).pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
 
 
@@ -49,7 +50,8 @@ def g_path_regularize(fake_img, latents, mean_path_length, decay=0.01, pl_noise=
     if pl_noise is None:
         pl_noise = torch.randn_like(fake_img)
     pl_noise = pl_noise / math.sqrt(fake_img.shape[2] * fake_img.shape[3])
-    grad, = torch.autograd.grad(outputs=(fake_img * pl_noise).sum(), inputs=latents, create_graph=True)
+    with data_grads_only():
+        grad, = torch.autograd.grad(outputs=(fake_img * pl_noise).sum(), inputs=latents, create_graph=True)
     path_lengths = torch.sqrt(grad.pow(2).sum(2).mean(1))
     local_mean = path_lengths.mean()
     if all_reduce_mean is None:

@@ -57,6 +57,18 @@ int b200gan_upfirdn2d(const void* x, void* y, const float* kernel, int dtype,
                       int kh, int kw, int up, int down, int pad0_y, int pad0_x,
                       int flip_kernel, float gain, void* stream);
 
+/* upfirdn2d with the StyledConv tail fused on the filter output (the upsampling
+ * StyledConv: `Blur` gm.py:307, demodulation scale gm.py:288-289, NoiseInjection
+ * gm.py:340-345, FusedLeakyReLU gm.py:32-35 -- four extra passes in the reference):
+ *   y = act_gain * lrelu(fir(x) * rowscale[n][c] + noise_w * noise[n][oy][ox] + bias[c]).
+ * bias / rowscale / noise may be NULL; `gain` still scales the taps.            */
+int b200gan_upfirdn2d_act(const void* x, void* y, const float* kernel, int dtype,
+                          int n, int in_h, int in_w, int c, int out_h, int out_w,
+                          int kh, int kw, int up, int down, int pad0_y, int pad0_x,
+                          int flip_kernel, float gain, const float* bias,
+                          const float* rowscale, const void* noise, const float* noise_w,
+                          float slope, float act_gain, void* stream);
+
 /* ---- bias + noise + scaled leaky-ReLU -----------------------------------
  * Replaces `fused_leaky_relu` / `FusedLeakyReLU` gm.py:25-41, the noise add of
  * `NoiseInjection` gm.py:340-345 and the demodulation scale of gm.py:288-289

@@ -31,14 +31,18 @@ def _zero_upsample(x, up):
     return z
 
 
-def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0):
+def upfirdn2d(x, taps, up, down, pad0_y, pad0_x, out_h, out_w, flip, gain=1.0, epilogue=None):
     xn = x.permute(0, 3, 1, 2)
     c = xn.shape[1]
     kh, kw = taps.shape
     z = _gather_pad(_zero_upsample(xn, up), pad0_y, pad0_x, (out_h - 1) * down + kh, (out_w - 1) * down + kw)
     f = (taps.flip(0, 1) if flip else taps).to(x.dtype) * gain
     y = F.conv2d(z, f[None, None].expand(c, 1, kh, kw), groups=c, stride=down)
-    return y.permute(0, 2, 3, 1).contiguous()
+    y = y.permute(0, 2, 3, 1).contiguous()
+    if epilogue is not None:
+        bias, rowscale, noise, noise_w, slope, act_gain = epilogue
+        y = bias_act_fwd(y, bias, rowscale, noise, noise_w, slope, act_gain)
+    return y
 
 
 def _bcast(v, x, planar, kind):

@@ -75,6 +75,14 @@ if not flt or flt in 'blur':
         x = torch.randn(B, h, h, c, device=dev).to(bf)
         report(f'blur 4x4 pad1 {c}ch @{h}', timeit(lambda: K.upfirdn2d(x, taps, 1, 1, 1, 1, h - 1, h - 1, True)), 0, 2.0 * B * c * (h * h + (h - 1) ** 2))
         del x
+    for h, c in [(1024, 32), (512, 64), (256, 128)]:
+        # ResBlock.skip: blur decimated by 2 (forward) and its adjoint (zero-insert x2, reversed taps)
+        x = torch.randn(B, h, h, c, device=dev).to(bf)
+        g = torch.randn(B, h // 2, h // 2, c, device=dev).to(bf)
+        t1 = taps / 4
+        report(f'blur-down 4x4 pad1 down2 {c}ch @{h}->{h // 2}', timeit(lambda: K.upfirdn2d(x, t1, 1, 2, 1, 1, h // 2, h // 2, True)), 0, 2.0 * B * c * (h * h + (h // 2) ** 2))
+        report(f'blur-down adjoint up2 {c}ch @{h // 2}->{h}', timeit(lambda: K.upfirdn2d(g, t1, 2, 1, 2, 2, h, h, False)), 0, 2.0 * B * c * (h * h + (h // 2) ** 2))
+        del x, g
     x = torch.randn(B, 512, 512, 3, device=dev).to(bf)
     report('skip upsample x2 3ch @512->1024', timeit(lambda: K.upfirdn2d(x, taps, 2, 1, 2, 2, 1024, 1024, True)), 0, 2.0 * B * 3 * (512 * 512 + 1024 * 1024))
 

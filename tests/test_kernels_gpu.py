@@ -48,6 +48,29 @@ def test_upfirdn2d(cfg, dt):
 
 
 @pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('cfg', [
+    # n, h, w, c, kh, up, down, pad0, out_h, out_w   (generic, blur_rows and TMA kernels; decimating / interpolating)
+    (2, 9, 9, 8, 4, 1, 1, 1, 8, 8), (2, 33, 33, 32, 4, 1, 1, 1, 32, 32), (2, 65, 65, 64, 4, 1, 1, 1, 64, 64),
+    (1, 129, 69, 96, 4, 1, 1, 1, 128, 68), (2, 16, 16, 24, 4, 1, 2, 1, 8, 8), (2, 8, 8, 16, 4, 2, 1, 2, 16, 16),
+    (3, 5, 5, 5, 4, 1, 1, 1, 4, 4),
+])
+def test_upfirdn2d_act(cfg, dt):
+    """FIR with the StyledConv tail fused on its output == FIR stand-in followed by the bias-act stand-in"""
+    n, h, w, c, k, up, down, pad0, oh, ow = cfg
+    x, xr = prep(rnd(1, n, h, w, c), dt)
+    taps = rnd(2, k, k).float()
+    bias, rs, nw = rnd(4, c).float(), (rnd(5, n, c).abs() + 0.5).float(), torch.tensor([0.7])
+    noise, noiser = prep(rnd(6, n, oh * ow), dt)
+    y = K.upfirdn2d(x, taps.cuda(), up, down, pad0, pad0, oh, ow, True, 1.5,
+                    epilogue=(bias.cuda(), rs.cuda(), noise, nw.cuda(), 0.2, 2 ** 0.5))
+    yr = R.upfirdn2d(xr, taps.double(), up, down, pad0, pad0, oh, ow, True, 1.5,
+                     epilogue=(bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5))
+    close(y, yr, dt)
+    y2 = K.upfirdn2d(x, taps.cuda(), up, down, pad0, pad0, oh, ow, True, 1.5, epilogue=(None, None, None, None, 0.2, 2.0))
+    close(y2, R.upfirdn2d(xr, taps.double(), up, down, pad0, pad0, oh, ow, True, 1.5, epilogue=(None, None, None, None, 0.2, 2.0)), dt)
+
+
+@pytest.mark.parametrize('dt', DTYPES)
 @pytest.mark.parametrize('shape,planar', [((3, 5, 7, 16), False), ((2, 4, 4, 3), False), ((2, 5, 6, 6), True), ((4, 24), True)])
 def test_bias_act(shape, planar, dt):
     x, xr = prep(rnd(3, *shape), dt)
