@@ -272,6 +272,11 @@ bool blur_tma_eligible(int dtype, int c, int kh, int kw, int up, int down, int o
 int blur_tma(const void* x, void* y, const float* taps, int n, int in_h, int in_w, int c, int out_h, int out_w, int kh,
              int kw, int pad0_y, int pad0_x, int flip, float gain, const FirEpilogue& ep, cudaStream_t st);
 
+bool fir_resample_tma_eligible(int dtype, int c, int kh, int kw, int up, int down, int out_h, int out_w, const void* x,
+                               const void* y);
+int fir_resample_tma(const void* x, void* y, const float* taps, int n, int in_h, int in_w, int c, int out_h, int out_w,
+                     int kh, int kw, int up, int down, int pad0_y, int pad0_x, int flip, float gain, cudaStream_t st);
+
 static int upfirdn2d_dispatch(const void* x, void* y, const float* kernel, int dtype, int n, int in_h, int in_w, int c,
                               int out_h, int out_w, int kh, int kw, int up, int down, int pad0_y, int pad0_x,
                               int flip_kernel, float gain, const FirEpilogue& ep, cudaStream_t st);
@@ -309,6 +314,9 @@ static int upfirdn2d_dispatch(const void* x, void* y, const float* kernel, int d
     B200_REQUIRE(n >= 0 && c >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 0 && out_w >= 0, "upfirdn2d: bad shape");
     if (n > 0 && blur_tma_eligible(dtype, c, kh, kw, up, down, out_h, out_w, x, y))
         return blur_tma(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip_kernel, gain, ep, st);
+    if (n > 0 && !ep.enabled && fir_resample_tma_eligible(dtype, c, kh, kw, up, down, out_h, out_w, x, y))
+        return fir_resample_tma(x, y, kernel, n, in_h, in_w, c, out_h, out_w, kh, kw, up, down, pad0_y, pad0_x,
+                                flip_kernel, gain, st);
     return B200_DISPATCH(dtype, [&] {
         constexpr int V = 16 / sizeof(T);
         bool aligned = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);

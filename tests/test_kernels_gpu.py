@@ -38,6 +38,10 @@ def close(out, ref, dt, what=''):
     (2, 33, 33, 32, 4, 1, 1, 1, 32, 32, True), (2, 5, 5, 24, 4, 1, 2, 1, 2, 2, False),
     (2, 37, 41, 64, 4, 1, 1, 2, 38, 42, False), (1, 20, 50, 128, 3, 1, 1, 1, 20, 50, True), (2, 65, 65, 96, 4, 1, 1, 1, 64, 64, True),
     (1, 130, 70, 32, 4, 1, 1, 1, 129, 69, True),
+    # decimating / interpolating TMA kernels (ResBlock.skip and its adjoint): even / odd pads, ragged edges, 3 taps
+    (2, 64, 64, 32, 4, 1, 2, 1, 32, 32, True), (1, 66, 70, 64, 4, 1, 2, 1, 33, 35, False), (2, 40, 40, 96, 4, 1, 2, 2, 21, 21, True),
+    (1, 37, 45, 32, 3, 1, 2, 0, 18, 22, True), (2, 32, 32, 32, 4, 2, 1, 2, 64, 64, False), (1, 33, 35, 64, 4, 2, 1, 2, 66, 70, True),
+    (2, 20, 24, 128, 4, 2, 1, 1, 38, 46, False), (1, 17, 19, 32, 3, 2, 1, 1, 33, 37, True), (1, 16, 16, 32, 4, 2, 1, 3, 35, 35, True),
 ])
 def test_upfirdn2d(cfg, dt):
     n, h, w, c, k, up, down, pad0, oh, ow, flip = cfg
