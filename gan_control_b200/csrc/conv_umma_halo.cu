@@ -27,6 +27,7 @@ struct HaloParams {
     int B, H, W, OC, IC;                 // stride-1 conv: output extent == (H + 2*pad - k + 1) passed as OH/OW
     int OH, OW, k, pad0;
     int tiles_h, tiles_w, total_tiles;
+    FastDiv div_img, div_tw;             // tile -> (sample, tile in image), tile in image -> (tile row, tile column)
     int BN, kchunks, kc, row_bytes, layout;
     int PW, RH;                          // buffer row pitch (pixels) and rows
     int w_per_sample;
@@ -41,6 +42,9 @@ struct HaloParams {
     __nv_bfloat16* y;
 };
 
+// KDIM = 3 or 1 (kernel size), ROWB = 128 or 64 (bytes per pixel row of a channel chunk = swizzle width): both
+// compile-time so that the MMA-issuing warp's tap loop is straight-line code with immediate descriptor offsets.
+template <int KDIM, int ROWB>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ HaloParams p) {
@@ -72,17 +76,18 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int taps = p.k * p.k;
-    const int tiles_per_img = p.tiles_h * p.tiles_w;
+    constexpr int taps = KDIM * KDIM;
 
     if (warp == 0) {
         // ================= TMA producer (whole warp, elected lane issues) =================
         int stage = 0, par = 0, key = -1;
         int last_stage = -1, last_par = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int n = tile / tiles_per_img, t = tile % tiles_per_img;
-            const int h0 = (t / p.tiles_w) * kHTH, w0 = (t % p.tiles_w) * kHTW;
-            const int wkey = p.w_per_sample ? n : 0;
+            uint32_t n, t, th, tw;
+            p.div_img.divmod((uint32_t)tile, n, t);
+            p.div_tw.divmod(t, th, tw);
+            const int h0 = (int)th * kHTH, w0 = (int)tw * kHTW;
+            const int wkey = p.w_per_sample ? (int)n : 0;
             if (wkey != key) {
                 // drain: every MMA that reads the resident weights has completed once the most recently
                 // filled activation stage has been released
@@ -100,7 +105,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 mbar_wait(aempty + stage, par ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(afull + stage, (uint32_t)p.a_stage_bytes);
-                    tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, c * p.kc, w0 - p.pad0, h0 - p.pad0, n);
+                    tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, c * p.kc, w0 - p.pad0, h0 - p.pad0, (int)n);
                 }
                 __syncwarp();
                 last_stage = stage; last_par = par;
@@ -109,20 +114,25 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp, elected lane issues) =================
+        // ncu on the first version (run-time tap loop): this ONE warp bounds the kernel -- 266 dependent, mostly
+        // uniform-datapath instructions per tile at ~7 clk each = the whole 1820-clk tile period, tensor pipe 17 %
+        // active, the TMA producer and the epilogue warps waiting on it (profiles/r01_halo_mma_issue.md).  Now the
+        // taps are unrolled with immediate descriptor offsets and the tile decode is a multiply-high.
         const uint32_t idesc = instr_desc_bf16(128, p.BN, 0, 0);
+        constexpr uint32_t PW = KDIM == 1 ? 8 : 16;
+        constexpr uint32_t ROW_UNITS = ROWB >> 4;                        // descriptor units (16 B) per pixel
+        constexpr int KSTEPS = ROWB / 32;                                // K = 16 elements = 32 B per MMA
         // A: one 8-pixel swizzle atom per tile row, atoms PW pixels apart; the swizzle is a function of the
         // absolute shared-memory address, so tap-shifted start addresses need no base-offset field
-        const uint32_t a_hi = desc_hi((uint32_t)(p.PW * p.row_bytes), (uint32_t)p.layout);
-        const uint32_t b_hi = desc_hi(8u * (uint32_t)p.row_bytes, (uint32_t)p.layout);
+        const uint32_t a_hi = desc_hi(PW * ROWB, (uint32_t)p.layout);
+        const uint32_t b_hi = desc_hi(8u * ROWB, (uint32_t)p.layout);
         const uint32_t w_lo0 = desc_lo(smem_u32(w_buf), 16), w_inc = (uint32_t)p.w_tile_bytes >> 4;
         const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), 16), a_inc = (uint32_t)p.a_stage_bytes >> 4;
-        const uint32_t row_units = (uint32_t)p.row_bytes >> 4, pw = (uint32_t)p.PW;
-        const bool k4 = p.kc == 64;
-        const int nstages = p.a_stages, kchunks = p.kchunks, bn = p.BN, total = p.total_tiles, kdim = p.k;
+        const int nstages = p.a_stages, kchunks = p.kchunks, bn = p.BN, total = p.total_tiles;
+        const uint32_t w_tap = w_inc * (uint32_t)kchunks;               // tiles are [tap][chunk]
         int stage = 0, par = 0, it = 0, key = -1, wpar = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-            const int n = tile / tiles_per_img;
-            const int wkey = p.w_per_sample ? n : 0;
+            const int wkey = p.w_per_sample ? (int)p.div_img.quot((uint32_t)tile) : 0;
             if (wkey != key) {
                 mbar_wait(wfull, wpar);
                 wpar ^= 1;
@@ -136,21 +146,18 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 mbar_wait(afull + stage, par);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_stage_lo = a_lo0 + (uint32_t)stage * a_inc;
-                    uint32_t w_lo = w_lo0 + (uint32_t)c * w_inc;
-                    bool first = c == 0;
-                    for (int ky = 0; ky < kdim; ++ky) {
-                        for (int kx = 0; kx < kdim; ++kx) {
-                            const uint32_t a_lo = a_stage_lo + ((uint32_t)ky * pw + (uint32_t)kx) * row_units;
-                            if (first) mma_issue<false>(d_tmem, a_lo, a_hi, w_lo, b_hi, idesc);
-                            else       mma_issue<true>(d_tmem, a_lo, a_hi, w_lo, b_hi, idesc);
-                            first = false;
-                            mma_issue<true>(d_tmem, a_lo + 2, a_hi, w_lo + 2, b_hi, idesc);
-                            if (k4) {
-                                mma_issue<true>(d_tmem, a_lo + 4, a_hi, w_lo + 4, b_hi, idesc);
-                                mma_issue<true>(d_tmem, a_lo + 6, a_hi, w_lo + 6, b_hi, idesc);
-                            }
-                            w_lo += w_inc * (uint32_t)kchunks;          // next tap (tiles are [tap][chunk])
+                    const uint32_t a_base = a_lo0 + (uint32_t)stage * a_inc;
+                    const uint32_t w_base = w_lo0 + (uint32_t)c * w_inc;
+#pragma unroll
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const uint32_t a_lo = a_base + (uint32_t)((tap / KDIM) * PW + (tap % KDIM)) * ROW_UNITS;
+                        const uint32_t w_lo = w_base + (uint32_t)tap * w_tap;
+#pragma unroll
+                        for (int ks = 0; ks < KSTEPS; ++ks) {
+                            if (tap == 0 && ks == 0)
+                                mma_issue_dyn(d_tmem, a_lo, a_hi, w_lo, b_hi, idesc, (uint32_t)(c != 0));
+                            else
+                                mma_issue<true>(d_tmem, a_lo + 2 * ks, a_hi, w_lo + 2 * ks, b_hi, idesc);
                         }
                     }
                     mma_commit(aempty + stage);
@@ -168,8 +175,10 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const float nw = (p.noise != nullptr && p.noise_w != nullptr) ? *p.noise_w : 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int n = tile / tiles_per_img, t = tile % tiles_per_img;
-            const int oy = (t / p.tiles_w) * kHTH + h_l, ox = (t % p.tiles_w) * kHTW + w_l;
+            uint32_t n, t, th, tw;
+            p.div_img.divmod((uint32_t)tile, n, t);
+            p.div_tw.divmod(t, th, tw);
+            const int oy = (int)th * kHTH + h_l, ox = (int)tw * kHTW + w_l;
             const int acc = it & 1, acc_par = (it >> 1) & 1;
             mbar_wait(tfull + acc, acc_par);
             tc_fence_after();
@@ -235,6 +244,8 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.tiles_h = (g.out_h + kHTH - 1) / kHTH;
     p.tiles_w = (g.out_w + kHTW - 1) / kHTW;
     p.total_tiles = g.b * p.tiles_h * p.tiles_w;
+    p.div_img = make_fastdiv((uint32_t)(p.tiles_h * p.tiles_w));
+    p.div_tw = make_fastdiv((uint32_t)p.tiles_w);
     p.BN = g.oc;
     p.row_bytes = g.ic >= 64 ? 128 : 64;
     p.layout = p.row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
@@ -283,11 +294,17 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (attr_dev != cur_dev) {
-        cudaFuncSetAttribute(conv_fwd_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_dev = cur_dev;
     }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    conv_fwd_halo_kernel<<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
+    if (g.kh == 3 && p.row_bytes == 128) conv_fwd_halo_kernel<3, 128><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
+    else if (g.kh == 3)                  conv_fwd_halo_kernel<3, 64><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
+    else if (p.row_bytes == 128)         conv_fwd_halo_kernel<1, 128><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
+    else                                 conv_fwd_halo_kernel<1, 64><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
     count_launch();
     return check_launch("conv_fwd_halo");
 }
