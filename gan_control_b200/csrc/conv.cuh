@@ -8,6 +8,13 @@ namespace b200gan {
 // z = x zero-upsampled by `up`; see include/b200gan.h.
 struct ConvGeom {
     int b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample;
+    // "Packed" sides (up = down = 1 only): the convolution runs on a space-to-depth VIEW of a tensor that stays in its
+    // plain NHWC layout in memory.  pack_in: the logical input (in_h, in_w, ic) is the physical tensor
+    // (2*in_h, 2*in_w, ic/4) with logical channel (py*2+px)*ic/4 + c <-> physical pixel (2*iy+py, 2*ix+px), channel c.
+    // pack_out: same for the output (the kernel stores depth-to-space).  A stride-2 convolution preceded by the FIR
+    // blur, or a transposed stride-2 convolution followed by it, is a 3x3 stride-1 convolution between such views
+    // with composite weights (ops.py), so the blurred / zero-inserted intermediate never exists.
+    int pack_in = 0, pack_out = 0;
 };
 
 int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,

@@ -15,31 +15,66 @@ extern "C" int b200gan_set_conv_engine(int engine) {
 }
 
 
+static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, const b200gan::ConvGeom& g,
+                             const float* bias, const float* rowscale, const void* noise, const float* noise_w,
+                             float slope, float gain, cudaStream_t st) {
+    using namespace b200gan;
+    const int b = g.b;
+    const bool packed = g.pack_in || g.pack_out;
+    if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
+        return conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st);
+    if (g_conv_engine.load() == 0 && b > 0 && conv_fwd_halo_eligible(dtype, g, x, w, y))
+        return conv_fwd_halo(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st);
+    if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
+        return conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st);
+    return conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st);
+}
+
+static int conv_wgrad_dispatch(const void* x, const void* gy, float* gw, int dtype, const b200gan::ConvGeom& g,
+                               cudaStream_t st) {
+    using namespace b200gan;
+    const int b = g.b;
+    const bool packed = g.pack_in || g.pack_out;
+    if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_wgrad_pointwise_eligible(dtype, g, x, gy))
+        return conv_wgrad_pointwise(x, gy, gw, dtype, g, st);
+    if (g_conv_engine.load() == 0 && b > 0 && conv_wgrad_halo_eligible(dtype, g, x, gy))
+        return conv_wgrad_halo(x, gy, gw, g, st);
+    if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_wgrad_umma_eligible(dtype, g, x, gy))
+        return conv_wgrad_umma(x, gy, gw, g, st);
+    return conv_wgrad_simt(x, gy, gw, dtype, g, st);
+}
+
 extern "C" int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype, int b, int in_h, int in_w, int ic,
                                 int out_h, int out_w, int oc, int kh, int kw, int up, int down, int pad0,
                                 int w_per_sample, const float* bias, const float* rowscale, const void* noise,
                                 const float* noise_w, float slope, float gain, void* stream) {
-    using namespace b200gan;
-    ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
-    if (g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
-        return conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
-    if (g_conv_engine.load() == 0 && b > 0 && conv_fwd_halo_eligible(dtype, g, x, w, y))
-        return conv_fwd_halo(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
-    if (g_conv_engine.load() != 1 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
-        return conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
-    return conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
+    b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    return conv_fwd_dispatch(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
+}
+
+extern "C" int b200gan_conv_fwd_packed(const void* x, const void* w, void* y, int dtype, int b, int in_h, int in_w,
+                                       int ic, int out_h, int out_w, int oc, int kh, int kw, int pad0,
+                                       int w_per_sample, int pack_in, int pack_out, const float* bias,
+                                       const float* rowscale, const void* noise, const float* noise_w, float slope,
+                                       float gain, void* stream) {
+    b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, 1, 1, pad0, w_per_sample};
+    g.pack_in = pack_in != 0;
+    g.pack_out = pack_out != 0;
+    return conv_fwd_dispatch(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
 }
 
 extern "C" int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int dtype, int b, int in_h, int in_w,
                                   int ic, int out_h, int out_w, int oc, int kh, int kw, int up, int down, int pad0,
                                   int w_per_sample, void* stream) {
-    using namespace b200gan;
-    ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
-    if (g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_wgrad_pointwise_eligible(dtype, g, x, gy))
-        return conv_wgrad_pointwise(x, gy, gw, dtype, g, (cudaStream_t)stream);
-    if (g_conv_engine.load() == 0 && b > 0 && conv_wgrad_halo_eligible(dtype, g, x, gy))
-        return conv_wgrad_halo(x, gy, gw, g, (cudaStream_t)stream);
-    if (g_conv_engine.load() != 1 && b > 0 && conv_wgrad_umma_eligible(dtype, g, x, gy))
-        return conv_wgrad_umma(x, gy, gw, g, (cudaStream_t)stream);
-    return conv_wgrad_simt(x, gy, gw, dtype, g, (cudaStream_t)stream);
+    b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    return conv_wgrad_dispatch(x, gy, gw, dtype, g, (cudaStream_t)stream);
+}
+
+extern "C" int b200gan_conv_wgrad_packed(const void* x, const void* gy, float* gw, int dtype, int b, int in_h, int in_w,
+                                         int ic, int out_h, int out_w, int oc, int kh, int kw, int pad0,
+                                         int w_per_sample, int pack_x, int pack_gy, void* stream) {
+    b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, 1, 1, pad0, w_per_sample};
+    g.pack_in = pack_x != 0;
+    g.pack_out = pack_gy != 0;
+    return conv_wgrad_dispatch(x, gy, gw, dtype, g, (cudaStream_t)stream);
 }

@@ -29,6 +29,25 @@ __device__ __forceinline__ bool tap_src(const ConvGeom& g, int oy, int ox, int k
     return iy < g.in_h && ix < g.in_w;
 }
 
+// element offsets of logical (b, row, col, channel) in the physical NHWC tensor (see ConvGeom::pack_*)
+__device__ __forceinline__ int64_t in_offset(const ConvGeom& g, int b, int iy, int ix, int k) {
+    if (!g.pack_in) return (((int64_t)b * g.in_h + iy) * g.in_w + ix) * g.ic + k;
+    const int cp = g.ic >> 2, q = k / cp, c = k - q * cp;
+    return (((int64_t)b * (2 * g.in_h) + 2 * iy + (q >> 1)) * (2 * g.in_w) + 2 * ix + (q & 1)) * cp + c;
+}
+// output: offset and (physical) pixel index / channel for the epilogue's side inputs
+__device__ __forceinline__ int64_t out_offset(const ConvGeom& g, int b, int oy, int ox, int o, int64_t& ppix, int& pch) {
+    if (!g.pack_out) {
+        ppix = ((int64_t)b * g.out_h + oy) * g.out_w + ox;
+        pch = o;
+        return ppix * g.oc + o;
+    }
+    const int cq = g.oc >> 2, q = o / cq;
+    pch = o - q * cq;
+    ppix = ((int64_t)b * (2 * g.out_h) + 2 * oy + (q >> 1)) * (2 * g.out_w) + 2 * ox + (q & 1);
+    return ppix * cq + pch;
+}
+
 template <typename T>
 __device__ __forceinline__ void load4(const T* p, int valid, bool vec, float out[4]) {
     if (vec && valid >= 4) {
@@ -71,14 +90,13 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(
         const int ky = tap / g.kw, kx = tap % g.kw;
         int iy = 0, ix = 0;
         const bool a_ok = lpix < npix && tap_src(g, loy, lox, ky, kx, iy, ix);
-        const T* a_ptr = x + (((int64_t)b * g.in_h + iy) * g.in_w + ix) * g.ic;
         const int oc_l = n0 + lrow;
         const T* b_ptr = w + (((int64_t)wb * taps + tap) * g.oc + oc_l) * g.ic;
         for (int k0 = 0; k0 < g.ic; k0 += BK) {
             float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
             const int kk = k0 + lq;
             const int valid = g.ic - kk;
-            if (a_ok && valid > 0) load4<T>(a_ptr + kk, valid, vec_in, av);
+            if (a_ok && valid > 0) load4<T>(x + in_offset(g, b, iy, ix, kk), valid, vec_in, av);
             if (oc_l < g.oc && valid > 0) load4<T>(b_ptr + kk, valid, vec_in, bv);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -107,16 +125,20 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(
     for (int i = 0; i < 4; ++i) {
         const int pix = m0 + tm * 4 + i;
         if (pix >= npix) continue;
-        const float nz = noise ? nw * io<T>::ld(noise + (int64_t)b * npix + pix) : 0.f;
-        T* dst = y + ((int64_t)b * npix + pix) * g.oc + n0 + tn * 4;
+        int64_t ppix;
+        int pch0;
+        const int oc_phys = g.pack_out ? g.oc >> 2 : g.oc;
+        const int o0 = n0 + tn * 4 < g.oc ? n0 + tn * 4 : 0;                  // 4 consecutive channels share a phase
+        T* dst = y + out_offset(g, b, pix / g.out_w, pix % g.out_w, o0, ppix, pch0);
+        const float nz = noise ? nw * io<T>::ld(noise + ppix) : 0.f;
         Pack<T, 4> o;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int o_ch = n0 + tn * 4 + j;
             float v = acc[i][j];
             if (has_ep && o_ch < g.oc) {
-                if (rowscale) v *= rowscale[(int64_t)b * g.oc + o_ch];
-                v += nz + (bias ? bias[o_ch] : 0.f);
+                if (rowscale) v *= rowscale[(int64_t)b * oc_phys + pch0 + j];
+                v += nz + (bias ? bias[pch0 + j] : 0.f);
                 v = gain * (v > 0.f ? v : v * slope);
             }
             io<T>::st(&o.v[j], v);
@@ -166,11 +188,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restric
         if (pix < p_end) {
             const int oy = pix / g.out_w, ox = pix % g.out_w;
             const int vo = g.oc - (m0 + lq);
-            if (vo > 0) load4<T>(gy + ((int64_t)b * npix + pix) * g.oc + m0 + lq, vo, vec_oc, av);
+            int64_t ppix;
+            int pch;
+            if (vo > 0) load4<T>(gy + out_offset(g, b, oy, ox, m0 + lq, ppix, pch), vo, vec_oc, av);
             int iy, ix;
             const int vi = g.ic - (n0 + lq);
             if (vi > 0 && tap_src(g, oy, ox, ky, kx, iy, ix))
-                load4<T>(x + (((int64_t)b * g.in_h + iy) * g.in_w + ix) * g.ic + n0 + lq, vi, vec_ic, bv);
+                load4<T>(x + in_offset(g, b, iy, ix, n0 + lq), vi, vec_ic, bv);
         }
         *reinterpret_cast<float4*>(&As[lp][lq]) = make_float4(av[0], av[1], av[2], av[3]);
         *reinterpret_cast<float4*>(&Bs[lp][lq]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
@@ -206,6 +230,11 @@ static int check_geom(const ConvGeom& g, const char* who) {
     B200_REQUIRE(g.kh >= 1 && g.kw >= 1 && g.kh <= 16 && g.kw <= 16, "%s: bad kernel size", who);
     B200_REQUIRE(g.up >= 1 && g.down >= 1, "%s: up/down must be >= 1", who);
     B200_REQUIRE(g.b <= 65535, "%s: batch too large", who);
+    if (g.pack_in || g.pack_out) {
+        B200_REQUIRE(g.up == 1 && g.down == 1, "%s: packed views need up = down = 1", who);
+        B200_REQUIRE(!g.pack_in || g.ic % 16 == 0, "%s: pack_in needs ic %% 16 == 0", who);
+        B200_REQUIRE(!g.pack_out || g.oc % 16 == 0, "%s: pack_out needs oc %% 16 == 0", who);
+    }
     return 0;
 }
 

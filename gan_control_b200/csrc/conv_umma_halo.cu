@@ -31,6 +31,9 @@ struct HaloParams {
     int BN, kchunks, kc, row_bytes, layout;
     int PW, RH;                          // buffer row pitch (pixels) and rows
     int w_per_sample;
+    int pack_in, pack_out;               // space-to-depth views (ConvGeom): 5-D activation map / depth-to-space store
+    int cpp;                             // pack_in: channel chunks per row phase py
+    int CQ;                              // pack_out: physical output channels (= OC / 4)
     int a_stages, a_stage_bytes, w_tile_bytes, w_bytes;
     int tmem_cols;
     const float* bias;
@@ -41,6 +44,29 @@ struct HaloParams {
     int has_ep;
     __nv_bfloat16* y;
 };
+
+// 16 accumulator columns of one pixel -> epilogue -> 32 bytes of bf16
+__device__ __forceinline__ void epilogue_store16(const HaloParams& p, float (&v)[16], __nv_bfloat16* dst, const float* rs,
+                                                 const float* bs, float nz) {
+    if (p.has_ep) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            float u = v[e];
+            if (rs) u *= rs[e];
+            u += nz + (bs ? bs[e] : 0.f);
+            v[e] = p.gain * (u > 0.f ? u : u * p.slope);
+        }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
 
 // KDIM = 3 or 1 (kernel size), ROWB = 128 or 64 (bytes per pixel row of a channel chunk = swizzle width): both
 // compile-time so that the MMA-issuing warp's tap loop is straight-line code with immediate descriptor offsets.
@@ -105,7 +131,11 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 mbar_wait(aempty + stage, par ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(afull + stage, (uint32_t)p.a_stage_bytes);
-                    tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, c * p.kc, w0 - p.pad0, h0 - p.pad0, (int)n);
+                    if (p.pack_in)      // chunk c = (row phase py, channel chunk of the 2*C contiguous (px, c) elements)
+                        tma_load_5d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, (c % p.cpp) * p.kc, w0 - p.pad0,
+                                    c / p.cpp, h0 - p.pad0, (int)n);
+                    else
+                        tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, c * p.kc, w0 - p.pad0, h0 - p.pad0, (int)n);
                 }
                 __syncwarp();
                 last_stage = stage; last_par = par;
@@ -183,33 +213,30 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             mbar_wait(tfull + acc, acc_par);
             tc_fence_after();
             const bool valid = oy < p.OH && ox < p.OW;
-            const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
-            __nv_bfloat16* dst = p.y + pix * p.OC;
-            const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
-            const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                float v[16];
-                tmem_ld_x16(taddr + (uint32_t)c0, v);
-                if (valid) {
-                    if (p.has_ep) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float u = v[e];
-                            if (rs) u *= rs[c0 + e];
-                            u += nz + (p.bias ? p.bias[c0 + e] : 0.f);
-                            v[e] = p.gain * (u > 0.f ? u : u * p.slope);
-                        }
+            if (!p.pack_out) {
+                const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
+                __nv_bfloat16* dst = p.y + pix * p.OC;
+                const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
+                const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
+                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                    float v[16];
+                    tmem_ld_x16(taddr + (uint32_t)c0, v);
+                    if (valid) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz);
+                }
+            } else {
+                // depth-to-space: accumulator columns [(py*2+px)*CQ + c] of view pixel (oy, ox) are channel c of the
+                // physical pixel (2*oy+py, 2*ox+px); bias / rowscale / noise follow the physical tensor
+                const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.CQ : nullptr;
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int64_t pix = ((int64_t)n * (2 * p.OH) + 2 * oy + (ph >> 1)) * (2 * p.OW) + 2 * ox + (ph & 1);
+                    __nv_bfloat16* dst = p.y + pix * p.CQ;
+                    const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
+                    for (int c0 = 0; c0 < p.CQ; c0 += 16) {
+                        float v[16];
+                        tmem_ld_x16(taddr + (uint32_t)(ph * p.CQ + c0), v);
+                        if (valid) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz);
                     }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-                    }
-                    uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
-                    d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
             tc_fence_before();
@@ -225,13 +252,47 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     }
 }
 
+// shared-memory plan: resident weights + >= 2 activation stages inside the 227 KB opt-in limit
+static bool halo_plan(const ConvGeom& g, HaloParams& p) {
+    const int min_row = g.pack_in ? (g.ic / 2) * 2 : g.ic * 2;       // bytes of the contiguous run a chunk is cut from
+    p.row_bytes = min_row >= 128 ? 128 : 64;
+    p.layout = p.row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+    p.kc = p.row_bytes / 2;
+    p.kchunks = g.ic / p.kc;
+    p.cpp = g.pack_in ? (g.ic / 2) / p.kc : 0;
+    p.BN = g.oc;
+    p.PW = g.kw == 1 ? 8 : 16;
+    p.RH = kHTH + g.kh - 1;
+    p.a_stage_bytes = p.RH * p.PW * p.row_bytes;
+    if (p.a_stage_bytes % 1024 != 0) return false;                   // expect_tx counts exactly one box per stage
+    p.w_tile_bytes = p.BN * p.row_bytes;
+    p.w_bytes = g.kh * g.kw * p.kchunks * p.w_tile_bytes;
+    const int budget = 224 * 1024 - 1024 - ((p.w_bytes + 1023) & ~1023) - 256;
+    p.a_stages = budget / p.a_stage_bytes;
+    if (p.a_stages > 6) p.a_stages = 6;
+    return p.a_stages >= 2;
+}
+
 bool conv_fwd_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
     if (dtype != B200GAN_BF16) return false;
     if (g.up != 1 || g.down != 1 || g.kh != g.kw || (g.kh != 1 && g.kh != 3)) return false;
-    if (!(g.ic == 32 || g.ic == 64) || !(g.oc == 16 || g.oc == 32 || g.oc == 64)) return false;
     if (g.out_h < kHTH || g.out_w < kHTW) return false;
     if (g.out_h != g.in_h + 2 * g.pad0 - g.kh + 1 || g.out_w != g.in_w + 2 * g.pad0 - g.kw + 1) return false;
     if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) % 16 != 0) return false;
+    if (g.pack_in || g.pack_out) {
+        // view channels = 4 x physical channels; a chunk must not straddle a row phase, a 16-column epilogue group
+        // must not straddle an output phase
+        if (g.kh != 3) return false;
+        if (g.pack_in && !(g.ic == 64 || g.ic == 128)) return false;
+        if (!g.pack_in && !(g.ic == 32 || g.ic == 64)) return false;
+        if (g.pack_out && !(g.oc == 64 || g.oc == 128)) return false;
+        if (!g.pack_out && !(g.oc == 16 || g.oc == 32 || g.oc == 64)) return false;
+    } else {
+        if (!(g.ic == 32 || g.ic == 64) || !(g.oc == 16 || g.oc == 32 || g.oc == 64)) return false;
+    }
+    HaloParams plan;
+    memset(&plan, 0, sizeof(plan));
+    if (!halo_plan(g, plan)) return false;
     return tensor_map_encoder() != nullptr;
 }
 
@@ -241,25 +302,13 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     memset(&p, 0, sizeof(p));
     p.B = g.b; p.H = g.in_h; p.W = g.in_w; p.OC = g.oc; p.IC = g.ic; p.OH = g.out_h; p.OW = g.out_w;
     p.k = g.kh; p.pad0 = g.pad0; p.w_per_sample = g.w_per_sample;
+    p.pack_in = g.pack_in; p.pack_out = g.pack_out; p.CQ = g.oc / 4;
     p.tiles_h = (g.out_h + kHTH - 1) / kHTH;
     p.tiles_w = (g.out_w + kHTW - 1) / kHTW;
     p.total_tiles = g.b * p.tiles_h * p.tiles_w;
     p.div_img = make_fastdiv((uint32_t)(p.tiles_h * p.tiles_w));
     p.div_tw = make_fastdiv((uint32_t)p.tiles_w);
-    p.BN = g.oc;
-    p.row_bytes = g.ic >= 64 ? 128 : 64;
-    p.layout = p.row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
-    p.kc = p.row_bytes / 2;
-    p.kchunks = g.ic / p.kc;
-    p.PW = g.kw == 1 ? 8 : 16;
-    p.RH = kHTH + g.kh - 1;
-    p.a_stage_bytes = p.RH * p.PW * p.row_bytes;
-    p.a_stage_bytes = (p.a_stage_bytes + 1023) & ~1023;
-    p.w_tile_bytes = p.BN * p.row_bytes;
-    p.w_bytes = g.kh * g.kw * p.kchunks * p.w_tile_bytes;
-    p.a_stages = (int)((190 * 1024 - p.w_bytes) / p.a_stage_bytes);
-    if (p.a_stages > 6) p.a_stages = 6;
-    if (p.a_stages < 2) return B200GAN_ENOSUP;
+    if (!halo_plan(g, p)) return B200GAN_ENOSUP;
     int cols = 32;
     while (cols < 2 * p.BN) cols <<= 1;
     p.tmem_cols = cols;
@@ -269,7 +318,16 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.y = (__nv_bfloat16*)y;
 
     CUtensorMap map_x, map_w;
-    {
+    if (g.pack_in) {
+        // physical (b, 2H, 2W, C) seen as (b, H, py, W, [px, c]): the 2*C elements of a (px, c) pair row are contiguous
+        const uint64_t c2 = (uint64_t)g.ic / 2;                          // 2 * physical channels
+        uint64_t dims[5] = {c2, (uint64_t)g.in_w, 2, (uint64_t)g.in_h, (uint64_t)g.b};
+        uint64_t strides[4] = {c2 * 2, (uint64_t)g.in_w * c2 * 2, 2 * (uint64_t)g.in_w * c2 * 2,
+                               (uint64_t)g.in_h * 2 * g.in_w * c2 * 2};
+        uint32_t box[5] = {(uint32_t)p.kc, (uint32_t)p.PW, 1, (uint32_t)p.RH, 1};
+        uint32_t es[5] = {1, 1, 1, 1, 1};
+        if (int e = encode_bf16_map(&map_x, x, 5, dims, strides, box, es, p.row_bytes)) return e;
+    } else {
         uint64_t dims[4] = {(uint64_t)g.ic, (uint64_t)g.in_w, (uint64_t)g.in_h, (uint64_t)g.b};
         uint64_t strides[3] = {(uint64_t)g.ic * 2, (uint64_t)g.in_w * g.ic * 2, (uint64_t)g.in_h * g.in_w * g.ic * 2};
         uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.PW, (uint32_t)p.RH, 1};
@@ -283,10 +341,6 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
         uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.BN, 1};
         uint32_t es[3] = {1, 1, 1};
         if (int e = encode_bf16_map(&map_w, w, 3, dims, strides, box, es, p.row_bytes)) return e;
-    }
-    if (p.a_stage_bytes != p.RH * p.PW * p.row_bytes) {      // expect_tx counts exactly one box per stage
-        set_error("conv_fwd_halo: stage/box size mismatch");
-        return B200GAN_ENOSUP;
     }
     const size_t smem = 1024 + ((size_t)(p.w_bytes + 1023) & ~(size_t)1023) + (size_t)p.a_stages * p.a_stage_bytes +
                         (2 * p.a_stages + 5) * sizeof(uint64_t) + 16;

@@ -28,6 +28,11 @@ struct WhParams {
     int PW, RH, a_slot_bytes, b_slot_bytes, stages;
     int ngroups, atoms_per_group;                         // MMA groups per tile, kx taps packed per group
     int tmem_cols;
+    // space-to-depth views (ConvGeom::pack_*): the packed operand is read one row phase py at a time through a 5-D
+    // map (its (px, c) pair row is contiguous), IC / OC above are then the channels of that HALF of the view and the
+    // result lands at channel offset ic_off / oc_off of the full (OC_total, IC_total) weight gradient
+    int x_packed, gy_packed, x_phase, gy_phase;
+    int IC_total, OC_total, ic_off, oc_off;
     float* gw;
 };
 
@@ -86,8 +91,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 mbar_wait(empty + stage, par ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(full + stage, (uint32_t)(p.a_slot_bytes + p.b_slot_bytes));
-                    tma_load_4d(a_buf + stage * p.a_slot_bytes, &map_x, full + stage, 0, w0 - p.pad0, h0 - p.pad0, n);
-                    tma_load_4d(b_buf + stage * p.b_slot_bytes, &map_gy, full + stage, 0, w0, h0, n);
+                    if (p.x_packed)
+                        tma_load_5d(a_buf + stage * p.a_slot_bytes, &map_x, full + stage, 0, w0 - p.pad0, p.x_phase, h0 - p.pad0, n);
+                    else
+                        tma_load_4d(a_buf + stage * p.a_slot_bytes, &map_x, full + stage, 0, w0 - p.pad0, h0 - p.pad0, n);
+                    if (p.gy_packed)
+                        tma_load_5d(b_buf + stage * p.b_slot_bytes, &map_gy, full + stage, 0, w0, p.gy_phase, h0, n);
+                    else
+                        tma_load_4d(b_buf + stage * p.b_slot_bytes, &map_gy, full + stage, 0, w0, h0, n);
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; par ^= 1; }
@@ -155,14 +166,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 for (int kx0 = 0; kx0 < p.k; kx0 += p.atoms_per_group, ++g) {
                     const int kx = kx0 + atom;
                     const bool valid = have && atom < p.atoms_per_group && kx < p.k;
-                    float* dst = p.gw + (((int64_t)wb * taps + ky * p.k + (valid ? kx : 0)) * p.OC) * p.IC + ic;
+                    float* dst = p.gw + (((int64_t)wb * taps + ky * p.k + (valid ? kx : 0)) * p.OC_total + p.oc_off) * p.IC_total +
+                                 p.ic_off + ic;
                     const uint32_t taddr = tmem_base + (uint32_t)(g * p.OC) + ((uint32_t)(q * 32) << 16);
                     for (int c0 = 0; c0 < p.OC; c0 += 16) {
                         float v[16];
                         if (have) tmem_ld_x16(taddr + (uint32_t)c0, v);
                         if (valid) {
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) atomicAdd(dst + (int64_t)(c0 + e) * p.IC, v[e]);
+                            for (int e = 0; e < 16; ++e) atomicAdd(dst + (int64_t)(c0 + e) * p.IC_total, v[e]);
                         }
                     }
                 }
@@ -182,7 +194,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 bool conv_wgrad_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy) {
     if (dtype != B200GAN_BF16) return false;
     if (g.up != 1 || g.down != 1 || g.kh != g.kw || (g.kh != 1 && g.kh != 3)) return false;
-    if (!(g.ic == 32 || g.ic == 64) || !(g.oc == 32 || g.oc == 64)) return false;
+    // a packed operand is processed as its two row-phase halves (see WhParams)
+    const int ic = g.pack_in ? g.ic / 2 : g.ic, oc = g.pack_out ? g.oc / 2 : g.oc;
+    if ((g.pack_in || g.pack_out) && g.kh != 3) return false;
+    if ((g.pack_in && g.ic % 4 != 0) || (g.pack_out && g.oc % 4 != 0)) return false;
+    if (!(ic == 32 || ic == 64) || !(oc == 32 || oc == 64)) return false;
     if (g.out_h < kWhTH || g.out_w < kWhTW) return false;
     if (g.out_h != g.in_h + 2 * g.pad0 - g.kh + 1 || g.out_w != g.in_w + 2 * g.pad0 - g.kw + 1) return false;
     if (((uintptr_t)x | (uintptr_t)gy) % 16 != 0) return false;
@@ -192,7 +208,9 @@ bool conv_wgrad_halo_eligible(int dtype, const ConvGeom& g, const void* x, const
 int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g, cudaStream_t st) {
     WhParams p;
     memset(&p, 0, sizeof(p));
-    p.B = g.b; p.H = g.in_h; p.W = g.in_w; p.IC = g.ic; p.OC = g.oc; p.k = g.kh; p.pad0 = g.pad0;
+    const int ic = g.pack_in ? g.ic / 2 : g.ic, oc = g.pack_out ? g.oc / 2 : g.oc;      // per launch (row-phase half)
+    p.B = g.b; p.H = g.in_h; p.W = g.in_w; p.IC = ic; p.OC = oc; p.k = g.kh; p.pad0 = g.pad0;
+    p.IC_total = g.ic; p.OC_total = g.oc; p.x_packed = g.pack_in; p.gy_packed = g.pack_out;
     p.per_sample = g.w_per_sample; p.gw = gw;
     p.tiles_h = (g.out_h + kWhTH - 1) / kWhTH;
     p.tiles_w = (g.out_w + kWhTW - 1) / kWhTW;
@@ -206,8 +224,8 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
     p.kt_per_unit = (p.kt_total + splits - 1) / splits;
     p.units_per_wb = (p.kt_total + p.kt_per_unit - 1) / p.kt_per_unit;
     p.units = wbs * p.units_per_wb;
-    p.rowb_m = g.ic * 2; p.layout_m = p.rowb_m == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
-    p.rowb_n = g.oc * 2; p.layout_n = p.rowb_n == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+    p.rowb_m = ic * 2; p.layout_m = p.rowb_m == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
+    p.rowb_n = oc * 2; p.layout_n = p.rowb_n == 128 ? LAYOUT_SW128 : LAYOUT_SW64;
     p.PW = g.kw == 1 ? 8 : 16;
     p.RH = kWhTH + g.kh - 1;
     p.a_slot_bytes = p.RH * p.PW * p.rowb_m;
@@ -215,7 +233,7 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
     // past the last buffer row by nothing (K rows = 16 tile rows <= RH): keep one spare KiB of slack per slot
     p.a_slot_bytes = ((p.a_slot_bytes + 1023) & ~1023);
     p.b_slot_bytes = 128 * p.rowb_n;
-    p.atoms_per_group = g.kh == 1 ? 1 : (128 / g.ic >= 3 ? 3 : 2);
+    p.atoms_per_group = g.kh == 1 ? 1 : (128 / ic >= 3 ? 3 : 2);
     p.ngroups = g.kh == 1 ? 1 : g.kh * ((g.kw + p.atoms_per_group - 1) / p.atoms_per_group);
     int cols = 32;
     while (cols < p.ngroups * p.OC) cols <<= 1;
@@ -228,21 +246,26 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
         set_error("conv_wgrad_halo: slot/box size mismatch");
         return B200GAN_ENOSUP;
     }
+    // plain operand: (b, h, w, c); packed operand: physical (b, 2h, 2w, c/4) seen as (b, h, py, w, [px, c/4])
+    auto make_map = [&](CUtensorMap* m, const void* ptr, bool packed, int ch, int w, int h, int box_w, int box_h,
+                        int row_bytes) -> int {
+        if (packed) {
+            uint64_t dims[5] = {(uint64_t)ch, (uint64_t)w, 2, (uint64_t)h, (uint64_t)g.b};
+            uint64_t strides[4] = {(uint64_t)ch * 2, (uint64_t)w * ch * 2, 2 * (uint64_t)w * ch * 2,
+                                   (uint64_t)h * 2 * w * ch * 2};
+            uint32_t box[5] = {(uint32_t)ch, (uint32_t)box_w, 1, (uint32_t)box_h, 1};
+            uint32_t es[5] = {1, 1, 1, 1, 1};
+            return encode_bf16_map(m, ptr, 5, dims, strides, box, es, row_bytes);
+        }
+        uint64_t dims[4] = {(uint64_t)ch, (uint64_t)w, (uint64_t)h, (uint64_t)g.b};
+        uint64_t strides[3] = {(uint64_t)ch * 2, (uint64_t)w * ch * 2, (uint64_t)h * w * ch * 2};
+        uint32_t box[4] = {(uint32_t)ch, (uint32_t)box_w, (uint32_t)box_h, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        return encode_bf16_map(m, ptr, 4, dims, strides, box, es, row_bytes);
+    };
     CUtensorMap map_x, map_gy;
-    {
-        uint64_t dims[4] = {(uint64_t)g.ic, (uint64_t)g.in_w, (uint64_t)g.in_h, (uint64_t)g.b};
-        uint64_t strides[3] = {(uint64_t)g.ic * 2, (uint64_t)g.in_w * g.ic * 2, (uint64_t)g.in_h * g.in_w * g.ic * 2};
-        uint32_t box[4] = {(uint32_t)g.ic, (uint32_t)p.PW, (uint32_t)p.RH, 1};
-        uint32_t es[4] = {1, 1, 1, 1};
-        if (int e = encode_bf16_map(&map_x, x, 4, dims, strides, box, es, p.rowb_m)) return e;
-    }
-    {
-        uint64_t dims[4] = {(uint64_t)g.oc, (uint64_t)g.out_w, (uint64_t)g.out_h, (uint64_t)g.b};
-        uint64_t strides[3] = {(uint64_t)g.oc * 2, (uint64_t)g.out_w * g.oc * 2, (uint64_t)g.out_h * g.out_w * g.oc * 2};
-        uint32_t box[4] = {(uint32_t)g.oc, (uint32_t)kWhTW, (uint32_t)kWhTH, 1};
-        uint32_t es[4] = {1, 1, 1, 1};
-        if (int e = encode_bf16_map(&map_gy, gy, 4, dims, strides, box, es, p.rowb_n)) return e;
-    }
+    if (int e = make_map(&map_x, x, g.pack_in, ic, g.in_w, g.in_h, p.PW, p.RH, p.rowb_m)) return e;
+    if (int e = make_map(&map_gy, gy, g.pack_out, oc, g.out_w, g.out_h, kWhTW, kWhTH, p.rowb_n)) return e;
     const size_t smem = 1024 + (size_t)p.stages * (p.a_slot_bytes + p.b_slot_bytes) + 2048 + (2 * p.stages + 2) * sizeof(uint64_t) + 64;
     static thread_local int attr_dev = -1;
     int cur_dev = 0;
@@ -252,8 +275,13 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
         attr_dev = cur_dev;
     }
     int grid = p.units < sm_count() ? p.units : sm_count();
-    conv_wgrad_halo_kernel<<<grid, kWhThreads, smem, st>>>(map_x, map_gy, p);
-    count_launch();
+    for (int xp = 0; xp < (g.pack_in ? 2 : 1); ++xp)
+        for (int yp = 0; yp < (g.pack_out ? 2 : 1); ++yp) {
+            p.x_phase = xp; p.gy_phase = yp;
+            p.ic_off = xp * ic; p.oc_off = yp * oc;
+            conv_wgrad_halo_kernel<<<grid, kWhThreads, smem, st>>>(map_x, map_gy, p);
+            count_launch();
+        }
     return check_launch("conv_wgrad_halo");
 }
 

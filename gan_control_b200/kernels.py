@@ -37,6 +37,8 @@ _SIGNATURES = {
     'b200gan_epilogue_bwd': ([_vp] * 10 + [_i, _i64, _i64, _i64, _f, _f, _vp], _i),
     'b200gan_reduce_nhwc': ([_vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
     'b200gan_conv_fwd': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
+    'b200gan_conv_fwd_packed': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
+    'b200gan_conv_wgrad_packed': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
     'b200gan_set_conv_engine': ([_i], _i),
     'b200gan_conv_wgrad': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
     'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
@@ -226,40 +228,69 @@ def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None
 
 
 def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None, noise=None, noise_w=None,
-             slope=1.0, gain=1.0):
-    """x: (B,H,W,IC) contiguous; w: (Bw,KH,KW,OC,IC) contiguous, same dtype; -> (B,out_h,out_w,OC)."""
+             slope=1.0, gain=1.0, pack_in=False, pack_out=False):
+    """x: (B,H,W,IC) contiguous; w: (Bw,KH,KW,OC,IC) contiguous, same dtype; -> (B,out_h,out_w,OC).
+    pack_in / pack_out: the convolution runs between space-to-depth views (include/b200gan.h): x is then the plain
+    (B,2H,2W,IC/4) tensor, and / or the result is the plain (B,2*out_h,2*out_w,OC/4) tensor; out_h, out_w and the
+    channel counts of `w` are the LOGICAL (view) sizes."""
     _cuda(x, w, bias, rowscale, noise, noise_w)
     assert x.ndim == 4 and w.ndim == 5 and x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
     b, h, wd, ic = x.shape
+    if pack_in:
+        assert up == 1 and down == 1 and h % 2 == 0 and wd % 2 == 0
+        h, wd, ic = h // 2, wd // 2, ic * 4
     bw, kh, kw, oc, ic2 = w.shape
     assert ic2 == ic and bw in (1, b), (x.shape, w.shape)
     bias, rowscale, noise_w = _f32c(bias), _f32c(rowscale), _f32c(noise_w)
+    if pack_out:
+        assert up == 1 and down == 1 and oc % 4 == 0
+        y = torch.empty((b, 2 * out_h, 2 * out_w, oc // 4), dtype=x.dtype, device=x.device)
+    else:
+        y = torch.empty((b, out_h, out_w, oc), dtype=x.dtype, device=x.device)
     if noise is not None:
         noise = noise.detach().to(x.dtype).contiguous()
-        assert noise.numel() == b * out_h * out_w
-    y = torch.empty((b, out_h, out_w, oc), dtype=x.dtype, device=x.device)
+        assert noise.numel() == b * y.shape[1] * y.shape[2]
     if y.numel() == 0:
         return y
     with torch.cuda.device(x.device):
-        _check(lib().b200gan_conv_fwd(_ptr(x), _ptr(w), _ptr(y), _dt(x), b, h, wd, ic, out_h, out_w, oc, kh, kw,
-                                      up, down, pad0, int(bw > 1),
-                                      _ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w), float(slope),
-                                      float(gain), _stream()), 'conv_fwd')
+        if pack_in or pack_out:
+            _check(lib().b200gan_conv_fwd_packed(_ptr(x), _ptr(w), _ptr(y), _dt(x), b, h, wd, ic, out_h, out_w, oc, kh, kw,
+                                                 pad0, int(bw > 1), int(pack_in), int(pack_out),
+                                                 _ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w), float(slope),
+                                                 float(gain), _stream()), 'conv_fwd_packed')
+        else:
+            _check(lib().b200gan_conv_fwd(_ptr(x), _ptr(w), _ptr(y), _dt(x), b, h, wd, ic, out_h, out_w, oc, kh, kw,
+                                          up, down, pad0, int(bw > 1),
+                                          _ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w), float(slope),
+                                          float(gain), _stream()), 'conv_fwd')
     return y
 
 
-def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False):
-    """x: (B,H,W,IC), gy: (B,OH,OW,OC) contiguous -> fp32 (Bw,KH,KW,OC,IC)."""
+def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False, pack_x=False, pack_gy=False):
+    """x: (B,H,W,IC), gy: (B,OH,OW,OC) contiguous -> fp32 (Bw,KH,KW,OC,IC) (logical channel counts when an
+    operand is read through its space-to-depth view, see conv_fwd)."""
     _cuda(x, gy)
     assert x.is_contiguous() and gy.is_contiguous() and x.dtype == gy.dtype
     b, h, wd, ic = x.shape
     b2, oh, ow, oc = gy.shape
     assert b2 == b
+    if pack_x:
+        assert h % 2 == 0 and wd % 2 == 0
+        h, wd, ic = h // 2, wd // 2, ic * 4
+    if pack_gy:
+        assert oh % 2 == 0 and ow % 2 == 0
+        oh, ow, oc = oh // 2, ow // 2, oc * 4
     gw = torch.zeros((b if per_sample else 1, kh, kw, oc, ic), dtype=torch.float32, device=x.device)
     if x.numel() and gy.numel():
         with torch.cuda.device(x.device):
-            _check(lib().b200gan_conv_wgrad(_ptr(x), _ptr(gy), _ptr(gw), _dt(x), b, h, wd, ic, oh, ow, oc, kh, kw, up,
-                                            down, pad0, int(per_sample), _stream()), 'conv_wgrad')
+            if pack_x or pack_gy:
+                assert up == 1 and down == 1
+                _check(lib().b200gan_conv_wgrad_packed(_ptr(x), _ptr(gy), _ptr(gw), _dt(x), b, h, wd, ic, oh, ow, oc, kh, kw,
+                                                       pad0, int(per_sample), int(pack_x), int(pack_gy), _stream()),
+                       'conv_wgrad_packed')
+            else:
+                _check(lib().b200gan_conv_wgrad(_ptr(x), _ptr(gy), _ptr(gw), _dt(x), b, h, wd, ic, oh, ow, oc, kh, kw, up,
+                                                down, pad0, int(per_sample), _stream()), 'conv_wgrad')
     return gw
 
 

@@ -151,6 +151,9 @@ class ModulatedConv2d(nn.Module):                                             # 
             factor = 2
             p = (len(blur_kernel) - factor) - (kernel_size - 1)
             self.blur = Blur(blur_kernel, pad=((p + 1) // 2 + factor - 1, p // 2 + 1), upsample_factor=factor)
+            if kernel_size == 3 and len(blur_kernel) == 4:
+                # not a parameter and not in the state_dict: the FIR as a (9 -> 36)-tap Toeplitz map (ops.composite_up)
+                self.register_buffer('fir_toeplitz', ops.fir_toeplitz(self.blur.kernel, False), persistent=False)
         self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
         self.padding = kernel_size // 2
         self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
@@ -185,6 +188,14 @@ class ModulatedConv2d(nn.Module):                                             # 
             wk = w.unsqueeze(0)
             x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
         return x, wk, d
+
+    # Above this many input channels the upsampling layer is bound by the tensor pipe, not by HBM, and the fused
+    # single-pass form (4x the MMA work of the transposed convolution, no (2H+1)^2 intermediate) stops paying.
+    FUSE_UP_MAX_IN_CHANNELS = 64
+
+    def fuses_up(self, height, width):
+        return (self.upsample and hasattr(self, 'fir_toeplitz') and self.in_channel <= self.FUSE_UP_MAX_IN_CHANNELS
+                and self.in_channel % 8 == 0 and self.out_channel % 4 == 0 and self._weight_form(height, width))
 
     def raw(self, input, style, blur=True):
         """Un-demodulated convolution and the demodulation coefficients: (z, d) with
@@ -245,6 +256,17 @@ class StyledConv(nn.Module):                                                  # 
 
     def forward(self, input, style, noise=None):
         conv = self.conv
+        if conv.upsample and conv.fuses_up(input.shape[2], input.shape[3]):
+            # the WHOLE upsampling StyledConv in one kernel: transposed stride-2 conv, 4x4 FIR, demodulation, noise,
+            # bias, leaky-ReLU (gm.py:295-307, 340-345, 32-35) = a 3x3 convolution with composite FIR (*) conv
+            # weights whose accumulator tile is stored depth-to-space through the fused epilogue
+            x, wk, d = conv.operands(input, style)
+            oh, ow = input.shape[2] * 2, input.shape[3] * 2
+            if noise is None:
+                noise = input.new_empty(input.shape[0], 1, oh, ow).normal_()
+            return ops.conv_epilogue(x, ops.composite_up(wk, conv.fir_toeplitz), d, noise, self.noise.weight,
+                                     self.activate.bias, 1, 1, 1, out_hw=(input.shape[2], input.shape[3]),
+                                     slope=self.activate.negative_slope, gain=self.activate.scale, pack_out=True)
         if conv.upsample:
             # transposed conv -> [blur + demod scale + noise + bias + leaky-ReLU*sqrt(2)] in one pass
             z, d = conv.raw(input, style, blur=False)
@@ -504,6 +526,14 @@ class ConvLayer(nn.Sequential):                                               # 
         if activate:
             layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
         super().__init__(*layers)
+        # Blur -> 3x3 stride-2 conv as ONE 3x3 convolution on the space-to-depth view of the input (ops.composite_down):
+        # only where the layer is HBM-bound (4x the MMA work, no blurred (H+1)^2 intermediate)
+        self.fuse_down = (downsample and kernel_size == 3 and len(blur_kernel) == 4 and activate
+                          and in_channel <= self.FUSE_DOWN_MAX_IN_CHANNELS and in_channel % 4 == 0)
+        if self.fuse_down:
+            self.register_buffer('fir_toeplitz', ops.fir_toeplitz(layers[0].kernel, True), persistent=False)
+
+    FUSE_DOWN_MAX_IN_CHANNELS = 32
 
     def forward(self, input, out_scale=1.0):
         """[Blur] -> conv (+ bias + leaky-ReLU fused into the convolution's epilogue).  `out_scale`
@@ -511,6 +541,14 @@ class ConvLayer(nn.Sequential):                                               # 
         mods = list(self)
         x = input
         stride = None
+        if self.fuse_down and input.shape[2] % 2 == 0 and input.shape[3] % 2 == 0:
+            blur, conv, act = mods
+            w = ops.composite_down((conv.weight * conv.scale).unsqueeze(0), self.fir_toeplitz)
+            bias = act.bias if isinstance(act, FusedLeakyReLU) else None
+            gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
+            y = ops.conv_epilogue(x, w, None, None, None, bias, 1, 1, 1, slope=act.negative_slope, gain=gain * out_scale,
+                                  pack_in=True)
+            return _plain_if_tiny(y)
         if isinstance(mods[0], Blur):
             blur, conv = mods[0], mods[1]
             if conv.weight.shape[2] == 1 and conv.stride == 2 and conv.padding == 0:

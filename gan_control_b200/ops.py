@@ -335,80 +335,94 @@ def _kernel_layout(w, dtype):
     return w.detach().permute(0, 3, 4, 1, 2).to(dtype).contiguous()
 
 
+def _flip_t(w):
+    """weights of the adjoint convolution: taps reversed, OC <-> IC"""
+    return w.flip(3, 4).transpose(1, 2)
+
+
 class _ConvGather(Function):
     """y[b,o,oy,ox] = sum_{i,ky,kx} z[b,i,oy*down+ky-pad0,ox*down+kx-pad0] * w[wb,o,i,ky,kx]
-    with z = x zero-upsampled by `up` (include/b200gan.h).  w: (Bw,OC,IC,KH,KW), Bw in {1,B}."""
+    with z = x zero-upsampled by `up` (include/b200gan.h).  w: (Bw,OC,IC,KH,KW), Bw in {1,B}.
+    pack_in / pack_out: the convolution runs between space-to-depth VIEWS of plain tensors (up = down = 1;
+    include/b200gan.h "packed"): x is then the plain (B,IC/4,2H,2W) tensor and / or y the plain (B,OC/4,2OH,2OW)
+    tensor, while w, out_h, out_w are in view terms.  The adjoint swaps the two flags."""
 
     @staticmethod
-    def forward(ctx, x, w, up, down, pad0, out_h, out_w):
-        ctx.cfg = (up, down, pad0, x.shape[2], x.shape[3])
+    def forward(ctx, x, w, up, down, pad0, out_h, out_w, pack_in=False, pack_out=False):
+        h, wd = (x.shape[2] // 2, x.shape[3] // 2) if pack_in else (x.shape[2], x.shape[3])
+        ctx.cfg = (up, down, pad0, h, wd, pack_in, pack_out)
         ctx.save_for_backward(x, w)
-        y = K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0)
+        y = K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0, pack_in=pack_in,
+                       pack_out=pack_out)
         return _nchw(y)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        up, down, pad0, h, wd = ctx.cfg
+        up, down, pad0, h, wd, pack_in, pack_out = ctx.cfg
         kh, kw = w.shape[3], w.shape[4]
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            wt = w.flip(3, 4).transpose(1, 2)                  # taps reversed, OC <-> IC
-            gx = _ConvGather.apply(gy, wt, down, up, kh - 1 - pad0, h, wd)
+            gx = _ConvGather.apply(gy, _flip_t(w), down, up, kh - 1 - pad0, h, wd, pack_out, pack_in)
         if ctx.needs_input_grad[1] and (w.shape[0] > 1 or _param_grads()):
-            gw = _ConvWgrad.apply(x, gy, up, down, pad0, kh, kw, w.shape[0] > 1).to(w.dtype)
-        return gx, gw, None, None, None, None, None
+            gw = _ConvWgrad.apply(x, gy, up, down, pad0, kh, kw, w.shape[0] > 1, pack_in, pack_out).to(w.dtype)
+        return gx, gw, None, None, None, None, None, None, None
 
 
 class _ConvWgrad(Function):
     """gw[wb,o,i,ky,kx] = sum_{b,oy,ox} gy[b,o,oy,ox] * z[b,i,oy*down+ky-pad0,ox*down+kx-pad0]
-    (fp32 result; summed over the batch unless per_sample)."""
+    (fp32 result; summed over the batch unless per_sample); pack_x / pack_gy as in _ConvGather."""
 
     @staticmethod
-    def forward(ctx, x, gy, up, down, pad0, kh, kw, per_sample):
-        ctx.cfg = (up, down, pad0, kh, kw, x.shape[2], x.shape[3], gy.shape[2], gy.shape[3])
+    def forward(ctx, x, gy, up, down, pad0, kh, kw, per_sample, pack_x=False, pack_gy=False):
+        h, wd = (x.shape[2] // 2, x.shape[3] // 2) if pack_x else (x.shape[2], x.shape[3])
+        oh, ow = (gy.shape[2] // 2, gy.shape[3] // 2) if pack_gy else (gy.shape[2], gy.shape[3])
+        ctx.cfg = (up, down, pad0, kh, kw, h, wd, oh, ow, pack_x, pack_gy)
         ctx.save_for_backward(x, gy)
-        gw = K.conv_wgrad(_nhwc(x), _nhwc(gy), kh, kw, up, down, pad0, per_sample)
+        gw = K.conv_wgrad(_nhwc(x), _nhwc(gy), kh, kw, up, down, pad0, per_sample, pack_x=pack_x, pack_gy=pack_gy)
         return gw.permute(0, 3, 4, 1, 2)                       # (Bw,OC,IC,KH,KW) view
 
     @staticmethod
     def backward(ctx, ggw):
         x, gy = ctx.saved_tensors
-        up, down, pad0, kh, kw, h, wd, oh, ow = ctx.cfg
+        up, down, pad0, kh, kw, h, wd, oh, ow, pack_x, pack_gy = ctx.cfg
         gx = ggy = None
         if ctx.needs_input_grad[0]:
-            gx = _ConvGather.apply(gy, ggw.flip(3, 4).transpose(1, 2), down, up, kh - 1 - pad0, h, wd)
+            gx = _ConvGather.apply(gy, _flip_t(ggw), down, up, kh - 1 - pad0, h, wd, pack_gy, pack_x)
         if ctx.needs_input_grad[1]:
-            ggy = _ConvGather.apply(x, ggw, up, down, pad0, oh, ow)
-        return gx, ggy, None, None, None, None, None, None
+            ggy = _ConvGather.apply(x, ggw, up, down, pad0, oh, ow, pack_x, pack_gy)
+        return gx, ggy, None, None, None, None, None, None, None, None
 
 
 class _ConvEpilogue(Function):
     """y = gain*lrelu(conv(x, w)*d[b,o] + nw*noise + bias[o]) in ONE kernel (the convolution's epilogue;
     the conv output never reaches HBM).  StyledConv without upsampling (gm.py:402-408) and the
-    discriminator's ConvLayer (EqualConv2d + FusedLeakyReLU, gm.py:872-888).
+    discriminator's ConvLayer (EqualConv2d + FusedLeakyReLU, gm.py:872-888); with pack_out / pack_in also the
+    upsampling StyledConv and the downsampling ConvLayer (composite FIR (*) conv weights, see composite_up/down).
     Backward: first order = fused epilogue backward (from the saved output) + the conv gradients;
     under create_graph the conv output is recomputed and the differentiable formulas are used."""
 
     @staticmethod
-    def forward(ctx, x, w, d, noise, noise_w, bias, up, down, pad0, out_h, out_w, slope, gain):
+    def forward(ctx, x, w, d, noise, noise_w, bias, up, down, pad0, out_h, out_w, slope, gain, pack_in=False,
+                pack_out=False):
         y = _nchw(K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0, bias, d, noise,
-                             noise_w, slope, gain))
-        ctx.cfg = (up, down, pad0, x.shape[2], x.shape[3], out_h, out_w, slope, gain)
+                             noise_w, slope, gain, pack_in=pack_in, pack_out=pack_out))
+        h, wd = (x.shape[2] // 2, x.shape[3] // 2) if pack_in else (x.shape[2], x.shape[3])
+        ctx.cfg = (up, down, pad0, h, wd, out_h, out_w, slope, gain, pack_in, pack_out)
         ctx.save_for_backward(x, w, d, noise, noise_w, bias, y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, d, noise, noise_w, bias, y = ctx.saved_tensors
-        up, down, pad0, h, wd, oh, ow, slope, gain = ctx.cfg
+        up, down, pad0, h, wd, oh, ow, slope, gain, pack_in, pack_out = ctx.cfg
         need = ctx.needs_input_grad
         kh, kw = w.shape[3], w.shape[4]
         gx = gw = gd = gnoise = gnw = gb = None
         if torch.is_grad_enabled():
             z = None
             if d is not None and need[2]:
-                z = _ConvGather.apply(x, w, up, down, pad0, oh, ow)              # recompute, differentiable
+                z = _ConvGather.apply(x, w, up, down, pad0, oh, ow, pack_in, pack_out)   # recompute, differentiable
             gconv, gd, gnoise, gnw, gb = _epilogue_grads_graph(gy, y, z, d, noise, noise_w, bias, need[2], need[3],
                                                                need[4], need[5], slope, gain)
         else:
@@ -427,28 +441,74 @@ class _ConvEpilogue(Function):
                 gz = _BiasActGrad.apply(gy, y, slope, gain)
                 gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
         if need[0]:
-            gx = _ConvGather.apply(gconv, w.flip(3, 4).transpose(1, 2), down, up, kh - 1 - pad0, h, wd)
+            gx = _ConvGather.apply(gconv, _flip_t(w), down, up, kh - 1 - pad0, h, wd, pack_out, pack_in)
         if need[1] and (w.shape[0] > 1 or _param_grads()):        # a shared weight depends on parameters only
-            gw = _ConvWgrad.apply(x, gconv, up, down, pad0, kh, kw, w.shape[0] > 1).to(w.dtype)
-        return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None
+            gw = _ConvWgrad.apply(x, gconv, up, down, pad0, kh, kw, w.shape[0] > 1, pack_in, pack_out).to(w.dtype)
+        return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None
+
+
+def _view_hw(x, w, up, down, pad0, pack_in):
+    h, wd = (x.shape[2] // 2, x.shape[3] // 2) if pack_in else (x.shape[2], x.shape[3])
+    zh, zw = (h - 1) * up + 1, (wd - 1) * up + 1
+    return (zh + 2 * pad0 - w.shape[3]) // down + 1, (zw + 2 * pad0 - w.shape[4]) // down + 1
 
 
 def conv_epilogue(x, w, d=None, noise=None, noise_w=None, bias=None, up=1, down=1, pad0=0, out_hw=None,
-                  slope=0.2, gain=SQRT2):
+                  slope=0.2, gain=SQRT2, pack_in=False, pack_out=False):
     """conv_gather fused with the demod-scale / noise / bias / leaky-ReLU epilogue; `w` (Bw,OC,IC,KH,KW)."""
     if out_hw is None:
-        zh, zw = (x.shape[2] - 1) * up + 1, (x.shape[3] - 1) * up + 1
-        out_hw = ((zh + 2 * pad0 - w.shape[3]) // down + 1, (zw + 2 * pad0 - w.shape[4]) // down + 1)
-    return _ConvEpilogue.apply(x, w, d, noise, noise_w, bias, up, down, pad0, out_hw[0], out_hw[1], slope, gain)
+        out_hw = _view_hw(x, w, up, down, pad0, pack_in)
+    return _ConvEpilogue.apply(x, w, d, noise, noise_w, bias, up, down, pad0, out_hw[0], out_hw[1], slope, gain,
+                               pack_in, pack_out)
 
 
-def conv_gather(x, w, up=1, down=1, pad0=0, out_hw=None):
+def conv_gather(x, w, up=1, down=1, pad0=0, out_hw=None, pack_in=False, pack_out=False):
     """General form; `w` (Bw,OC,IC,KH,KW).  Default output extent = 'valid' over the padded,
-    zero-upsampled input with symmetric padding pad0."""
+    zero-upsampled input with symmetric padding pad0 (in view terms when packed)."""
     if out_hw is None:
-        zh, zw = (x.shape[2] - 1) * up + 1, (x.shape[3] - 1) * up + 1
-        out_hw = ((zh + 2 * pad0 - w.shape[3]) // down + 1, (zw + 2 * pad0 - w.shape[4]) // down + 1)
-    return _ConvGather.apply(x, w, up, down, pad0, out_hw[0], out_hw[1])
+        out_hw = _view_hw(x, w, up, down, pad0, pack_in)
+    return _ConvGather.apply(x, w, up, down, pad0, out_hw[0], out_hw[1], pack_in, pack_out)
+
+
+# ---------------------------------------------------------------------------------------------
+# composite FIR (*) convolution weights for the packed (space-to-depth view) convolutions
+# ---------------------------------------------------------------------------------------------
+def fir_toeplitz(kernel, flip):
+    """(9, 36) matrix T with  full_conv2d(w3x3, g).reshape(36) == w3x3.reshape(9) @ T,  g = kernel (flipped when
+    asked): the TRUE (not correlated) full 2-D convolution of a 3x3 weight with the 4x4 FIR."""
+    g = kernel.flip(0, 1) if flip else kernel
+    assert g.shape == (4, 4)
+    t = g.new_zeros(3, 3, 6, 6)
+    for a in range(3):
+        for b in range(3):
+            t[a, b, a:a + 4, b:b + 4] = g
+    return t.reshape(9, 36)
+
+
+def _composite6(w, toeplitz):
+    bw, oc, ic = w.shape[:3]
+    c = _Gemm.apply(w.reshape(-1, 9), toeplitz.to(w.dtype), False, False, 1.0)
+    return c.reshape(bw, oc, ic, 3, 2, 3, 2)                   # 6x6 taps as (m_y, p_y, m_x, p_x), n = 2*m + p
+
+
+def composite_up(w, toeplitz):
+    """Transposed stride-2 3x3 convolution followed by the 4x4 FIR (gm.py:295-307) as ONE 3x3 stride-1 convolution
+    whose output is read depth-to-space (four output phases):
+        out[2y+py, 2x+px, o] = sum_{ky,kx,i} x[y+ky-1, x+kx-1, i] * C[o, i, 4-2ky+py, 4-2kx+px],   C = fir (*) w
+    w (Bw,OC,IC,3,3) -> (Bw,4*OC,IC,3,3) with output channel (py*2+px)*OC + o; toeplitz = fir_toeplitz(fir, False)."""
+    bw, oc, ic = w.shape[:3]
+    c = _composite6(w, toeplitz).flip(3, 5)                    # m -> ky = 2 - m
+    return c.permute(0, 4, 6, 1, 2, 3, 5).reshape(bw, 4 * oc, ic, 3, 3)
+
+
+def composite_down(w, toeplitz):
+    """4x4 FIR (pad 2,2) followed by a stride-2 3x3 convolution (gm.py:857-872) as ONE 3x3 stride-1 convolution on
+    the space-to-depth view of the input:
+        out[y, x, o] = sum_{ky,kx,py,px,i} x[2(y+ky-1)+py, 2(x+kx-1)+px, i] * C[o, i, 2ky+py, 2kx+px],  C = flip(fir) (*) w
+    w (Bw,OC,IC,3,3) -> (Bw,OC,4*IC,3,3) with input channel (py*2+px)*IC + i; toeplitz = fir_toeplitz(fir, True)."""
+    bw, oc, ic = w.shape[:3]
+    c = _composite6(w, toeplitz)
+    return c.permute(0, 1, 4, 6, 2, 3, 5).reshape(bw, oc, 4 * ic, 3, 3)
 
 
 def conv2d(input, weight, bias=None, stride=1, padding=0):

@@ -137,6 +137,27 @@ int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int dtype,
                        int kh, int kw, int up, int down, int pad0, int w_per_sample,
                        void* stream);
 
+/* Convolution between space-to-depth VIEWS (up = down = 1).  Replaces, in ONE pass each,
+ *   `conv_transpose2d(stride 2)` -> `Blur`            (upsampling ModulatedConv2d, gm.py:295-307): pack_out
+ *   `Blur` -> `conv2d(stride 2)`                      (ConvLayer(downsample=True), gm.py:857-872): pack_in
+ * and their data / weight gradients, with composite (FIR (*) conv) weights prepared by the caller:
+ * the blurred / zero-inserted intermediate of the reference never exists.
+ * pack_in : x is the plain NHWC tensor (b, 2*in_h, 2*in_w, ic/4); logical channel (py*2+px)*ic/4 + c
+ *           of logical pixel (iy, ix) is physical pixel (2*iy+py, 2*ix+px), channel c.
+ * pack_out: y is the plain NHWC tensor (b, 2*out_h, 2*out_w, oc/4), same correspondence; bias / rowscale are
+ *           indexed by the physical channel, noise by the physical pixel.
+ * in_h .. oc describe the LOGICAL (view) geometry; w is [wb][kh][kw][oc][ic] over logical channels. */
+int b200gan_conv_fwd_packed(const void* x, const void* w, void* y, int dtype,
+                            int b, int in_h, int in_w, int ic, int out_h, int out_w, int oc,
+                            int kh, int kw, int pad0, int w_per_sample, int pack_in, int pack_out,
+                            const float* bias, const float* rowscale, const void* noise, const float* noise_w,
+                            float slope, float gain, void* stream);
+/* Weight gradient of the packed form: pack_x / pack_gy say which operand is read through the view. */
+int b200gan_conv_wgrad_packed(const void* x, const void* gy, float* gw, int dtype,
+                              int b, int in_h, int in_w, int ic, int out_h, int out_w, int oc,
+                              int kh, int kw, int pad0, int w_per_sample, int pack_x, int pack_gy,
+                              void* stream);
+
 /* ---- dense layers ------------------------------------------------------------
  * Replaces `EqualLinear.forward` gm.py:189-197 (`F.linear` + bias*lr_mul
  * [+ fused_leaky_relu]):  y[m][n] = act( scale * sum_k x[m][k] w[n][k] + bias[n]*bias_mul )

@@ -116,8 +116,23 @@ def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None
             v.sum(1).to(out_t) if per_sample_channel else None)
 
 
+def _s2d(x):
+    """plain NHWC (B,2H,2W,C) -> its space-to-depth view (B,H,W,4C), channel = (py*2+px)*C + c"""
+    b, h2, w2, c = x.shape
+    return x.reshape(b, h2 // 2, 2, w2 // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h2 // 2, w2 // 2, 4 * c)
+
+
+def _d2s(y):
+    """(B,H,W,4C) -> plain NHWC (B,2H,2W,C): inverse of _s2d"""
+    b, h, w, c4 = y.shape
+    c = c4 // 4
+    return y.reshape(b, h, w, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(b, 2 * h, 2 * w, c).contiguous()
+
+
 def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None, noise=None, noise_w=None,
-             slope=1.0, gain=1.0):
+             slope=1.0, gain=1.0, pack_in=False, pack_out=False):
+    if pack_in:
+        x = _s2d(x)
     b = x.shape[0]
     bw, kh, kw, oc, ic = w.shape
     xn = x.permute(0, 3, 1, 2)
@@ -128,12 +143,18 @@ def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None,
     else:
         y = torch.cat([F.conv2d(z[i:i + 1], wt[i], stride=down) for i in range(b)], 0)
     y = y.permute(0, 2, 3, 1).contiguous()
+    if pack_out:
+        y = _d2s(y)
     if bias is not None or rowscale is not None or noise is not None or slope != 1.0 or gain != 1.0:
         y = bias_act_fwd(y, bias, rowscale, noise, noise_w, slope, gain)
     return y
 
 
-def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False):
+def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False, pack_x=False, pack_gy=False):
+    if pack_x:
+        x = _s2d(x)
+    if pack_gy:
+        gy = _s2d(gy)
     b, _, _, ic = x.shape
     oc = gy.shape[-1]
     with torch.enable_grad():

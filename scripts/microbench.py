@@ -69,6 +69,25 @@ for name, h, ic, oc, k, up, down, pad0, ps in convs:
     report('wgrad ' + name, timeit(lambda: K.conv_wgrad(x, gy, k, k, up, down, pad0, ps)), fl, by)
     del x, w, gy
 
+# fused resampling layers: 3x3 convolutions between space-to-depth views (composite FIR (*) conv weights)
+packed = [  # name, view h, view ic, view oc, per_sample, pack_in, pack_out
+    ('up 64->32 @512->1024 fused (pack_out) ps', 512, 64, 128, True, False, True),
+    ('up 64->32 dgrad (pack_in) ps', 512, 128, 64, True, True, False),
+    ('down 32->64 @1024->512 fused (pack_in)', 512, 128, 64, False, True, False),
+    ('down 32->64 dgrad (pack_out)', 512, 64, 128, False, False, True),
+]
+for name, h, ic, oc, ps, pin, pout in packed:
+    if flt and flt not in name and flt not in ('conv', 'packed'):
+        continue
+    x = torch.randn(B, 2 * h, 2 * h, ic // 4, device=dev).to(bf) if pin else torch.randn(B, h, h, ic, device=dev).to(bf)
+    w = (torch.randn(B if ps else 1, 3, 3, oc, ic, device=dev) / (ic * 9) ** 0.5).to(bf)
+    gy = torch.randn(B, 2 * h, 2 * h, oc // 4, device=dev).to(bf) if pout else torch.randn(B, h, h, oc, device=dev).to(bf)
+    fl = 2.0 * B * h * h * ic * oc * 9
+    by = 2.0 * B * h * h * (ic + oc)
+    report('fwd   ' + name, timeit(lambda: K.conv_fwd(x, w, h, h, 1, 1, 1, pack_in=pin, pack_out=pout)), fl, by)
+    report('wgrad ' + name, timeit(lambda: K.conv_wgrad(x, gy, 3, 3, 1, 1, 1, ps, pack_x=pin, pack_gy=pout)), fl, by)
+    del x, w, gy
+
 if not flt or flt in 'blur':
     taps = (torch.outer(torch.tensor([1., 3, 3, 1]), torch.tensor([1., 3, 3, 1])) / 64 * 4).to(dev)
     for h, c in [(1025, 32), (1024, 32), (513, 64), (257, 128), (65, 512)]:

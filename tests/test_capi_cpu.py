@@ -38,3 +38,14 @@ def test_no_cpu_fallback():
         ops.upfirdn2d(x, k)
     with pytest.raises(RuntimeError, match='CUDA'):
         ops.fused_leaky_relu(x, torch.zeros(2))
+
+
+def test_ctypes_signatures_match_header():
+    """every binding in kernels._SIGNATURES has as many arguments as the prototype in include/b200gan.h"""
+    src = open(os.path.join(ROOT, 'include', 'b200gan.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {m.group(1): m.group(2) for m in re.finditer(r'\b(b200gan_\w+)\s*\(([^)]*)\)\s*;', src)}
+    for name, (argtypes, _) in kernels._SIGNATURES.items():
+        args = protos[name].strip()
+        n = 0 if args in ('', 'void') else len(args.split(','))
+        assert n == len(argtypes), f'{name}: header has {n} parameters, binding {len(argtypes)}'

@@ -338,3 +338,49 @@ def test_conv_wgrad_halo(case):
     assert float((gw - gw_gen).abs().max()) / scale < 2e-4, 'halo vs general wgrad'
     gwr = R.conv_wgrad(xr, gyr, k, k, 1, 1, pad0, ps)
     assert float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max()) < 2e-4
+
+
+# ---- convolutions between space-to-depth views (fused FIR resampling, include/b200gan.h "packed") -------------
+PACKED_CASES = [
+    # b, h, w (view extent), ic, oc (view channels), per_sample, pack_in, pack_out
+    (2, 32, 32, 64, 128, True, False, True),      # upsampling StyledConv 64 -> 32 (1024^2 layer)
+    (2, 32, 24, 128, 64, True, True, False),      # ... its data gradient
+    (2, 32, 32, 128, 64, False, True, False),     # downsampling ConvLayer 32 -> 64 (res1024.conv2)
+    (3, 48, 40, 64, 128, False, False, True),     # ... its data gradient, ragged tiles
+    (2, 32, 32, 64, 64, False, True, False), (2, 32, 32, 32, 64, True, False, True), (1, 64, 64, 128, 128, False, True, True),
+    (2, 8, 8, 16, 32, False, True, True), (2, 6, 10, 32, 16, True, False, True),      # small: CUDA-core engine
+]
+
+
+@pytest.mark.parametrize('case', PACKED_CASES)
+def test_conv_packed(case):
+    """packed forward (+ fused epilogue) and weight gradient on every engine that takes the shape, against the
+    fp64 stand-in (which materialises the space-to-depth views)"""
+    b, h, w, ic, oc, ps, pin, pout = case
+    dt = torch.bfloat16
+    x, xr = prep(rnd(101, b, 2 * h, 2 * w, ic // 4) if pin else rnd(101, b, h, w, ic), dt)
+    wt, wr = prep(rnd(102, b if ps else 1, 3, 3, oc, ic) / (ic * 9) ** 0.5, dt)
+    ocp = oc // 4 if pout else oc
+    oh, ow = (2 * h, 2 * w) if pout else (h, w)
+    bias, rs, nw = rnd(103, ocp).float(), (rnd(104, b, ocp).abs() + 0.5).float(), torch.tensor([0.3])
+    noise, noiser = prep(rnd(105, b, oh, ow), dt)
+    gy, gyr = prep(rnd(106, b, oh, ow, ocp), dt)
+    ref = R.conv_fwd(xr, wr, h, w, 1, 1, 1, pack_in=pin, pack_out=pout)
+    ref_ep = R.conv_fwd(xr, wr, h, w, 1, 1, 1, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5,
+                        pack_in=pin, pack_out=pout)
+    gwr = R.conv_wgrad(xr, gyr, 3, 3, 1, 1, 1, ps, pack_x=pin, pack_gy=pout)
+    for engine in (0, 1):
+        prev = K.set_conv_engine(engine)
+        try:
+            y = K.conv_fwd(x, wt, h, w, 1, 1, 1, pack_in=pin, pack_out=pout)
+            y_ep = K.conv_fwd(x, wt, h, w, 1, 1, 1, bias.cuda(), rs.cuda(), noise, nw.cuda(), 0.2, 2 ** 0.5,
+                              pack_in=pin, pack_out=pout)
+            gw = K.conv_wgrad(x, gy, 3, 3, 1, 1, 1, ps, pack_x=pin, pack_gy=pout)
+            torch.cuda.synchronize()
+        finally:
+            K.set_conv_engine(prev)
+        assert y.shape == ref.shape
+        close(y, ref, dt, f'packed fwd engine {engine}')
+        close(y_ep, ref_ep, dt, f'packed fwd+epilogue engine {engine}')
+        err = float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max())
+        assert err < 2e-4, f'packed wgrad engine {engine} rel err {err:.2e}'

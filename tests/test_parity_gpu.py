@@ -276,3 +276,64 @@ def test_graph_replay_runs_and_counts_launches():
     assert step.replayed_launches > 5 * step.graph_launches['d'] > 0
     step.g_arena.check_views()
     step.d_arena.check_views()
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+def test_fused_resampling_layers(dt):
+    """The single-pass forms (composite FIR (*) conv weights between space-to-depth views: upsampling StyledConv,
+    downsampling ConvLayer) against the two-pass forms that the goldens above pin: output, first-order gradients and
+    an R1 / path-length style double backward, through the CUDA kernels."""
+    tol1, tol2 = (2e-4, 2e-3) if dt == torch.float32 else (4e-2, 1.5e-1)
+    b, h, sdim = 2, 32, 24
+    x0 = rnd(301, b, 64, h, h).to(DEV, dt).contiguous(memory_format=torch.channels_last)
+    s0 = rnd(302, b, sdim).to(DEV)
+    noise = rnd(303, b, 1, 2 * h, 2 * h).to(DEV, dt)
+    gy = rnd(304, b, 32, 2 * h, 2 * h).to(DEV, dt)
+    res = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        m = M.StyledConv(64, 32, 3, sdim, upsample=True, conv_transpose=True)
+        m.conv.form = 'weight'
+        m.noise.weight.data.fill_(0.3)
+        m.activate.bias.data.normal_()
+        if not fused:
+            m.conv.FUSE_UP_MAX_IN_CHANNELS = 0
+        m.to(DEV)
+        assert bool(m.conv.fuses_up(h, h)) == fused
+        x, s = x0.clone().requires_grad_(True), s0.clone().requires_grad_(True)
+        ps = (x, s, m.conv.weight, m.conv.modulation.weight, m.noise.weight, m.activate.bias)
+        y = m(x, s, noise=noise)
+        g = torch.autograd.grad(y, ps, gy, create_graph=True)
+        gg = torch.autograd.grad(g[1].float().pow(2).sum(), (s, m.conv.weight, m.conv.modulation.weight))
+        g1 = torch.autograd.grad(m(x, s, noise=noise), ps, gy)
+        res.append((y, g, gg, g1))
+    (y, g, gg, g1), (yr, gr, ggr, g1r) = res
+    assert y.shape == yr.shape and rel_err(y, yr) < tol1
+    for a, r in zip(g + g1, gr + g1r):
+        assert rel_err(a, r) < tol1
+    for a, r in zip(gg, ggr):
+        assert rel_err(a, r) < tol2
+
+    x0 = rnd(311, b, 32, 2 * h, 2 * h).to(DEV, dt).contiguous(memory_format=torch.channels_last)
+    gy = rnd(312, b, 64, h, h).to(DEV, dt)
+    res = []
+    for fused in (True, False):
+        torch.manual_seed(11)
+        m = M.ConvLayer(32, 64, 3, downsample=True)
+        m[2].bias.data.normal_()
+        assert m.fuse_down
+        m.fuse_down = fused
+        m.to(DEV)
+        x = x0.clone().requires_grad_(True)
+        ps = (x, m[1].weight, m[2].bias)
+        y = m(x, out_scale=0.7)
+        g = torch.autograd.grad(y, ps, gy, create_graph=True)
+        gg = torch.autograd.grad(g[0].float().pow(2).sum(), (x, m[1].weight))
+        g1 = torch.autograd.grad(m(x, out_scale=0.7), ps, gy)
+        res.append((y, g, gg, g1))
+    (y, g, gg, g1), (yr, gr, ggr, g1r) = res
+    assert y.shape == yr.shape and rel_err(y, yr) < tol1
+    for a, r in zip(g + g1, gr + g1r):
+        assert rel_err(a, r) < tol1
+    for a, r in zip(gg, ggr):
+        assert rel_err(a, r) < tol2
