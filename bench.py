@@ -136,28 +136,49 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def conv_roofline(torch, K, dtype, size, batch):
-    """Dominant kernel = the modulated / plain 3x3 convolution.  Time the forward convolution of the
-    layer with the most FLOPs per launch at this resolution, alone, with CUDA events on the launching
-    stream, inputs >> L2."""
-    # the 64ch 3x3 conv at size/2 (G conv512 / D res512.conv1 at size 1024): 19.33 GFLOP/img
-    res = size // 2
-    ch = {1024: 64, 512: 128, 256: 256}.get(size, 64)
-    x = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
-    w = (torch.randn(1, 3, 3, ch, ch, device='cuda') / (3 * ch ** 0.5)).to(dtype)
-    flops = 2.0 * batch * res * res * ch * ch * 9
-    for _ in range(3):
-        K.conv_fwd(x, w, res, res, 1, 1, 1)
-    torch.cuda.synchronize()
-    reps = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        K.conv_fwd(x, w, res, res, 1, 1, 1)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    return flops / (ms * 1e-3) / 1e12, ms, f'conv3x3 {ch}->{ch} @{res}x{res} batch {batch}'
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at batch 16, from the `ncu --set full` captures summarised in
+# profiles/r01_ncu_kernels.md (None where the layer has not been captured)
+NCU_TRAFFIC_BYTES = {'conv3x3 128->128 @256x256 batch 16': 268.762e6 + 220.351e6,
+                     'conv3x3 64->64 @512x512 batch 16': 537.110e6 + 487.299e6,
+                     'conv3x3 32->32 @1024x1024 batch 16': 1.073810e9 + 1.025126e9}
+
+
+def conv_roofline(torch, K, dtype, size, batch, peaks):
+    """The dominant kernels = the 3x3 convolutions (conv_fwd_umma_kernel has the largest share of the step,
+    conv_fwd_halo_kernel the second, profiles/).  Each layer class of the resolution is timed alone with CUDA events
+    on the launching stream (inputs >> L2, L2 flushed between launches) against the roofline that bounds it:
+    tensor pipe (algorithmic 2*MAC FLOPs) for >= 64 channels, HBM (input read once + output written once) for the
+    32-channel full-resolution layer.  Returns (headline, all layers)."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    layers = [(size // 8, 256, 'tensor'), (size // 4, 128, 'tensor'), (size // 2, 64, 'tensor'), (size, 32, 'hbm')]
+    out = []
+    for res, ch, bound in layers:
+        x = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
+        w = (torch.randn(batch, 3, 3, ch, ch, device='cuda') / (3 * ch ** 0.5)).to(dtype)     # per-sample (modulated) weights
+        flops = 2.0 * batch * res * res * ch * ch * 9
+        nbytes = 2.0 * batch * res * res * ch * x.element_size()
+        for _ in range(3):
+            K.conv_fwd(x, w, res, res, 1, 1, 1)
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            K.conv_fwd(x, w, res, res, 1, 1, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sum(ts) / len(ts)
+        what = f'conv3x3 {ch}->{ch} @{res}x{res} batch {batch}'
+        if bound == 'tensor':
+            ach, peak, unit = flops / (ms * 1e-3) / 1e12, peaks.get('bf16_tflops', 1590.0), 'TFLOP/s'
+        else:
+            ach, peak, unit = nbytes / (ms * 1e-3) / 1e9, peaks.get('hbm_gbs', 6650.0), 'GB/s'
+        out.append({'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
+                    'traffic': NCU_TRAFFIC_BYTES.get(what) if batch == 16 else None, 'kernel': what, 'kernel_ms': ms,
+                    'algorithmic_flops': flops, 'algorithmic_bytes': nbytes})
+        del x, w
+    return out[0], out
 
 
 def run_b200(args):
@@ -264,10 +285,9 @@ def run_b200(args):
         'step_tflops': GFLOP_PER_IMG.get(size, 0) * value / 1e3,
     }
     if not args.skip_roofline:
-        tf, ms, what = conv_roofline(torch, K, act, size, batch)
-        peak = peaks.get('bf16_tflops', 1590.0)
-        line['roofline'] = {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak,
-                            'traffic': None, 'kernel': what, 'kernel_ms': ms, 'peak_source': peak_kind + ' (burst, kernel timed alone)'}
+        head, layers = conv_roofline(torch, K, act, size, batch, peaks)
+        line['roofline'] = dict(head, peak_source=peak_kind + ' (burst, kernel timed alone)')
+        line['roofline_layers'] = layers
     if not args.skip_cpu_baseline:
         threads = os.cpu_count() or 1
         csize = args.cpu_sample_size or size

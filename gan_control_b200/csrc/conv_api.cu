@@ -23,7 +23,9 @@ static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, c
     const bool packed = g.pack_in || g.pack_out;
     if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
         return conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st);
-    if (g_conv_engine.load() == 0 && b > 0 && conv_fwd_halo_eligible(dtype, g, x, w, y))
+    // the halo kernel's epilogue reads bias / rowscale as float4
+    if (g_conv_engine.load() == 0 && b > 0 && (((uintptr_t)bias | (uintptr_t)rowscale) & 15) == 0 &&
+        conv_fwd_halo_eligible(dtype, g, x, w, y))
         return conv_fwd_halo(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st);
     if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
         return conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st);

@@ -364,6 +364,18 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
     if (p.TN > g.b) p.TN = g.b;
     p.rows = p.TW * p.TH * p.TN;
     p.BN = g.oc <= 256 ? g.oc : (g.oc % 256 == 0 ? 256 : 128);
+    // Low-resolution layers (4^2 .. 32^2) have only a handful of pixel tiles, and each tile walks the whole K = taps*IC
+    // loop serially (512 -> 512: 288 MMAs): with BN = 256 a 8^2 layer occupies 16 of the 148 SMs for 288 x 128 clk.
+    // Narrower N tiles spread the same work over more SMs (the A tile is re-read from L2 per N tile; an MMA costs
+    // 32 + N/4 clk for N <= 128, scripts/umma_pacing.cu, so the total tensor time grows only mildly).
+    {
+        int m_tiles = 0;
+        for (int i = 0; i < p.n_phases; ++i) {
+            const FwdPhase& P = p.phase[i];
+            m_tiles += ((P.ph + p.TH - 1) / p.TH) * ((P.pw + p.TW - 1) / p.TW) * ((g.b + p.TN - 1) / p.TN);
+        }
+        while (p.BN > 32 && p.BN % 32 == 0 && m_tiles * (g.oc / p.BN) < sm_count() && g.oc % (p.BN / 2) == 0) p.BN /= 2;
+    }
     p.n_oc_tiles = g.oc / p.BN;
     p.row_bytes = g.ic >= 64 ? 128 : 64;
     p.layout = p.row_bytes == 128 ? LAYOUT_SW128 : LAYOUT_SW64;

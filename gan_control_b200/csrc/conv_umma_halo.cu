@@ -11,6 +11,7 @@
 //   * all taps of the (per-sample) weights stay resident in shared memory while consecutive tiles use
 //     the same sample, so steady-state traffic per tile is the activation halo only.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "conv.cuh"
@@ -20,7 +21,8 @@ namespace b200gan {
 
 using namespace umma;
 
-constexpr int kHaloThreads = 256;
+constexpr int kHaloThreads = 384;            // warps 0-2: TMA / MMA / TMEM alloc, 4-7 and 8-11: two epilogue groups
+constexpr int kHaloAcc = 4;                  // TMEM accumulators in flight (tiles alternate between the epilogue groups)
 constexpr int kHTW = 8, kHTH = 16;
 
 struct HaloParams {
@@ -42,18 +44,26 @@ struct HaloParams {
     const float* noise_w;
     float slope, gain;
     int has_ep;
+    int dbg;                             // B200GAN_HALO_DEBUG (timing experiments only): 1 no MMA, 2 no TMA loads, 4 no stores, 8 no tcgen05.ld
     __nv_bfloat16* y;
 };
 
-// 16 accumulator columns of one pixel -> epilogue -> 32 bytes of bf16
+// 16 accumulator columns of one pixel -> epilogue -> 32 bytes of bf16.  rs / bs: 16 floats each, 16-byte aligned
+// (warp-uniform addresses: four broadcast LDG.128 each instead of 16 scalar loads).
 __device__ __forceinline__ void epilogue_store16(const HaloParams& p, float (&v)[16], __nv_bfloat16* dst, const float* rs,
                                                  const float* bs, float nz) {
     if (p.has_ep) {
+        float r[16], b[16];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float4 r4 = rs ? __ldg(reinterpret_cast<const float4*>(rs) + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 b4 = bs ? __ldg(reinterpret_cast<const float4*>(bs) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[4 * e] = r4.x; r[4 * e + 1] = r4.y; r[4 * e + 2] = r4.z; r[4 * e + 3] = r4.w;
+            b[4 * e] = b4.x; b[4 * e + 1] = b4.y; b[4 * e + 2] = b4.z; b[4 * e + 3] = b4.w;
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-            float u = v[e];
-            if (rs) u *= rs[e];
-            u += nz + (bs ? bs[e] : 0.f);
+            const float u = fmaf(v[e], r[e], nz + b[e]);
             v[e] = p.gain * (u > 0.f ? u : u * p.slope);
         }
     }
@@ -83,8 +93,8 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint64_t* aempty = afull + p.a_stages;
     uint64_t* wfull = aempty + p.a_stages;
     uint64_t* tfull = wfull + 1;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + kHaloAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kHaloAcc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -94,7 +104,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
         mbar_init(wfull, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+        for (int a = 0; a < kHaloAcc; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -129,7 +139,9 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
             for (int c = 0; c < p.kchunks; ++c) {
                 mbar_wait(aempty + stage, par ^ 1);
-                if (elect_one()) {
+                if (p.dbg & 2) {
+                    if (elect_one()) mbar_arrive(afull + stage);
+                } else if (elect_one()) {
                     mbar_arrive_expect_tx(afull + stage, (uint32_t)p.a_stage_bytes);
                     if (p.pack_in)      // chunk c = (row phase py, channel chunk of the 2*C contiguous (px, c) elements)
                         tma_load_5d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, (c % p.cpp) * p.kc, w0 - p.pad0,
@@ -168,7 +180,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 wpar ^= 1;
                 key = wkey;
             }
-            const int acc = it & 1, acc_par = (it >> 1) & 1;
+            const int acc = it % kHaloAcc, acc_par = (it / kHaloAcc) & 1;
             mbar_wait(tempty + acc, acc_par ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * bn);
@@ -180,6 +192,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint32_t w_base = w_lo0 + (uint32_t)c * w_inc;
 #pragma unroll
                     for (int tap = 0; tap < taps; ++tap) {
+                        if (p.dbg & 1) break;
                         const uint32_t a_lo = a_base + (uint32_t)((tap / KDIM) * PW + (tap % KDIM)) * ROW_UNITS;
                         const uint32_t w_lo = w_base + (uint32_t)tap * w_tap;
 #pragma unroll
@@ -198,20 +211,22 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int q = warp - 4;
+        // ================= epilogue: two groups of four warps, tiles alternate between them =================
+        // ncu (profiles/r01_ncu_kernels.md, 32->32 @1024^2): with ONE group and two accumulators the kernel ran at
+        // 1340 clk per tile against 720 clk of HBM time: the epilogue warps were busy ~58 % of it (64 scalar side loads
+        // per lane, the noise load's DRAM latency exposed after the accumulator wait) and the MMA warp could not run
+        // more than one tile ahead.  Now: four accumulators, two groups, noise fetched BEFORE the wait, vector side loads.
+        const int q = warp & 3, group = (warp - 4) >> 2;      // TMEM lane quadrant = warp % 4
         const int r = q * 32 + lane;
         const int w_l = r % kHTW, h_l = r / kHTW;
         const float nw = (p.noise != nullptr && p.noise_w != nullptr) ? *p.noise_w : 0.f;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        int it = group;
+        for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
             uint32_t n, t, th, tw;
             p.div_img.divmod((uint32_t)tile, n, t);
             p.div_tw.divmod(t, th, tw);
             const int oy = (int)th * kHTH + h_l, ox = (int)tw * kHTW + w_l;
-            const int acc = it & 1, acc_par = (it >> 1) & 1;
-            mbar_wait(tfull + acc, acc_par);
-            tc_fence_after();
+            const int acc = it % kHaloAcc, acc_par = (it / kHaloAcc) & 1;
             const bool valid = oy < p.OH && ox < p.OW;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
             if (!p.pack_out) {
@@ -219,23 +234,34 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 __nv_bfloat16* dst = p.y + pix * p.OC;
                 const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
                 const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
+                mbar_wait(tfull + acc, acc_par);
+                tc_fence_after();
                 for (int c0 = 0; c0 < p.BN; c0 += 16) {
                     float v[16];
-                    tmem_ld_x16(taddr + (uint32_t)c0, v);
-                    if (valid) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz);
+                    if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)c0, v);
+                    if (valid && !(p.dbg & 4)) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz);
                 }
             } else {
                 // depth-to-space: accumulator columns [(py*2+px)*CQ + c] of view pixel (oy, ox) are channel c of the
                 // physical pixel (2*oy+py, 2*ox+px); bias / rowscale / noise follow the physical tensor
                 const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.CQ : nullptr;
+                const int64_t pix0 = ((int64_t)n * (2 * p.OH) + 2 * oy) * (2 * p.OW) + 2 * ox;
+                float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid && p.noise) {
+                    const __nv_bfloat162 n0 = *reinterpret_cast<const __nv_bfloat162*>(p.noise + pix0);
+                    const __nv_bfloat162 n1 = *reinterpret_cast<const __nv_bfloat162*>(p.noise + pix0 + 2 * p.OW);
+                    nz[0] = nw * __low2float(n0); nz[1] = nw * __high2float(n0);
+                    nz[2] = nw * __low2float(n1); nz[3] = nw * __high2float(n1);
+                }
+                mbar_wait(tfull + acc, acc_par);
+                tc_fence_after();
+#pragma unroll
                 for (int ph = 0; ph < 4; ++ph) {
-                    const int64_t pix = ((int64_t)n * (2 * p.OH) + 2 * oy + (ph >> 1)) * (2 * p.OW) + 2 * ox + (ph & 1);
-                    __nv_bfloat16* dst = p.y + pix * p.CQ;
-                    const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
+                    __nv_bfloat16* dst = p.y + (pix0 + (ph >> 1) * (2 * p.OW) + (ph & 1)) * p.CQ;
                     for (int c0 = 0; c0 < p.CQ; c0 += 16) {
                         float v[16];
-                        tmem_ld_x16(taddr + (uint32_t)(ph * p.CQ + c0), v);
-                        if (valid) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz);
+                        if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)(ph * p.CQ + c0), v);
+                        if (valid && !(p.dbg & 4)) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz[ph]);
                     }
                 }
             }
@@ -310,12 +336,13 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.div_tw = make_fastdiv((uint32_t)p.tiles_w);
     if (!halo_plan(g, p)) return B200GAN_ENOSUP;
     int cols = 32;
-    while (cols < 2 * p.BN) cols <<= 1;
+    while (cols < kHaloAcc * p.BN) cols <<= 1;
     p.tmem_cols = cols;
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
     p.slope = slope; p.gain = gain;
     p.has_ep = (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0;
     p.y = (__nv_bfloat16*)y;
+    if (const char* e = getenv("B200GAN_HALO_DEBUG")) p.dbg = atoi(e);
 
     CUtensorMap map_x, map_w;
     if (g.pack_in) {
@@ -343,7 +370,7 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
         if (int e = encode_bf16_map(&map_w, w, 3, dims, strides, box, es, p.row_bytes)) return e;
     }
     const size_t smem = 1024 + ((size_t)(p.w_bytes + 1023) & ~(size_t)1023) + (size_t)p.a_stages * p.a_stage_bytes +
-                        (2 * p.a_stages + 5) * sizeof(uint64_t) + 16;
+                        (2 * p.a_stages + 1 + 2 * kHaloAcc) * sizeof(uint64_t) + 16;
     static thread_local int attr_dev = -1;
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);

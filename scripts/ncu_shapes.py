@@ -1,5 +1,5 @@
 """Launch one convolution shape twice (warm + profiled) for `ncu --set full --launch-skip 1 -c 1`.
-    python scripts/ncu_shapes.py {c32|c64|up64|down32} [wgrad]"""
+    python scripts/ncu_shapes.py {c32|c64|up64|down32|upfused|downfused} [wgrad]"""
 import os
 import sys
 
@@ -16,11 +16,25 @@ wgrad = len(sys.argv) > 2 and sys.argv[2] == 'wgrad'
 B, bf, dev = 16, torch.bfloat16, 'cuda'
 # name: (h, ic, oc, k, up, down, pad0, out)
 shapes = {'c32': (1024, 32, 32, 3, 1, 1, 1, 1024), 'c64': (512, 64, 64, 3, 1, 1, 1, 512),
+          'c128': (256, 128, 128, 3, 1, 1, 1, 256), 'c256': (128, 256, 256, 3, 1, 1, 1, 128),
           'up64': (512, 64, 32, 3, 2, 1, 2, 1025), 'down32': (1025, 32, 64, 3, 1, 2, 0, 512)}
-h, ic, oc, k, up, down, pad0, oh = shapes[which]
+h, ic, oc, k, up, down, pad0, oh = shapes.get(which, shapes['c32'])
 x = torch.randn(B, h, h, ic, device=dev).to(bf)
 w = (torch.randn(1, k, k, oc, ic, device=dev) / (k * ic ** 0.5)).to(bf)
 gy = torch.randn(B, oh, oh, oc, device=dev).to(bf)
+packed = {'upfused': (512, 64, 128, True, False, True), 'downfused': (512, 128, 64, False, True, False)}
+if which in packed:
+    h, ic, oc, ps, pin, pout = packed[which]
+    x = torch.randn(B, 2 * h, 2 * h, ic // 4, device=dev).to(bf) if pin else torch.randn(B, h, h, ic, device=dev).to(bf)
+    w = (torch.randn(B if ps else 1, 3, 3, oc, ic, device=dev) / (ic * 9) ** 0.5).to(bf)
+    gy = torch.randn(B, 2 * h, 2 * h, oc // 4, device=dev).to(bf) if pout else torch.randn(B, h, h, oc, device=dev).to(bf)
+    for _ in range(2):
+        if wgrad:
+            K.conv_wgrad(x, gy, 3, 3, 1, 1, 1, ps, pack_x=pin, pack_gy=pout)
+        else:
+            K.conv_fwd(x, w, h, h, 1, 1, 1, pack_in=pin, pack_out=pout)
+    torch.cuda.synchronize()
+    sys.exit(0)
 for _ in range(2):
     if wgrad:
         K.conv_wgrad(x, gy, k, k, up, down, pad0, False)
