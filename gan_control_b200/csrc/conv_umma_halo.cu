@@ -21,8 +21,9 @@ namespace b200gan {
 
 using namespace umma;
 
-constexpr int kHaloThreads = 384;            // warps 0-2: TMA / MMA / TMEM alloc, 4-7 and 8-11: two epilogue groups
-constexpr int kHaloAcc = 4;                  // TMEM accumulators in flight (tiles alternate between the epilogue groups)
+constexpr int kHaloThreads = 384;            // warp 0: TMA, 1-3: MMA issuers (2 also allocates TMEM), 4-7 and 8-11: two epilogue groups
+constexpr int kHaloIssuers = 3;              // MMA-issuing warps (1, 2, 3), tiles round-robin
+constexpr int kHaloAcc = 6;                  // max TMEM accumulators in flight (HaloParams::nacc in use; tiles alternate between the epilogue groups)
 constexpr int kHTW = 8, kHTH = 16;
 
 struct HaloParams {
@@ -37,6 +38,11 @@ struct HaloParams {
     int cpp;                             // pack_in: channel chunks per row phase py
     int CQ;                              // pack_out: physical output channels (= OC / 4)
     int a_stages, a_stage_bytes, w_tile_bytes, w_bytes;
+    // Tiles go round-robin over `issuers` MMA warps, `nacc` accumulators and the two epilogue groups.  mbarrier waits
+    // only see a phase PARITY, so every waiter must observe each barrier's phases one by one: issuers and the epilogue
+    // group count (2) both divide nacc (an accumulator always belongs to the same issuer and the same group), and
+    // issuers <= a_stages / kchunks (the previous fill of a stage is then complete when a warp returns to it).
+    int issuers, nacc;
     int tmem_cols;
     const float* bias;
     const float* rowscale;
@@ -116,18 +122,24 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
     if (warp == 0) {
         // ================= TMA producer (whole warp, elected lane issues) =================
-        int stage = 0, par = 0, key = -1;
-        int last_stage = -1, last_par = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int stage = 0, par = 0, key = -1, it = 0;
+        int last_stage[kHaloIssuers], last_par[kHaloIssuers];       // last stage of the most recent tiles (one per MMA warp)
+#pragma unroll
+        for (int k = 0; k < kHaloIssuers; ++k) { last_stage[k] = -1; last_par[k] = 0; }
+        int hist = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             uint32_t n, t, th, tw;
             p.div_img.divmod((uint32_t)tile, n, t);
             p.div_tw.divmod(t, th, tw);
             const int h0 = (int)th * kHTH, w0 = (int)tw * kHTW;
             const int wkey = p.w_per_sample ? (int)n : 0;
             if (wkey != key) {
-                // drain: every MMA that reads the resident weights has completed once the most recently
-                // filled activation stage has been released
-                if (last_stage >= 0) mbar_wait(aempty + last_stage, last_par);
+                // drain: every MMA that reads the resident weights has completed once the last activation stage of
+                // each of the most recent tiles (one per MMA-issuing warp: a commit covers its own thread's MMAs)
+                // has been released
+#pragma unroll
+                for (int k = 0; k < kHaloIssuers; ++k)
+                    if (last_stage[k] >= 0) mbar_wait(aempty + last_stage[k], last_par[k]);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(wfull, (uint32_t)p.w_bytes);
                     for (int tp = 0; tp < taps; ++tp)
@@ -150,12 +162,26 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, afull + stage, c * p.kc, w0 - p.pad0, h0 - p.pad0, (int)n);
                 }
                 __syncwarp();
-                last_stage = stage; last_par = par;
+                // this stage's previous use was released before the refill above, so a recorded (stage, parity) of that
+                // use is stale -- waiting for its parity again would alias a LATER phase of the same barrier and hang
+#pragma unroll
+                for (int k = 0; k < kHaloIssuers; ++k) {
+                    if (last_stage[k] == stage) last_stage[k] = -1;
+                    if (k == hist) { last_stage[k] = stage; last_par[k] = par; }
+                }
                 if (++stage == p.a_stages) { stage = 0; par ^= 1; }
             }
+            if (++hist == p.issuers) hist = 0;
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer (whole warp, elected lane issues) =================
+    } else if (warp >= 1 && warp <= p.issuers) {
+        // ================= kHaloIssuers MMA issuers (whole warp, elected lane issues), tiles round-robin =================
+        // The per-tile protocol of an issuing warp (tile decode, two mbarrier waits + fences, elect, two commits) costs
+        // ~600 clk during which the 8-deep tcgen05 queue drains (profiles/r01_umma_pacing.md: the MMA stream alone took
+        // 1408 clk per tile for 720 clk of pipe time).  Several warps issue tiles round-robin, so one warp's protocol
+        // overlaps the others' MMAs (measured 32->32 @1024^2: 0.66 ms with one issuer, 0.56 ms with two, 0.48 ms with three).
+        // All walk every tile (weight-buffer phases and the stage ring are sequential) but issue only their own.
+        const int mine = warp - 1;
+        int turn = 0;
         // ncu on the first version (run-time tap loop): this ONE warp bounds the kernel -- 266 dependent, mostly
         // uniform-datapath instructions per tile at ~7 clk each = the whole 1820-clk tile period, tensor pipe 17 %
         // active, the TMA producer and the epilogue warps waiting on it (profiles/r01_halo_mma_issue.md).  Now the
@@ -180,7 +206,14 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 wpar ^= 1;
                 key = wkey;
             }
-            const int acc = it % kHaloAcc, acc_par = (it / kHaloAcc) & 1;
+            const bool skip = turn != mine;
+            if (++turn == p.issuers) turn = 0;
+            if (skip) {                                 // another warp's tile: only advance the stage ring
+                for (int c = 0; c < kchunks; ++c)
+                    if (++stage == nstages) { stage = 0; par ^= 1; }
+                continue;
+            }
+            const int acc = it % p.nacc, acc_par = (it / p.nacc) & 1;
             mbar_wait(tempty + acc, acc_par ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * bn);
@@ -226,7 +259,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             p.div_img.divmod((uint32_t)tile, n, t);
             p.div_tw.divmod(t, th, tw);
             const int oy = (int)th * kHTH + h_l, ox = (int)tw * kHTW + w_l;
-            const int acc = it % kHaloAcc, acc_par = (it / kHaloAcc) & 1;
+            const int acc = it % p.nacc, acc_par = (it / p.nacc) & 1;
             const bool valid = oy < p.OH && ox < p.OW;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
             if (!p.pack_out) {
@@ -335,8 +368,14 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.div_img = make_fastdiv((uint32_t)(p.tiles_h * p.tiles_w));
     p.div_tw = make_fastdiv((uint32_t)p.tiles_w);
     if (!halo_plan(g, p)) return B200GAN_ENOSUP;
+    // see HaloParams::issuers
+    const int ring_tiles = p.a_stages / p.kchunks;
+    p.nacc = p.BN <= 64 ? 6 : 4;
+    p.issuers = p.BN <= 64 ? kHaloIssuers : 2;
+    if (p.issuers > ring_tiles) p.issuers = ring_tiles;
+    if (p.issuers < 1) return B200GAN_ENOSUP;
     int cols = 32;
-    while (cols < kHaloAcc * p.BN) cols <<= 1;
+    while (cols < p.nacc * p.BN) cols <<= 1;
     p.tmem_cols = cols;
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
     p.slope = slope; p.gain = gain;
