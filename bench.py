@@ -138,7 +138,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at batch 16, from the `ncu --set full` captures summarised in
 # profiles/r01_ncu_kernels.md (None where the layer has not been captured)
-NCU_TRAFFIC_BYTES = {'conv3x3 128->128 @256x256 batch 16': 268.762e6 + 220.351e6,
+NCU_TRAFFIC_BYTES = {'conv3x3 256->256 @128x128 batch 16': 135.4e6 + 85.79e6,
+                     'conv3x3 128->128 @256x256 batch 16': 268.762e6 + 220.351e6,
                      'conv3x3 64->64 @512x512 batch 16': 537.110e6 + 487.299e6,
                      'conv3x3 32->32 @1024x1024 batch 16': 1.073810e9 + 1.025126e9}
 

@@ -16,6 +16,7 @@ wgrad = len(sys.argv) > 2 and sys.argv[2] == 'wgrad'
 B, bf, dev = 16, torch.bfloat16, 'cuda'
 # name: (h, ic, oc, k, up, down, pad0, out)
 shapes = {'c32': (1024, 32, 32, 3, 1, 1, 1, 1024), 'c64': (512, 64, 64, 3, 1, 1, 1, 512),
+          'torgb': (1024, 32, 3, 1, 1, 1, 0, 1024), 'fromrgb': (1024, 3, 32, 1, 1, 1, 0, 1024),
           'c128': (256, 128, 128, 3, 1, 1, 1, 256), 'c256': (128, 256, 256, 3, 1, 1, 1, 128),
           'up64': (512, 64, 32, 3, 2, 1, 2, 1025), 'down32': (1025, 32, 64, 3, 1, 2, 0, 512)}
 h, ic, oc, k, up, down, pad0, oh = shapes.get(which, shapes['c32'])
