@@ -87,6 +87,14 @@ def measured_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
+def workload_config(size, reg, batch, world):
+    """`config` of the JSON line: the same for this repo's arm and for the reference arm"""
+    return {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]): Generator({size})+Discriminator({size}) '
+                        f'channel_multiplier 2, random init, lazy regularisers at real cadence '
+                        f'(R1 /16, path-length /4)' + ('' if reg else ' DISABLED'),
+            'global_batch': batch * world, 'per_gpu_batch': batch, 'parallelism': f'dp{world}'}
+
+
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_sample(size, threads, reps=1):
     """Bounded sample of the reference's CPU path (oracle port of gan_model.py, fp32, FUSED=False arithmetic):
@@ -128,8 +136,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': t * ratio * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]), reference FUSED=False arithmetic '
-                                   f'on the host CPU, bounded sample', 'global_batch': 1},
+            'config': dict(workload_config(args.size, not args.no_reg, args.batch, args.gpus),
+                           reference_arm='reference FUSED=False arithmetic (oracle port) on the host CPU; every step is a bounded '
+                                         'sample of this workload, see cpu_baseline.sample'),
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -274,11 +283,8 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16' if act == torch.bfloat16 else 'f32', 'data': 'synthetic',
-        'config': {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]): Generator({size})+Discriminator({size}) '
-                               f'channel_multiplier 2, random init, lazy regularisers at real cadence '
-                               f'(R1 /16, path-length /4)' + ('' if reg else ' DISABLED'),
-                   'global_batch': global_batch, 'per_gpu_batch': batch, 'parallelism': f'dp{world}', 'cuda_graphs': use_graph,
-                   'l2': 'inputs larger than L2 (each step streams >10 GB of activations; no explicit flush)'},
+        'config': dict(workload_config(size, reg, batch, world), cuda_graphs=use_graph,
+                       l2='inputs larger than L2 (each step streams >10 GB of activations; no explicit flush)'),
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': host_real.numel() * 4, 'd2h_bytes_per_step': 8},
