@@ -293,6 +293,8 @@ HALO_CASES = [
     (2, 32, 32, 64, 64, 3, False), (3, 64, 64, 64, 64, 3, True), (2, 32, 32, 32, 32, 3, True), (2, 48, 40, 32, 64, 3, False),
     (2, 32, 32, 64, 32, 3, True), (2, 64, 64, 64, 64, 1, False), (2, 40, 24, 32, 32, 1, True), (1, 128, 128, 64, 64, 3, False),
     (5, 17, 9, 64, 16, 3, True),
+    # protocol stress for the multi-issuer kernel: a per-sample weight reload every 1 / 2 / 4 tiles, more samples than SMs
+    (150, 16, 8, 32, 32, 3, True), (160, 16, 16, 64, 64, 3, True), (75, 32, 16, 64, 32, 3, True), (301, 16, 8, 32, 64, 1, True),
 ]
 
 
@@ -349,6 +351,8 @@ PACKED_CASES = [
     (3, 48, 40, 64, 128, False, False, True),     # ... its data gradient, ragged tiles
     (2, 32, 32, 64, 64, False, True, False), (2, 32, 32, 32, 64, True, False, True), (1, 64, 64, 128, 128, False, True, True),
     (2, 8, 8, 16, 32, False, True, True), (2, 6, 10, 32, 16, True, False, True),      # small: CUDA-core engine
+    # protocol stress: per-sample weight reload every 1 / 2 tiles with 2 activation stages (<= 2 issuers) and 2 chunks (1 issuer)
+    (150, 16, 8, 64, 128, True, False, True), (80, 16, 16, 128, 64, True, True, False),
 ]
 
 
