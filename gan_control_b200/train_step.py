@@ -115,6 +115,7 @@ class ParamArena:
         for p, o in zip(self.params, self.offsets):
             assert p.grad is not None and p.grad.data_ptr() == self.grad.data_ptr() + self.grad.element_size() * o, \
                 'a parameter gradient left the flat arena'
+            assert p.data_ptr() == self.data.data_ptr() + self.data.element_size() * o, 'a parameter left the flat arena'
 
 
 class ArenaAdam:
@@ -149,6 +150,56 @@ class ArenaAdam:
                 ema = self.ema.data[lo:hi]
             K.adam_ema(a.data[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], ema, self.lr, self.betas[0],
                        self.betas[1], 1e-8, bias_corr, ema_decay if ema is not None else 0.0, grad_scale)
+
+
+    # -- torch.optim.Adam wire format (the reference checkpoints `g_optim` / `d_optim`, gt.py:852-865, 192-193) ----
+    def _arena_index(self, module):
+        """arena slot of every parameter, in `module.parameters()` order (the order `optim.Adam(model.parameters())`
+        numbers them, gt.py:161-173)"""
+        slot = {id(p): j for j, p in enumerate(self.arena.params)}
+        return [slot[id(p)] for p in module.parameters()]
+
+    def state_dict(self, module):
+        """`torch.optim.Adam(module.parameters(), lr, betas).state_dict()` of the equivalent optimiser: per-parameter
+        `step` / `exp_avg` / `exp_avg_sq` (a parameter of the tail range has stepped only in the non-regularised
+        iterations, exactly like a parameter whose gradient `set_grad_none` dropped, gt.py:594,708)."""
+        a = self.arena
+        order = self._arena_index(module)
+        probe = torch.optim.Adam([torch.zeros(1)], lr=self.lr, betas=self.betas)       # the installed torch's group keys
+        group = dict(probe.state_dict()['param_groups'][0], params=list(range(len(order))))
+        t = self.t.tolist()
+        state = {}
+        for i, j in enumerate(order):
+            lo, n = a.offsets[j], a.params[j].numel()
+            steps = t[1] if lo >= a.split else t[0]
+            if steps <= 0:
+                continue                                   # torch creates the state at a parameter's first step
+            shape = a.params[j].shape
+            state[i] = {'step': torch.tensor(float(steps)),
+                        'exp_avg': self.m[lo:lo + n].view(shape).detach().clone(),
+                        'exp_avg_sq': self.v[lo:lo + n].view(shape).detach().clone()}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, module, sd):
+        a = self.arena
+        order = self._arena_index(module)
+        group = sd['param_groups'][0]
+        assert len(group['params']) == len(order), 'optimizer state is for a different parameter list'
+        self.lr, self.betas = group['lr'], tuple(group['betas'])
+        self.log_betas.copy_(torch.tensor([math.log(b) if b > 0 else -math.inf for b in self.betas], dtype=torch.float64))
+        self.m.zero_()
+        self.v.zero_()
+        steps = [0.0, 0.0]
+        for i, j in enumerate(order):
+            st = sd['state'].get(group['params'][i])
+            if st is None:
+                continue
+            lo, n = a.offsets[j], a.params[j].numel()
+            self.m[lo:lo + n].copy_(st['exp_avg'].reshape(-1))
+            self.v[lo:lo + n].copy_(st['exp_avg_sq'].reshape(-1))
+            which = 1 if lo >= a.split else 0
+            steps[which] = max(steps[which], float(st['step']))
+        self.t.copy_(torch.tensor(steps, dtype=torch.float64))
 
 
 class GradBuckets:
@@ -338,6 +389,50 @@ class GanTrainStep:
         self.g_optim.step(skip_tail=True, grad_scale=1.0 / self.world)                    # set_grad_none gt.py:594
         self.stats['path_loss'] = path_loss.detach()
         return path_loss.detach()
+
+    # -- checkpoints in the reference's wire format (gt.py:852-865 save_nets, :175-193 resume) ---------------------
+    def checkpoint(self):
+        """{'g', 'd', 'g_ema', 'g_optim', 'd_optim'} as `GeneratorTrainer.save_nets` writes them: module state_dicts
+        (same keys / shapes as the reference's, tests/test_host_algebra_cpu.py) and `torch.optim.Adam` state_dicts, so
+        the file resumes either implementation.  The path-length running mean is not part of the reference's
+        checkpoint (it restarts from 0 there as well, gt.py:330); it is stored under an extra key."""
+        cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}
+        out = {'g': cpu(self.g.state_dict()), 'd': cpu(self.d.state_dict()),
+               'g_optim': self.g_optim.state_dict(self.g), 'd_optim': self.d_optim.state_dict(self.d)}
+        if self.g_ema is not None:
+            out['g_ema'] = cpu(self.g_ema.state_dict())
+        for opt in ('g_optim', 'd_optim'):
+            for st in out[opt]['state'].values():
+                st['exp_avg'], st['exp_avg_sq'] = st['exp_avg'].cpu(), st['exp_avg_sq'].cpu()
+        out['b200gan_mean_path_length'] = self.mean_path_length.detach().cpu().clone()
+        return out
+
+    def save_nets(self, i, save_dir, best_fid=False):
+        """`<save_dir>/checkpoint/<iteration, 6 digits>.pt` (gt.py:852-854)"""
+        import os
+        os.makedirs(os.path.join(save_dir, 'checkpoint'), exist_ok=True)
+        path = os.path.join(save_dir, 'checkpoint', 'best_fid.pt' if best_fid else f'{str(i).zfill(6)}.pt')
+        torch.save(self.checkpoint(), path)
+        return path
+
+    def load_checkpoint(self, ckpt):
+        """resume from a reference-format checkpoint (a dict or a path), gt.py:179-193.  Parameters are copied INTO the
+        arena views (the modules keep pointing at the flat buffers; captured CUDA graphs stay valid)."""
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location='cpu')
+        self.g.load_state_dict(ckpt['g'])
+        self.d.load_state_dict(ckpt['d'])
+        if self.g_ema is not None and 'g_ema' in ckpt:
+            self.g_ema.load_state_dict(ckpt['g_ema'])
+        self.g_arena.check_views()
+        self.d_arena.check_views()
+        if 'g_optim' in ckpt:
+            self.g_optim.load_state_dict(self.g, ckpt['g_optim'])
+        if 'd_optim' in ckpt:
+            self.d_optim.load_state_dict(self.d, ckpt['d_optim'])
+        if 'b200gan_mean_path_length' in ckpt:
+            self.mean_path_length.copy_(ckpt['b200gan_mean_path_length'])
+        return self
 
     # -- one iteration (gt.py:343-353: discriminator_update, generator_update) ------------------------
     def train_step(self, i, real_img, regularize=True):

@@ -46,3 +46,17 @@ def test_install_patches_reference(cpu_kernels):
             setattr(gm, k, v)
         sys.modules.pop('gan_control.models.op', None)
         sys.modules.pop('gan_control.models.op.conv2d_gradfix', None)
+
+
+def test_parameter_order_matches_reference():
+    """`optim.Adam(model.parameters())` numbers parameters by registration order (gt.py:161-173): the optimiser entries
+    of a checkpoint interchange only if the new modules register their parameters in the reference's order."""
+    gm, _ = import_reference()
+    from gan_control_b200 import modules as M
+    for size in (16, 64):
+        ref_g = gm.Generator(size, 32, 2, channel_multiplier=2, conv_transpose=True)
+        new_g = M.Generator(size, 32, 2, channel_multiplier=2, conv_transpose=True)
+        assert [(n, tuple(p.shape)) for n, p in ref_g.named_parameters()] == [(n, tuple(p.shape)) for n, p in new_g.named_parameters()]
+        assert list(ref_g.state_dict()) == list(new_g.state_dict())
+        ref_d, new_d = gm.Discriminator(size, channel_multiplier=2), M.Discriminator(size, channel_multiplier=2)
+        assert [(n, tuple(p.shape)) for n, p in ref_d.named_parameters()] == [(n, tuple(p.shape)) for n, p in new_d.named_parameters()]

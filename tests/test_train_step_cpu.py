@@ -44,7 +44,7 @@ def build(batch):
     return g, g_ema, d
 
 
-def oracle_run(batch, real, zs, pl_noise, iters):
+def oracle_run(batch, real, zs, pl_noise, iters, return_optim=False):
     """generator_trainer.py:343-369,407-436,568-599,645-711 restated on the oracle."""
     sd_g = {k: v.clone().requires_grad_(not k.endswith('kernel') and not k.startswith('noises.'))
             for k, v in P.seeded_state_dict(P.generator_shapes(SIZE, SDIM, NMLP, 2), 5, dtype=F64).items()}
@@ -91,15 +91,19 @@ def oracle_run(batch, real, zs, pl_noise, iters):
                     gp[k].grad = None                                   # set_grad_none, gt.py:594
             g_opt.step()
         O.ema_accumulate(ema, sd_g, accum)
+    if return_optim:
+        return sd_g, sd_d, ema, (g_opt, gp), (d_opt, dp)
     return sd_g, sd_d, ema
 
 
-def product_run(batch, real, zs, pl_noise, iters, world=1, rank=0):
+def product_run(batch, real, zs, pl_noise, iters, world=1, rank=0, resume=None, return_step=False):
     g, g_ema, d = build(batch * world)
     if world > 1:   # replica r owns samples r::world of the global batch (strided like minibatch-stddev groups)
         g.fixed_noise = [n[rank::world] for n in g.fixed_noise]
         real = real[rank::world]
     step = GanTrainStep(g, d, g_ema, batch=batch, latent_size=SDIM, world_size=world, bucket_mb=1)
+    if resume is not None:
+        step.load_checkpoint(resume)
     for i in iters:
         z_d, z_g, z_pl = [z[rank::world] if world > 1 else z for z in zs[i]]
         step.discriminator_step(real, [z_d])
@@ -113,6 +117,8 @@ def product_run(batch, real, zs, pl_noise, iters, world=1, rank=0):
             step.ema_arena.data.mul_(step.accum).add_(step.g_arena.data, alpha=1 - step.accum)
         step.g_arena.check_views()
         step.d_arena.check_views()
+    if return_step:
+        return g, d, g_ema, step
     return g, d, g_ema
 
 
@@ -176,3 +182,39 @@ def test_two_replicas_match_one(cpu_kernels, tmp_path):
     compare(g, ddp['g'], 1e-9)
     compare(d, ddp['d'], 1e-9)
     compare(g_ema, ddp['ema'], 1e-9)
+
+
+def test_checkpoint_wire_format(cpu_kernels, tmp_path):
+    """`GanTrainStep.checkpoint()` is the reference's {g, d, g_ema, g_optim, d_optim} file (gt.py:852-865): the optimiser
+    entries equal the state of the torch.optim.Adam that the restated reference step drove (per-parameter step counts
+    included: parameters dropped by set_grad_none in the regularisation steps have stepped once less), torch.optim.Adam
+    loads them, and resuming from the file continues exactly like the uninterrupted run."""
+    batch = 4
+    real, zs, pl_noise = make_inputs(batch)
+    sd_g, sd_d, ema, (g_opt, gp), (d_opt, dp) = oracle_run(batch, real, zs, pl_noise, [0], return_optim=True)
+    g, d, g_ema, step = product_run(batch, real, zs, pl_noise, [0], return_step=True)
+    path = step.save_nets(0, str(tmp_path))
+    assert path.endswith('checkpoint/000000.pt')
+    ckpt = torch.load(path)
+    assert set(ckpt) >= {'g', 'd', 'g_ema', 'g_optim', 'd_optim'}
+    for module, key, (opt, params) in [(g, 'g_optim', (g_opt, gp)), (d, 'd_optim', (d_opt, dp))]:
+        osd = ckpt[key]
+        names = [n for n, _ in module.named_parameters()]
+        assert osd['param_groups'][0]['params'] == list(range(len(names)))
+        assert osd['param_groups'][0]['lr'] == opt.param_groups[0]['lr'] and tuple(osd['param_groups'][0]['betas']) == tuple(opt.param_groups[0]['betas'])
+        for i, n in enumerate(names):
+            ref = opt.state[params[n]]
+            mine = osd['state'][i]
+            assert float(mine['step']) == float(ref['step']), n
+            for k in ('exp_avg', 'exp_avg_sq'):
+                err = float((mine[k] - ref[k]).abs().max() / ref[k].abs().max().clamp_min(1e-30))
+                assert err < 1e-7, (n, k, err)
+        steps = {n: float(osd['state'][i]['step']) for i, n in enumerate(names)}
+        assert max(steps.values()) == 2.0 and min(steps.values()) == 1.0           # iteration 0: plain + regularised step
+        # a real torch.optim.Adam over the same parameter list accepts the entry
+        torch.optim.Adam(list(module.parameters()), lr=1.0).load_state_dict(osd)
+    # resume: iteration 1 from the file == iterations 0, 1 uninterrupted
+    g2, d2, g_ema2 = product_run(batch, real, zs, pl_noise, [1], resume=path)
+    g1, d1, g_ema1 = product_run(batch, real, zs, pl_noise, [0, 1])
+    for a, b in [(g2, g1), (d2, d1), (g_ema2, g_ema1)]:
+        compare(a, b.state_dict(), 1e-12)
