@@ -60,3 +60,36 @@ def test_parameter_order_matches_reference():
         assert list(ref_g.state_dict()) == list(new_g.state_dict())
         ref_d, new_d = gm.Discriminator(size, channel_multiplier=2), M.Discriminator(size, channel_multiplier=2)
         assert [(n, tuple(p.shape)) for n, p in ref_d.named_parameters()] == [(n, tuple(p.shape)) for n, p in new_d.named_parameters()]
+
+
+def test_ada_augment_runs_on_the_registered_op(cpu_kernels):
+    """`trainers/non_leaking.py` imports `upfirdn2d` from `gan_control.models.op` (:6), the package
+    install() registers; its 12x12-tap up=2 / down=2 calls (:338, :359) then run on the new operator and give the same
+    augmented images as the reference's own pure-PyTorch upfirdn2d."""
+    import importlib.util
+    import os
+    import sys
+    from oracle.ref_import import REF_SRC
+    gm, _ = import_reference()
+    saved = {k: getattr(gm, k) for k in dir(gm) if not k.startswith('__')}
+    ref_upfirdn2d = gm.upfirdn2d
+    try:
+        import gan_control_b200
+        gan_control_b200.install(gm)
+        spec = importlib.util.spec_from_file_location('ref_non_leaking_real', os.path.join(REF_SRC, 'gan_control', 'trainers', 'non_leaking.py'))
+        nl = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(nl)                      # `from gan_control.models.op import upfirdn2d` resolves to the new op
+        assert nl.upfirdn2d is sys.modules['gan_control.models.op'].upfirdn2d and nl.upfirdn2d is not ref_upfirdn2d
+        img = rnd(400, 2, 3, 32, 32)
+        torch.manual_seed(7)
+        out_new, _ = nl.augment(img, 1.0)
+        nl.upfirdn2d = ref_upfirdn2d
+        torch.manual_seed(7)
+        out_ref, _ = nl.augment(img, 1.0)
+        assert out_new.shape == out_ref.shape == img.shape
+        assert max_rel(out_new, out_ref) < 1e-9
+    finally:
+        for k, v in saved.items():
+            setattr(gm, k, v)
+        sys.modules.pop('gan_control.models.op', None)
+        sys.modules.pop('gan_control.models.op.conv2d_gradfix', None)
