@@ -302,6 +302,52 @@ class GanTrainStep:
         self.stats = {}
         self.graphs = None
 
+    # -- construction from the reference's config files (configs/*.json, `args.json` of a run) -----------------------
+    @classmethod
+    def from_config(cls, config, device='cuda', world_size=1, act_dtype=torch.bfloat16, **overrides):
+        """Networks and step exactly as `GeneratorTrainer.init_models_and_optim` builds them (gt.py:120-173) from the
+        `model_config` / `training_config` sections of a gan-control config (a dict, or the path of `configs/ffhq.json`
+        or of a run's `args.json`): Generator / g_ema / Discriminator constructor arguments, split-FC layout from
+        `sub_groups_dict`, lazy-regularisation Adam, R1 / path-length weights and cadence, EMA horizon, style mixing.
+        `training_config['batch']` is the GLOBAL batch (the reference scatters it over its DataParallel replicas); each
+        of the `world_size` processes gets batch / world_size.  Resumes from `ckpt_config` when enabled (gt.py:175-193)."""
+        import json
+        from . import modules as M
+        if not isinstance(config, dict):
+            with open(config) as f:
+                config = json.load(f)
+        mc, tc = config['model_config'], config['training_config']
+        if mc.get('marge_fc') or mc.get('vae'):
+            raise NotImplementedError('marge_fc / vae are not used by any shipped config and are not built')
+        if tc.get('mini_batch', tc['batch']) != tc['batch']:
+            raise NotImplementedError('gradient accumulation over mini-batches (mini_batch < batch) is not built: one '
+                                      'process per GPU holds batch / world_size samples')
+        groups = None if mc.get('vanilla') or not mc.get('split_fc') else tc['sub_groups_dict']
+        fc_config = M.FcConfig.from_sub_groups_dict(groups) if groups else None
+
+        def generator():
+            return M.Generator(mc['size'], mc['latent_size'], mc['n_mlp'], channel_multiplier=mc['channel_multiplier'],
+                               out_channels=mc['img_channels'], split_fc=bool(groups), fc_config=fc_config,
+                               conv_transpose=mc['conv_transpose'], noise_mode=mc.get('g_noise_mode', 'normal'),
+                               act_dtype=act_dtype).to(device)
+        g, g_ema = generator(), generator()
+        g_ema.eval()
+        d = M.Discriminator(mc['size'], channel_multiplier=mc['channel_multiplier'], in_channels=mc['img_channels'],
+                            act_dtype=act_dtype).to(device)
+        if tc['batch'] % world_size:
+            raise ValueError('batch %d is not divisible by world size %d' % (tc['batch'], world_size))
+        kw = dict(batch=tc['batch'] // world_size, lr_g=tc['lr_g'], lr_d=tc['lr_d'], r1=tc['r1'], d_reg_every=tc['d_reg_every'],
+                  g_reg_every=tc['g_reg_every'], path_regularize=tc['path_regularize'],
+                  path_batch_shrink=tc['path_batch_shrink'], mixing=tc['mixing'], g_moving_average=tc['g_moving_average'],
+                  latent_size=mc['latent_size'], world_size=world_size, global_batch=tc['batch'])
+        kw.update(overrides)
+        step = cls(g, d, g_ema, **kw)
+        step.config = config
+        ck = config.get('ckpt_config') or {}
+        if ck.get('enabled'):
+            step.load_checkpoint(ck['ckpt'])
+        return step
+
     # -- helpers ------------------------------------------------------------------------------
     @staticmethod
     def requires_grad(model, flag=True):                                                 # tu:13-15

@@ -93,3 +93,39 @@ def test_ada_augment_runs_on_the_registered_op(cpu_kernels):
             setattr(gm, k, v)
         sys.modules.pop('gan_control.models.op', None)
         sys.modules.pop('gan_control.models.op.conv2d_gradfix', None)
+
+
+@pytest.mark.parametrize('name', ['ffhq', 'metfaces', 'afhq'])
+def test_from_config_matches_reference_construction(name):
+    """SURVEY.md 8(f) row 3, config wire format: `GanTrainStep.from_config` on the reference's shipped configs builds the
+    networks `GeneratorTrainer.init_models_and_optim` builds (gt.py:120-157: same state_dict keys and shapes as the
+    reference classes with the reference's own MiniBatchUtils fc_config) and the optimiser / regulariser settings of
+    gt.py:158-173 (resolution reduced to keep the test light)."""
+    import json
+    import os
+    from oracle.ref_import import REF_SRC
+    from gan_control_b200.train_step import GanTrainStep
+    gm, _ = import_reference()
+    from gan_control.utils.mini_batch_multi_split_utils import MiniBatchUtils
+    cfg = json.load(open(os.path.join(REF_SRC, 'gan_control', 'configs', name + '.json')))
+    cfg['model_config']['size'] = 32
+    mc, tc = cfg['model_config'], cfg['training_config']
+    step = GanTrainStep.from_config(cfg, device='cpu', world_size=4, act_dtype=torch.float32)
+    bu = MiniBatchUtils(tc['mini_batch'], tc['sub_groups_dict'], total_batch=tc['batch'])
+    ref_g = gm.Generator(mc['size'], mc['latent_size'], mc['n_mlp'], channel_multiplier=mc['channel_multiplier'],
+                         out_channels=mc['img_channels'], split_fc=mc['split_fc'], marge_fc=mc['marge_fc'],
+                         fc_config=bu.get_fc_config(), conv_transpose=mc['conv_transpose'], noise_mode=mc['g_noise_mode'])
+    ref_d = gm.Discriminator(mc['size'], channel_multiplier=mc['channel_multiplier'], in_channels=mc['img_channels'])
+    shapes = lambda m: [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert shapes(step.g) == shapes(ref_g) and shapes(step.g_ema) == shapes(ref_g) and shapes(step.d) == shapes(ref_d)
+    assert [n for n, _ in step.g.named_parameters()] == [n for n, _ in ref_g.named_parameters()]
+    assert step.batch == tc['batch'] // 4 and step.global_batch == tc['batch']
+    g_ratio, d_ratio = tc['g_reg_every'] / (tc['g_reg_every'] + 1), tc['d_reg_every'] / (tc['d_reg_every'] + 1)
+    assert step.g_optim.lr == tc['lr_g'] * g_ratio and step.g_optim.betas == (0 ** g_ratio, 0.99 ** g_ratio)
+    assert step.d_optim.lr == tc['lr_d'] * d_ratio and step.d_optim.betas == (0 ** d_ratio, 0.99 ** d_ratio)
+    assert (step.r1, step.d_reg_every, step.g_reg_every, step.path_regularize, step.path_batch_shrink, step.mixing) == \
+        (tc['r1'], tc['d_reg_every'], tc['g_reg_every'], tc['path_regularize'], tc['path_batch_shrink'], tc['mixing'])
+    assert step.accum == 0.5 ** (tc['batch'] / tc['g_moving_average'])
+    # g_ema starts as a copy of g (accumulate(g_ema, g, 0), gt.py:156)
+    for (k, a), (_, b) in zip(step.g.named_parameters(), step.g_ema.named_parameters()):
+        assert torch.equal(a, b), k
