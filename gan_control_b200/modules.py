@@ -342,6 +342,8 @@ def _cached_fc_table(module, groups_fn, device):
     tbl = module.__dict__.get('_fc_table')
     if tbl is None or tbl['key'] != key or tbl['table'].device != device:
         tbl = ops.build_fc_table(groups, device)
+        tbl['key'] = key        # group-major, as computed above (build_fc_table lists its tensors layer-major: with more than
+        #                         one group the two orders differ and the table was rebuilt -- an H2D copy -- on every call)
         module.__dict__['_fc_table'] = tbl
     return tbl
 

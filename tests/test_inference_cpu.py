@@ -79,3 +79,17 @@ def test_gen_batch_and_controls(cpu_kernels, tmp_path):
     c2.noise = noise_c
     img2, _, _ = c2.gen_batch_by_controls(latent=w.clone(), input_is_latent=True, normalize=False, pose=pose)
     assert max_rel(img2, img_c) < 1e-6
+
+
+def test_fc_table_is_cached_for_split_fc():
+    """The persistent mapping kernel's layer table must be built once (its H2D copy cannot run inside CUDA-graph capture):
+    with several latent groups the cache key used to be compared in a different order than it was stored in, and the
+    table was rebuilt on every call."""
+    from gan_control_b200 import modules as M
+    groups = {'a': {'place_in_latent': [0, 8]}, 'b': {'place_in_latent': [8, 24]}, 'c': {'place_in_latent': [24, 32]}}
+    g = M.Generator(8, 32, 3, channel_multiplier=2, split_fc=True, fc_config=M.FcConfig.from_sub_groups_dict(groups), conv_transpose=True)
+    t1 = M._cached_fc_table(g, g._mapping_groups, torch.device('cpu'))
+    t2 = M._cached_fc_table(g, g._mapping_groups, torch.device('cpu'))
+    assert t1 is t2 and t1['n_groups'] == 3 and t1['n_layers'] == 3
+    g.style.a[1].weight.data = g.style.a[1].weight.data.clone()          # a parameter moved: rebuilt
+    assert M._cached_fc_table(g, g._mapping_groups, torch.device('cpu')) is not t1
