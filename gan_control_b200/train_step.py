@@ -505,6 +505,7 @@ class GanTrainStep:
         randomness per step, tu:19-23)."""
         assert self.mixing == 0, 'graph capture needs mixing=0 (host-side random control flow)'
         self.static_real = torch.zeros(real_shape, device=self.device)
+        snapshot = self._snapshot()          # the warm-up runs are real optimiser steps on a dummy batch: undone below
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -515,7 +516,7 @@ class GanTrainStep:
                 self._variant('g_reg')
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graphs, self.graph_launches, self.replayed_launches = {}, {}, 0
+        self.graphs, self.graph_launches, self.replayed_launches, self.graph_out = {}, {}, 0, {}
         pool = None
         for name in ('d', 'd_reg', 'g', 'g_reg'):
             graph = torch.cuda.CUDAGraph()
@@ -525,7 +526,29 @@ class GanTrainStep:
             self.graph_launches[name] = K.launch_count() - n0      # libb200gan kernels inside this graph
             pool = graph.pool()
             self.graphs[name] = graph
+            # this variant's loss tensors: the references keep their memory out of the later captures that share the pool
+            # (a dropped one is reused there, and `stats` alone only remembers the LAST variant captured)
+            self.graph_out[name] = dict(self.stats)
+        self._restore(snapshot)
+        torch.cuda.synchronize()
         return self
+
+    def _state_tensors(self):
+        """everything a step mutates that outlives it: parameters, Adam moments and step counts, EMA, path-length mean"""
+        ts = [self.g_arena.data, self.d_arena.data, self.g_optim.m, self.g_optim.v, self.g_optim.t,
+              self.d_optim.m, self.d_optim.v, self.d_optim.t, self.mean_path_length]
+        if self.ema_arena is not None:
+            ts.append(self.ema_arena.data)
+        return ts
+
+    def _snapshot(self):
+        return [t.detach().clone() for t in self._state_tensors()]
+
+    def _restore(self, snapshot):
+        """in place: the tensors are what the modules' parameters view and what captured graphs point at"""
+        with torch.no_grad():
+            for t, s in zip(self._state_tensors(), snapshot):
+                t.copy_(s)
 
     def _replay(self, name):
         self.graphs[name].replay()
@@ -549,5 +572,6 @@ class GanTrainStep:
         self._replay('d')
         if regularize and i % self.d_reg_every == 0:
             self._replay('d_reg')
-        self._replay('g_reg' if regularize and i % self.g_reg_every == 0 else 'g')
-        return self.stats['d_loss'], self.stats['g_loss']
+        g_name = 'g_reg' if regularize and i % self.g_reg_every == 0 else 'g'
+        self._replay(g_name)
+        return self.graph_out['d']['d_loss'], self.graph_out[g_name]['g_loss']

@@ -43,3 +43,49 @@ def test_train_checkpoint_resume_and_inference(cpu_kernels, tmp_path):
     assert ckpt_iter == '000005' and latent_size == 32 and not groups
     for (k, a), (_, b) in zip(g.named_parameters(), step2.g_ema.named_parameters()):
         assert torch.equal(a, b.detach()), k
+
+
+def test_snapshot_restore_undoes_steps(cpu_kernels):
+    """`GanTrainStep.capture` runs warm-up iterations before recording the CUDA graphs; `_snapshot` / `_restore` must bring
+    parameters, Adam state, EMA and the path-length mean back exactly (in place: modules keep viewing the arenas)."""
+    from gan_control_b200.train_step import GanTrainStep
+    torch.manual_seed(0)
+    step = GanTrainStep.from_config(json.loads(json.dumps(CONFIG)), device='cpu', act_dtype=torch.float32, mixing=0)
+    real = torch.randn(4, 3, 8, 8).clamp_(-1, 1)
+    step.train_step(1, real)                                   # some non-trivial optimiser state first
+    before = [t.clone() for t in step._state_tensors()]
+    ptrs = [p.data_ptr() for p in step.g.parameters()]
+    snap = step._snapshot()
+    step.train_step(0, real)                                   # both regularisers: every state tensor changes
+    assert any(not torch.equal(a, b) for a, b in zip(before, step._state_tensors()))
+    step._restore(snap)
+    assert all(torch.equal(a, b) for a, b in zip(before, step._state_tensors()))
+    assert ptrs == [p.data_ptr() for p in step.g.parameters()]
+    step.g_arena.check_views()
+
+
+def test_graphed_step_returns_the_replayed_variants_losses(cpu_kernels):
+    """train_step_graphed hands back the loss tensors of the graphs it replayed (each variant keeps its own): checked here
+    with stand-in graph objects, the capture itself needs CUDA (scripts/train_smoke.py)."""
+    from gan_control_b200.train_step import GanTrainStep
+    step = GanTrainStep.from_config(json.loads(json.dumps(CONFIG)), device='cpu', act_dtype=torch.float32, mixing=0)
+    replayed = []
+
+    class FakeGraph:
+        def __init__(self, name):
+            self.name = name
+
+        def replay(self):
+            replayed.append(self.name)
+    step.static_real = torch.zeros(4, 3, 8, 8)
+    step.graphs = {n: FakeGraph(n) for n in ('d', 'd_reg', 'g', 'g_reg')}
+    step.graph_launches = {n: 1 for n in step.graphs}
+    step.replayed_launches = 0
+    step.graph_out = {'d': {'d_loss': torch.tensor(1.0)}, 'd_reg': {'r1_loss': torch.tensor(2.0)},
+                      'g': {'g_loss': torch.tensor(3.0)}, 'g_reg': {'g_loss': torch.tensor(4.0), 'path_loss': torch.tensor(5.0)}}
+    real = torch.ones(4, 3, 8, 8)
+    d0, g0 = step.train_step_graphed(0, real)
+    d1, g1 = step.train_step_graphed(1, real)
+    assert replayed == ['d', 'd_reg', 'g_reg', 'd', 'g'] and step.replayed_launches == 5
+    assert (float(d0), float(g0), float(d1), float(g1)) == (1.0, 4.0, 1.0, 3.0)
+    assert torch.equal(step.static_real, real)
