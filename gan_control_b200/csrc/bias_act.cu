@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256, 4) epilogue_bwd_vec_kernel(const T* __res
     const float inv_gain = 1.f / gain, inv_gs = 1.f / (gain * slope);
     // Per-thread state is kept small (<= 64 registers, 4 blocks per SM) and two pixels' loads are issued before
     // any use: the first version (76 registers, one vector pair in flight) was latency-bound -- ncu: 8.3
-    // long-scoreboard stalls per issue, 34 % warps active, 51 % of HBM (profiles/r01_streaming_kernels.md).
+    // long-scoreboard stalls per issue, 34 % warps active, 51 % of HBM (profiles/r01_ncu_kernels.md).
     // sd accumulates gz*(u - nw*noise); the bias term and 1/d are applied once at the end:
     //   sum gz*z = (sum gz*(u - nw*noise) - bias*sum gz) / d
     float dv[VEC], sb[VEC], sd[VEC];

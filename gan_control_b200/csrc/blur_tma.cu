@@ -1,7 +1,7 @@
 // Blur (upfirdn2d with up = down = 1, <= 4x4 taps) as a TMA-fed shared-memory stencil, bf16 NHWC.
 //
 // The register-only kernel (upfirdn2d.cu::blur_rows_kernel) is latency-bound: ncu shows 64 % of the
-// stall samples on long_scoreboard at 26 % of HBM bandwidth (profiles/r01_blur.md) -- every thread
+// stall samples on long_scoreboard at 26 % of HBM bandwidth (profiles/r01_ncu_kernels.md) -- every thread
 // waits for its own loads.  Here the loads are decoupled from the threads: an elected thread streams
 // (16+kh-1) x (TW+kw-1)-pixel input tiles through a double-buffered TMA pipeline (out-of-bounds =
 // the zero padding), 128 threads run the separable FIR out of shared memory with rolling row
@@ -34,7 +34,7 @@ struct BlurParams {
 // (row r, column tx + kx) sits at  t*16 + r*PITCH + kx*ROWB, so a warp reads 512 contiguous bytes (conflict-free)
 // and every address in the unrolled row loop is an immediate offset from one per-thread base.  ncu on the first
 // version of this kernel (swizzled tile, run-time strides): issue-bound, 72 % issue-slot utilisation at 41 % of HBM,
-// 250 warp instructions per 8-channel output of which 64 were FMAs (profiles/r01_streaming_kernels.md).  Here the
+// 250 warp instructions per 8-channel output of which 64 were FMAs (profiles/r01_ncu_kernels.md).  Here the
 // address arithmetic is gone, the FMAs are packed (fma.rn.f32x2), and the rolling accumulators are (re)started by
 // the first tap of a row instead of being zeroed.
 template <int CH>

@@ -184,7 +184,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         int turn = 0;
         // ncu on the first version (run-time tap loop): this ONE warp bounds the kernel -- 266 dependent, mostly
         // uniform-datapath instructions per tile at ~7 clk each = the whole 1820-clk tile period, tensor pipe 17 %
-        // active, the TMA producer and the epilogue warps waiting on it (profiles/r01_halo_mma_issue.md).  Now the
+        // active, the TMA producer and the epilogue warps waiting on it (profiles/r01_conv_issue_bound.md, r01_ncu_kernels.md).  Now the
         // taps are unrolled with immediate descriptor offsets and the tile decode is a multiply-high.
         const uint32_t idesc = instr_desc_bf16(128, p.BN, 0, 0);
         constexpr uint32_t PW = KDIM == 1 ? 8 : 16;
