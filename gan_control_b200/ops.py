@@ -331,8 +331,10 @@ def fir_epilogue(x, kernel, pad, d=None, noise=None, noise_w=None, bias=None, up
 # convolution family
 # ---------------------------------------------------------------------------------------------
 def _kernel_layout(w, dtype):
-    """(Bw,OC,IC,KH,KW) parameter layout -> (Bw,KH,KW,OC,IC) K-major operand in `dtype`."""
-    return w.detach().permute(0, 3, 4, 1, 2).to(dtype).contiguous()
+    """(Bw,OC,IC,KH,KW) parameter layout -> (Bw,KH,KW,OC,IC) K-major operand in `dtype`, contiguous.
+    One strided-read / cast / dense-write kernel (`.to(dtype).contiguous()` on the permuted view is two)."""
+    v = w.detach().permute(0, 3, 4, 1, 2)
+    return torch.empty(v.shape, dtype=dtype, device=w.device).copy_(v)
 
 
 def _flip_t(w):

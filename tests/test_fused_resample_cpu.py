@@ -93,3 +93,14 @@ def test_composite_weights_shapes(cpu_kernels):
     w = torch.randn(2, 4, 8, 3, 3, dtype=F64)
     assert ops.composite_up(w, ops.fir_toeplitz(k.double() * 4, False)).shape == (2, 16, 8, 3, 3)
     assert ops.composite_down(w, ops.fir_toeplitz(k.double(), True)).shape == (2, 4, 32, 3, 3)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float64])
+def test_kernel_layout(dtype):
+    """the K-major weight operand: values, dtype and dense layout (kernels.conv_fwd asserts contiguity)"""
+    w = torch.randn(3, 5, 4, 3, 3, dtype=torch.float32, requires_grad=True)
+    for src in (w, w.flip(3, 4).transpose(1, 2)):
+        k = ops._kernel_layout(src, dtype)
+        ref = src.detach().permute(0, 3, 4, 1, 2).to(dtype).contiguous()
+        assert k.dtype == dtype and k.is_contiguous() and not k.requires_grad and k.shape == ref.shape
+        assert torch.equal(k, ref)
