@@ -34,6 +34,10 @@ def op_package():
     gradfix = types.ModuleType('gan_control.models.op.conv2d_gradfix')
     gradfix.conv2d = ops.conv2d
     gradfix.conv_transpose2d = ops.conv_transpose2d
+    # upstream's switches: `with conv2d_gradfix.no_weight_gradients():` around the path-length inner backward
+    gradfix.no_weight_gradients = ops.data_grads_only
+    gradfix.enabled = True
+    gradfix.weight_gradients_disabled = False
     op.conv2d_gradfix = gradfix
     return op, gradfix
 

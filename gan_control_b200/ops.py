@@ -513,9 +513,16 @@ def composite_down(w, toeplitz):
     return c.permute(0, 1, 4, 6, 2, 3, 5).reshape(bw, oc, 4 * ic, 3, 3)
 
 
-def conv2d(input, weight, bias=None, stride=1, padding=0):
-    """``conv2d_gradfix.conv2d`` / ``F.conv2d`` (groups=1, dilation=1).  weight (OC,IC,KH,KW), or
-    (B,OC,IC,KH,KW) for per-sample weights (the reference's groups=batch trick, gm.py:326-329)."""
+def _only_defaults(who, **kw):
+    for k, (v, default) in kw.items():
+        if v != default:
+            raise NotImplementedError(f'{who}: {k}={v!r} is not used on the gan-control path and is not built')
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """``conv2d_gradfix.conv2d`` / ``F.conv2d`` (upstream signature; groups=1, dilation=1 only).  weight (OC,IC,KH,KW),
+    or (B,OC,IC,KH,KW) for per-sample weights (the reference's groups=batch trick, gm.py:326-329)."""
+    _only_defaults('conv2d', dilation=(dilation, 1), groups=(groups, 1))
     w = weight if weight.ndim == 5 else weight.unsqueeze(0)
     y = conv_gather(input, w, 1, stride, padding)
     if bias is not None:
@@ -523,8 +530,10 @@ def conv2d(input, weight, bias=None, stride=1, padding=0):
     return y
 
 
-def conv_transpose2d(input, weight, bias=None, stride=1, padding=0):
-    """``F.conv_transpose2d`` (groups=1).  weight (IC,OC,KH,KW) like torch, or (B,IC,OC,KH,KW)."""
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    """``conv2d_gradfix.conv_transpose2d`` / ``F.conv_transpose2d`` (upstream signature; groups=1, dilation=1,
+    output_padding=0 only).  weight (IC,OC,KH,KW) like torch, or (B,IC,OC,KH,KW)."""
+    _only_defaults('conv_transpose2d', output_padding=(output_padding, 0), groups=(groups, 1), dilation=(dilation, 1))
     w = weight if weight.ndim == 5 else weight.unsqueeze(0)
     w = w.flip(3, 4).transpose(1, 2)                            # -> gather form (Bw,OC,IC,KH,KW)
     kh, kw = w.shape[3], w.shape[4]

@@ -129,3 +129,31 @@ def test_from_config_matches_reference_construction(name):
     # g_ema starts as a copy of g (accumulate(g_ema, g, 0), gt.py:156)
     for (k, a), (_, b) in zip(step.g.named_parameters(), step.g_ema.named_parameters()):
         assert torch.equal(a, b), k
+
+
+def test_conv2d_gradfix_surface(cpu_kernels):
+    """upstream `op/conv2d_gradfix.py` surface (README.md:88-89): both functions with upstream's full signatures (the
+    unused dilation / groups / output_padding only at their defaults), `no_weight_gradients()`, and the values of
+    F.conv2d / F.conv_transpose2d incl. gradients."""
+    import torch.nn.functional as F
+    from gan_control_b200.install import op_package
+    op, gradfix = op_package()
+    assert op.conv2d_gradfix is gradfix and gradfix.enabled is True
+    x = rnd(500, 2, 6, 9, 9).requires_grad_(True)
+    w = rnd(501, 4, 6, 3, 3).requires_grad_(True)
+    b = rnd(502, 4).requires_grad_(True)
+    y = gradfix.conv2d(x, w, bias=b, stride=1, padding=1, dilation=1, groups=1)
+    ref = F.conv2d(x, w, b, stride=1, padding=1)
+    assert max_rel(y, ref) < 1e-12
+    for a, r in zip(torch.autograd.grad(y.sum() + (y * y).sum(), (x, w, b)), torch.autograd.grad(ref.sum() + (ref * ref).sum(), (x, w, b))):
+        assert max_rel(a, r) < 1e-11
+    wt = rnd(503, 6, 4, 3, 3).requires_grad_(True)
+    yt = gradfix.conv_transpose2d(x, wt, bias=None, stride=2, padding=0, output_padding=0, groups=1, dilation=1)
+    reft = F.conv_transpose2d(x, wt, None, stride=2, padding=0)
+    assert yt.shape == reft.shape and max_rel(yt, reft) < 1e-12
+    with gradfix.no_weight_gradients():
+        gx, = torch.autograd.grad(gradfix.conv2d(x, w, padding=1).sum(), x)
+    assert max_rel(gx, torch.autograd.grad(F.conv2d(x, w, padding=1).sum(), x)[0]) < 1e-12
+    for bad in (dict(dilation=2), dict(groups=2)):
+        with pytest.raises(NotImplementedError):
+            gradfix.conv2d(x, w, **bad)
