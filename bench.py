@@ -295,7 +295,7 @@ def run_b200(args):
         head, layers = conv_roofline(torch, K, act, size, batch, peaks)
         line['roofline'] = dict(head, peak_source=peak_kind + ' (burst, kernel timed alone)')
         line['roofline_layers'] = layers
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
         threads = os.cpu_count() or 1
         csize = args.cpu_sample_size or size
         v, t, ratio = cpu_reference_sample(csize, threads)
