@@ -21,6 +21,8 @@ NVCC_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '--use_fast_math', '-Xcompiler',
               '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 # exported symbols are marked by extern "C" in the sources; keep them visible
 NVCC_FLAGS[NVCC_FLAGS.index('-fvisibility=hidden')] = '-fvisibility=default'
+# IEEE arithmetic (no approximate division / sqrt, no flush-to-zero): the optimiser must match torch.optim.Adam
+NO_FAST_MATH = {'optim.cu'}
 
 
 def nvcc():
@@ -36,7 +38,7 @@ def _digest(paths):
         with open(p, 'rb') as f:
             h.update(p.encode())
             h.update(f.read())
-    h.update(' '.join(ARCH + NVCC_FLAGS).encode())
+    h.update(' '.join(ARCH + NVCC_FLAGS + sorted(NO_FAST_MATH)).encode())
     return h.hexdigest()
 
 
@@ -64,7 +66,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj, stamp, want = job
-        cmd = [nvcc()] + ARCH + NVCC_FLAGS + ['-Xptxas', '-v'] + ['-c', src, '-o', obj]
+        flags = [f for f in NVCC_FLAGS if not (f == '--use_fast_math' and os.path.basename(src) in NO_FAST_MATH)]
+        cmd = [nvcc()] + ARCH + flags + ['-Xptxas', '-v'] + ['-c', src, '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'nvcc failed for {src}:\n{r.stdout}\n{r.stderr}')

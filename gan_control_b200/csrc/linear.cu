@@ -163,28 +163,6 @@ static int launch_gemm(const TA* a, const float* b, TC* c, int m, int n, int k, 
 }
 
 // ---- Adam (+ EMA) -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                       float* __restrict__ m, float* __restrict__ v,
-                                                       float* __restrict__ ema, int64_t numel, float lr,
-                                                       float beta1, float beta2, float eps,
-                                                       const float* __restrict__ bias_corr, float ema_decay,
-                                                       float grad_scale) {
-    // 1 - beta^t lives on the device so that a captured CUDA graph replays with the right step count
-    const float bias_c1 = bias_corr[0], bias_c2 = bias_corr[1];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        float gi = g[i] * grad_scale;
-        float mi = beta1 * m[i] + (1.f - beta1) * gi;
-        float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        // torch.optim.Adam: denom = sqrt(v)/sqrt(bias_c2) + eps ; p -= lr/bias_c1 * m/denom
-        float denom = sqrtf(vi) / sqrtf(bias_c2) + eps;
-        float pi = p[i] - (lr / bias_c1) * (mi / denom);
-        p[i] = pi;
-        if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
-    }
-}
 
 }  // namespace b200gan
 
@@ -214,19 +192,4 @@ extern "C" int b200gan_gemm_f32(const float* a, const float* b, float* c, int m,
     B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_f32: bad shape");
     return launch_gemm<float, float>(a, b, c, m, n, k, lda, ldb, ldc, trans_a, trans_b, alpha, beta, nullptr, 0.f,
                                      0, (cudaStream_t)stream);
-}
-
-extern "C" int b200gan_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t numel, float lr,
-                                float beta1, float beta2, float eps, const float* bias_corr,
-                                float ema_decay, float grad_scale, void* stream) {
-    using namespace b200gan;
-    if (numel <= 0) return 0;
-    B200_REQUIRE(bias_corr != nullptr, "adam_ema: bias_corr (device float[2] = {1-beta1^t, 1-beta2^t}) is required");
-    int64_t blocks = cdiv(numel, 256);
-    int64_t cap = (int64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    adam_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, numel, lr, beta1, beta2,
-                                                                        eps, bias_corr, ema_decay, grad_scale);
-    count_launch();
-    return check_launch("adam_ema");
 }

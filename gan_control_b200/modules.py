@@ -172,8 +172,10 @@ class ModulatedConv2d(nn.Module):                                             # 
         return self.out_channel * self.kernel_size ** 2 <= height * width
 
     def operands(self, input, style):
-        """(x, wk, d): the convolution operands of one of the two equivalent forms (module docstring)
-        and the demodulation coefficients d (None when demodulate=False)."""
+        """(x, wk, d, shared): the convolution operands of one of the two equivalent forms (module docstring), the
+        demodulation coefficients d (None when demodulate=False) and whether wk is the shared, parameter-only weight
+        of the activation-modulated form (ops.conv_gather `param_weight`; the weight-modulated wk carries the style
+        even when the batch is 1)."""
         batch, in_channel, height, width = input.shape
         s = self.modulation(style)                                            # (B, IC) fp32, gm.py:284
         w = self.weight[0] * self.scale                                       # (OC, IC, k, k)
@@ -183,11 +185,10 @@ class ModulatedConv2d(nn.Module):                                             # 
             d = torch.rsqrt(ops._Gemm.apply(s * s, wsq, False, True, 1.0) + 1e-8)
         if self._weight_form(height, width):
             wk = w.unsqueeze(0) * s.view(batch, 1, in_channel, 1, 1)          # (B, OC, IC, k, k)
-            x = input
-        else:
-            wk = w.unsqueeze(0)
-            x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
-        return x, wk, d
+            return input, wk, d, False
+        wk = w.unsqueeze(0)
+        x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
+        return x, wk, d, True
 
     # Above this many input channels the upsampling layer is bound by the tensor pipe, not by HBM, and the fused
     # single-pass form (4x the MMA work of the transposed convolution, no (2H+1)^2 intermediate) stops paying.
@@ -202,16 +203,16 @@ class ModulatedConv2d(nn.Module):                                             # 
         ModulatedConv2d(x, style) == z * d[:, :, None, None].  blur=False leaves the upsampling layer's Blur
         (gm.py:307) to the caller (StyledConv fuses it with its epilogue)."""
         height, width = input.shape[2], input.shape[3]
-        x, wk, d = self.operands(input, style)
+        x, wk, d, shared = self.operands(input, style)
         k = self.kernel_size
         if self.upsample:
             # conv_transpose2d(stride 2, padding 0) in gather form (gm.py:301-306) ...
             z = ops.conv_gather(x, wk.flip(3, 4), up=2, down=1, pad0=k - 1,
-                                out_hw=((height - 1) * 2 + k, (width - 1) * 2 + k))
+                                out_hw=((height - 1) * 2 + k, (width - 1) * 2 + k), param_weight=shared)
             if blur:
                 z = self.blur(z)                                              # ... then Blur (gm.py:307)
         else:
-            z = ops.conv_gather(x, wk, 1, 1, self.padding)
+            z = ops.conv_gather(x, wk, 1, 1, self.padding, param_weight=shared)
         return z, d
 
     def forward(self, input, style):
@@ -260,13 +261,14 @@ class StyledConv(nn.Module):                                                  # 
             # the WHOLE upsampling StyledConv in one kernel: transposed stride-2 conv, 4x4 FIR, demodulation, noise,
             # bias, leaky-ReLU (gm.py:295-307, 340-345, 32-35) = a 3x3 convolution with composite FIR (*) conv
             # weights whose accumulator tile is stored depth-to-space through the fused epilogue
-            x, wk, d = conv.operands(input, style)
+            x, wk, d, shared = conv.operands(input, style)
             oh, ow = input.shape[2] * 2, input.shape[3] * 2
             if noise is None:
                 noise = input.new_empty(input.shape[0], 1, oh, ow).normal_()
             return ops.conv_epilogue(x, ops.composite_up(wk, conv.fir_toeplitz), d, noise, self.noise.weight,
                                      self.activate.bias, 1, 1, 1, out_hw=(input.shape[2], input.shape[3]),
-                                     slope=self.activate.negative_slope, gain=self.activate.scale, pack_out=True)
+                                     slope=self.activate.negative_slope, gain=self.activate.scale, pack_out=True,
+                                     param_weight=shared)
         if conv.upsample:
             # transposed conv -> [blur + demod scale + noise + bias + leaky-ReLU*sqrt(2)] in one pass
             z, d = conv.raw(input, style, blur=False)
@@ -276,11 +278,11 @@ class StyledConv(nn.Module):                                                  # 
             return ops.fir_epilogue(z, conv.blur.kernel, conv.blur.pad, d, noise, self.noise.weight, self.activate.bias,
                                     slope=self.activate.negative_slope, gain=self.activate.scale)
         # plain layer: the whole StyledConv is ONE kernel (epilogue fused into the convolution)
-        x, wk, d = conv.operands(input, style)
+        x, wk, d, shared = conv.operands(input, style)
         if noise is None:
             noise = input.new_empty(input.shape[0], 1, input.shape[2], input.shape[3]).normal_()
         return ops.conv_epilogue(x, wk, d, noise, self.noise.weight, self.activate.bias, 1, 1, conv.padding,
-                                 slope=self.activate.negative_slope, gain=self.activate.scale)
+                                 slope=self.activate.negative_slope, gain=self.activate.scale, param_weight=shared)
 
 
 class ToRGB(nn.Module):                                                       # gm.py:411-435
@@ -549,7 +551,7 @@ class ConvLayer(nn.Sequential):                                               # 
             bias = act.bias if isinstance(act, FusedLeakyReLU) else None
             gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
             y = ops.conv_epilogue(x, w, None, None, None, bias, 1, 1, 1, slope=act.negative_slope, gain=gain * out_scale,
-                                  pack_in=True)
+                                  pack_in=True, param_weight=True)
             return _plain_if_tiny(y)
         if isinstance(mods[0], Blur):
             blur, conv = mods[0], mods[1]
@@ -566,14 +568,14 @@ class ConvLayer(nn.Sequential):                                               # 
         stride = conv.stride if stride is None else stride
         if len(mods) == 1:                                   # no activation (ResBlock.skip): scale the weights
             w = (conv.weight * (conv.scale * out_scale)).unsqueeze(0)
-            y = ops.conv_gather(x, w, 1, stride, conv.padding)
+            y = ops.conv_gather(x, w, 1, stride, conv.padding, param_weight=True)
             return y if conv.bias is None else y + (conv.bias * out_scale).view(1, -1, 1, 1).to(y.dtype)
         w = (conv.weight * conv.scale).unsqueeze(0)
         act = mods[1]
         bias = act.bias if isinstance(act, FusedLeakyReLU) else None
         gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
         y = ops.conv_epilogue(x, w, None, None, None, bias, 1, stride, conv.padding,
-                              slope=act.negative_slope, gain=gain * out_scale)
+                              slope=act.negative_slope, gain=gain * out_scale, param_weight=True)
         return _plain_if_tiny(y)
 
 
@@ -654,8 +656,8 @@ class Discriminator(nn.Module):                                               # 
         conv, act = mods[0], mods[1]
         channel = out.shape[1]
         w = conv.weight * conv.scale
-        z = ops.conv_gather(out, w[:, :channel].unsqueeze(0), 1, conv.stride, conv.padding)
-        z = z + ops.conv_gather(stddev, w[:, channel:].unsqueeze(0), 1, conv.stride, conv.padding)
+        z = ops.conv_gather(out, w[:, :channel].unsqueeze(0), 1, conv.stride, conv.padding, param_weight=True)
+        z = z + ops.conv_gather(stddev, w[:, channel:].unsqueeze(0), 1, conv.stride, conv.padding, param_weight=True)
         y = ops.fused_leaky_relu(z, act.bias, act.negative_slope, act.scale)
         return _plain_if_tiny(y)
 

@@ -350,9 +350,9 @@ class _ConvGather(Function):
     tensor, while w, out_h, out_w are in view terms.  The adjoint swaps the two flags."""
 
     @staticmethod
-    def forward(ctx, x, w, up, down, pad0, out_h, out_w, pack_in=False, pack_out=False):
+    def forward(ctx, x, w, up, down, pad0, out_h, out_w, pack_in=False, pack_out=False, param_weight=False):
         h, wd = (x.shape[2] // 2, x.shape[3] // 2) if pack_in else (x.shape[2], x.shape[3])
-        ctx.cfg = (up, down, pad0, h, wd, pack_in, pack_out)
+        ctx.cfg = (up, down, pad0, h, wd, pack_in, pack_out, param_weight)
         ctx.save_for_backward(x, w)
         y = K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0, pack_in=pack_in,
                        pack_out=pack_out)
@@ -361,14 +361,16 @@ class _ConvGather(Function):
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        up, down, pad0, h, wd, pack_in, pack_out = ctx.cfg
+        up, down, pad0, h, wd, pack_in, pack_out, param_weight = ctx.cfg
         kh, kw = w.shape[3], w.shape[4]
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = _ConvGather.apply(gy, _flip_t(w), down, up, kh - 1 - pad0, h, wd, pack_out, pack_in)
-        if ctx.needs_input_grad[1] and (w.shape[0] > 1 or _param_grads()):
+            gx = _ConvGather.apply(gy, _flip_t(w), down, up, kh - 1 - pad0, h, wd, pack_out, pack_in, param_weight)
+        # only a weight the CALLER declared parameter-only may be skipped (never inferred from its shape: at batch 1 a
+        # style-modulated per-sample weight is (1,OC,IC,k,k) too, and its gradient carries the path latent -> style -> w)
+        if ctx.needs_input_grad[1] and (not param_weight or _param_grads()):
             gw = _ConvWgrad.apply(x, gy, up, down, pad0, kh, kw, w.shape[0] > 1, pack_in, pack_out).to(w.dtype)
-        return gx, gw, None, None, None, None, None, None, None
+        return gx, gw, None, None, None, None, None, None, None, None
 
 
 class _ConvWgrad(Function):
@@ -406,25 +408,25 @@ class _ConvEpilogue(Function):
 
     @staticmethod
     def forward(ctx, x, w, d, noise, noise_w, bias, up, down, pad0, out_h, out_w, slope, gain, pack_in=False,
-                pack_out=False):
+                pack_out=False, param_weight=False):
         y = _nchw(K.conv_fwd(_nhwc(x), _kernel_layout(w, x.dtype), out_h, out_w, up, down, pad0, bias, d, noise,
                              noise_w, slope, gain, pack_in=pack_in, pack_out=pack_out))
         h, wd = (x.shape[2] // 2, x.shape[3] // 2) if pack_in else (x.shape[2], x.shape[3])
-        ctx.cfg = (up, down, pad0, h, wd, out_h, out_w, slope, gain, pack_in, pack_out)
+        ctx.cfg = (up, down, pad0, h, wd, out_h, out_w, slope, gain, pack_in, pack_out, param_weight)
         ctx.save_for_backward(x, w, d, noise, noise_w, bias, y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, d, noise, noise_w, bias, y = ctx.saved_tensors
-        up, down, pad0, h, wd, oh, ow, slope, gain, pack_in, pack_out = ctx.cfg
+        up, down, pad0, h, wd, oh, ow, slope, gain, pack_in, pack_out, param_weight = ctx.cfg
         need = ctx.needs_input_grad
         kh, kw = w.shape[3], w.shape[4]
         gx = gw = gd = gnoise = gnw = gb = None
         if torch.is_grad_enabled():
             z = None
             if d is not None and need[2]:
-                z = _ConvGather.apply(x, w, up, down, pad0, oh, ow, pack_in, pack_out)   # recompute, differentiable
+                z = _ConvGather.apply(x, w, up, down, pad0, oh, ow, pack_in, pack_out, param_weight)   # recompute, differentiable
             gconv, gd, gnoise, gnw, gb = _epilogue_grads_graph(gy, y, z, d, noise, noise_w, bias, need[2], need[3],
                                                                need[4], need[5], slope, gain)
         else:
@@ -443,10 +445,10 @@ class _ConvEpilogue(Function):
                 gz = _BiasActGrad.apply(gy, y, slope, gain)
                 gnoise = (up32(gz).sum(1, keepdim=True) * up32(noise_w)).to(noise.dtype)
         if need[0]:
-            gx = _ConvGather.apply(gconv, _flip_t(w), down, up, kh - 1 - pad0, h, wd, pack_out, pack_in)
-        if need[1] and (w.shape[0] > 1 or _param_grads()):        # a shared weight depends on parameters only
+            gx = _ConvGather.apply(gconv, _flip_t(w), down, up, kh - 1 - pad0, h, wd, pack_out, pack_in, param_weight)
+        if need[1] and (not param_weight or _param_grads()):      # skipped only when the caller declared it parameter-only
             gw = _ConvWgrad.apply(x, gconv, up, down, pad0, kh, kw, w.shape[0] > 1, pack_in, pack_out).to(w.dtype)
-        return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None
+        return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None, None
 
 
 def _view_hw(x, w, up, down, pad0, pack_in):
@@ -456,20 +458,24 @@ def _view_hw(x, w, up, down, pad0, pack_in):
 
 
 def conv_epilogue(x, w, d=None, noise=None, noise_w=None, bias=None, up=1, down=1, pad0=0, out_hw=None,
-                  slope=0.2, gain=SQRT2, pack_in=False, pack_out=False):
-    """conv_gather fused with the demod-scale / noise / bias / leaky-ReLU epilogue; `w` (Bw,OC,IC,KH,KW)."""
+                  slope=0.2, gain=SQRT2, pack_in=False, pack_out=False, param_weight=False):
+    """conv_gather fused with the demod-scale / noise / bias / leaky-ReLU epilogue; `w` (Bw,OC,IC,KH,KW).
+    param_weight: `w` is a function of parameters only (see conv_gather)."""
     if out_hw is None:
         out_hw = _view_hw(x, w, up, down, pad0, pack_in)
     return _ConvEpilogue.apply(x, w, d, noise, noise_w, bias, up, down, pad0, out_hw[0], out_hw[1], slope, gain,
-                               pack_in, pack_out)
+                               pack_in, pack_out, param_weight)
 
 
-def conv_gather(x, w, up=1, down=1, pad0=0, out_hw=None, pack_in=False, pack_out=False):
+def conv_gather(x, w, up=1, down=1, pad0=0, out_hw=None, pack_in=False, pack_out=False, param_weight=False):
     """General form; `w` (Bw,OC,IC,KH,KW).  Default output extent = 'valid' over the padded,
-    zero-upsampled input with symmetric padding pad0 (in view terms when packed)."""
+    zero-upsampled input with symmetric padding pad0 (in view terms when packed).
+    param_weight=True declares that `w` depends on parameters only (an EqualConv2d weight, the shared weight of the
+    activation-modulated form): inside `data_grads_only` its gradient is then skipped.  A style-modulated weight must
+    keep the default -- its gradient is part of d(output)/d(latent) -- whatever its batch dimension is."""
     if out_hw is None:
         out_hw = _view_hw(x, w, up, down, pad0, pack_in)
-    return _ConvGather.apply(x, w, up, down, pad0, out_hw[0], out_hw[1], pack_in, pack_out)
+    return _ConvGather.apply(x, w, up, down, pad0, out_hw[0], out_hw[1], pack_in, pack_out, param_weight)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -524,7 +530,8 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     or (B,OC,IC,KH,KW) for per-sample weights (the reference's groups=batch trick, gm.py:326-329)."""
     _only_defaults('conv2d', dilation=(dilation, 1), groups=(groups, 1))
     w = weight if weight.ndim == 5 else weight.unsqueeze(0)
-    y = conv_gather(input, w, 1, stride, padding)
+    # upstream `no_weight_gradients` semantics for an ordinary (OC,IC,KH,KW) weight; per-sample weights are data
+    y = conv_gather(input, w, 1, stride, padding, param_weight=weight.ndim == 4)
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1).to(y.dtype)
     return y
@@ -539,7 +546,7 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
     kh, kw = w.shape[3], w.shape[4]
     h, wd = input.shape[2], input.shape[3]
     out_hw = ((h - 1) * stride - 2 * padding + kh, (wd - 1) * stride - 2 * padding + kw)
-    y = _ConvGather.apply(input, w, stride, 1, kh - 1 - padding, out_hw[0], out_hw[1])
+    y = _ConvGather.apply(input, w, stride, 1, kh - 1 - padding, out_hw[0], out_hw[1], False, False, weight.ndim == 4)
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1).to(y.dtype)
     return y

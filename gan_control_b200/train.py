@@ -27,7 +27,7 @@ def synthetic_images(batch, size, channels, device, seed=0):
 
 
 def train(config, save_dir=None, iters=None, data=None, device='cuda', act_dtype=torch.bfloat16, use_graphs=None, log_every=100,
-          log=print):
+          log=print, vanilla_only=False):
     """Runs iterations ``start_iter .. iter`` of the config (gt.py:340-353) and returns the GanTrainStep."""
     if not isinstance(config, dict):
         with open(config) as f:
@@ -36,7 +36,9 @@ def train(config, save_dir=None, iters=None, data=None, device='cuda', act_dtype
     rank = dist.get_rank() if world > 1 else 0
     mc, tc = config['model_config'], config['training_config']
     torch.manual_seed(1234)                                   # identical initialisation on every replica
-    step = GanTrainStep.from_config(config, device=device, world_size=world, act_dtype=act_dtype)
+    step = GanTrainStep.from_config(config, device=device, world_size=world, act_dtype=act_dtype, vanilla_only=vanilla_only)
+    if rank == 0 and step.effective_objective['ignored_config_terms']:
+        log('WARNING: vanilla objective only; ignored config terms: ' + ', '.join(step.effective_objective['ignored_config_terms']))
     start = int(tc.get('start_iter', 0))
     ck = config.get('ckpt_config') or {}
     if ck.get('enabled'):                                     # gt.py:181-185
@@ -63,7 +65,7 @@ def train(config, save_dir=None, iters=None, data=None, device='cuda', act_dtype
     if rank == 0 and save_dir:
         step.save_nets(total, save_dir)
         with open(os.path.join(save_dir, 'args.json'), 'w') as f:          # read back by inference.Inference.retrieve_model
-            json.dump(config, f, indent=1)
+            json.dump(dict(config, b200gan_effective_objective=step.effective_objective), f, indent=1)
     return step
 
 
@@ -74,6 +76,9 @@ def main():
     ap.add_argument('--iter', type=int, default=None, help='iterations to run from the start / resume point (default: the config\'s)')
     ap.add_argument('--ckpt', type=str, default=None, help='resume from this reference-format checkpoint')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--vanilla-only', action='store_true',
+                    help='train adversarial + R1 + path-length only even if the config enables attribute losses / ADA / '
+                         'd_every / transfer learning (which this path does not build); without it such a config is rejected')
     args = ap.parse_args()
     with open(args.config_path) as f:
         config = json.load(f)
@@ -85,7 +90,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     train(config, save_dir=args.save_dir, iters=args.iter, device=f'cuda:{local_rank}',
-          act_dtype=torch.bfloat16 if args.dtype == 'bf16' else torch.float32)
+          act_dtype=torch.bfloat16 if args.dtype == 'bf16' else torch.float32, vanilla_only=args.vanilla_only)
     if world > 1:
         torch.cuda.synchronize()
         os._exit(0)                                           # see bench.py::_finish

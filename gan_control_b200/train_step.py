@@ -138,19 +138,30 @@ class ArenaAdam:
         # 1 - beta^t  (beta = 0 -> exp(-inf * t) = 0 -> correction 1, like 0 ** t for t >= 1)
         return (1.0 - torch.exp(self.log_betas * self.t[which])).to(self.arena.data.dtype)
 
-    def step(self, skip_tail=False, ema_decay=None, grad_scale=1.0):
+    def step(self, skip_tail=False, ema_decay=None, grad_scale=1.0, buckets=None):
+        """One optimiser step.  With `buckets` (a GradBuckets whose all-reduces are in flight) the arena is stepped
+        bucket by bucket, each as soon as ITS all-reduce has completed, so the update of the early buckets overlaps the
+        reduction of the late ones instead of waiting for all of them (the gradients that backward produces last --
+        the large 4x4..64x64 weights -- no longer gate a monolithic step)."""
         a = self.arena
-        ranges = [(0, a.split, 0)] + ([] if skip_tail or a.split == a.numel else [(a.split, a.numel, 1)])
-        for lo, hi, which in ranges:
-            if hi <= lo:
+        corr = {0: self._bias_corr(0) if a.split > 0 else None}
+        tail = not skip_tail and a.split < a.numel
+        if tail:
+            corr[1] = self._bias_corr(1)
+        if buckets is not None and buckets.enabled:
+            ranges = [(lo, hi, 0 if hi <= a.split else 1, work) for lo, hi, work in buckets.drain()]
+        else:
+            ranges = [(0, a.split, 0, None), (a.split, a.numel, 1, None)]
+        for lo, hi, which, work in ranges:
+            if work is not None:
+                work.wait()                            # this stream waits for this bucket's all-reduce only
+            if hi <= lo or (which == 1 and not tail):
                 continue
-            bias_corr = self._bias_corr(which)
             ema = None
             if self.ema is not None and ema_decay is not None:
                 ema = self.ema.data[lo:hi]
             K.adam_ema(a.data[lo:hi], a.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], ema, self.lr, self.betas[0],
-                       self.betas[1], 1e-8, bias_corr, ema_decay if ema is not None else 0.0, grad_scale)
-
+                       self.betas[1], 1e-8, corr[which], ema_decay if ema is not None else 0.0, grad_scale)
 
     # -- torch.optim.Adam wire format (the reference checkpoints `g_optim` / `d_optim`, gt.py:852-865, 192-193) ----
     def _arena_index(self, module):
@@ -203,32 +214,37 @@ class ArenaAdam:
 
 
 class GradBuckets:
-    """Bucketed gradient all-reduce out of a ParamArena, launched as backward fills buckets."""
+    """Bucketed gradient all-reduce out of a ParamArena, launched as backward fills buckets.
 
-    def __init__(self, arena, world_size, bucket_mb=32, group=None):
+    Buckets are contiguous arena ranges, numbered from the END of the arena (backward produces gradients roughly in
+    reverse registration order) and never straddle `arena.split` (the optimiser steps the two sides separately).
+    Collectives are issued strictly in bucket-index order on every rank -- bucket b is launched only once buckets
+    0..b-1 have been -- so ranks always pair collectives of the same range even if their autograd graphs complete
+    parameters in different orders (e.g. style mixing drawing a different number of latents per rank)."""
+
+    def __init__(self, arena, world_size, bucket_mb=8, group=None):
         self.arena, self.world, self.group = arena, world_size, group
         self.enabled = world_size > 1
         self.pending = []
         if not self.enabled:
             return
-        cap = bucket_mb * (1 << 20) // 4
+        cap = max(1, int(bucket_mb * (1 << 20)) // arena.data.element_size())
         self.bucket_of, self.bucket_range, self.bucket_size = {}, [], []
-        # backward produces gradients roughly in reverse registration order: bucket from the end
-        hi = arena.numel
-        members = 0
-        lo_edge = hi
-        idx = 0
-        for i in reversed(range(len(arena.params))):
+        hi, members, idx = arena.numel, 0, 0
+        n = len(arena.params)
+        for i in reversed(range(n)):
             lo_edge = arena.offsets[i]
             self.bucket_of[i] = idx
             members += 1
-            if hi - lo_edge >= cap or i == 0:
+            at_split = lo_edge == arena.split and i > 0          # close the bucket at the head / tail boundary
+            if hi - lo_edge >= cap or i == 0 or at_split:
                 self.bucket_range.append((lo_edge, hi))
                 self.bucket_size.append(members)
                 hi, members, idx = lo_edge, 0, idx + 1
-        self.count = [0] * len(self.bucket_range)
         for i, p in enumerate(arena.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
+        self.active = False
+        self.begin()
         self.active = False
 
     def _make_hook(self, i):
@@ -238,43 +254,73 @@ class GradBuckets:
             b = self.bucket_of[i]
             self.count[b] += 1
             if self.count[b] == self.bucket_size[b]:
-                self._launch(b)
+                self.ready[b] = True
+                self._launch_ready()
         return hook
 
-    def _launch(self, b):
-        lo, hi = self.bucket_range[b]
-        self.launched[b] = True
-        self.pending.append(dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+    def _launch_ready(self):
+        while self.next < len(self.bucket_range) and self.ready[self.next]:
+            lo, hi = self.bucket_range[self.next]
+            work = dist.all_reduce(self.arena.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.pending.append((lo, hi, work))
+            self.next += 1
 
-    def begin(self, expected=None):
+    def begin(self):
         """arm the hooks for one backward pass"""
         if not self.enabled:
             return
         self.active = True
-        self.count = [0] * len(self.bucket_range)
-        self.launched = [False] * len(self.bucket_range)
+        nb = len(self.bucket_range)
+        self.count, self.ready, self.next, self.pending = [0] * nb, [False] * nb, 0, []
 
     def finish(self):
-        """after backward: reduce whatever did not fill (parameters without a gradient this pass),
-        wait for everything; gradients are SUMS over ranks (the optimiser divides by world)."""
+        """after backward: launch (still in index order) whatever did not fill -- parameters without a gradient this
+        pass.  Gradients are SUMS over ranks (the optimiser divides by world).  The collectives stay in flight: the
+        optimiser consumes them bucket by bucket through `drain`."""
         if not self.enabled:
             return
         self.active = False
-        for b in range(len(self.bucket_range)):
-            if not self.launched[b]:
-                self._launch(b)
-        for w in self.pending:
+        self.ready = [True] * len(self.bucket_range)
+        self._launch_ready()
+
+    def drain(self):
+        """(lo, hi, work) of this pass in launch order; the caller waits on each `work` before touching its range"""
+        out, self.pending = self.pending, []
+        return out
+
+    def wait_all(self):
+        for _, _, w in self.drain():
             w.wait()
-        self.pending = []
 
 
 # ---------------------------------------------------------------------------------------------
+def unbuilt_objective_terms(config):
+    """What a gan-control config asks for that this step does NOT do.  The reference applies, when `model_config.vanilla`
+    is false, every enabled `training_config.*_loss` (embedding / orientation / expression / age / hair / ..., gt.py:205-
+    300, 431-434) on batches arranged by `MiniBatchUtils.re_arrange_z`; independently it applies ADA augmentation
+    (`augment.enabled`, gt.py:647-653), `d_every` (gt.py:351), and a transfer-learning initialisation (gt.py:134-143).
+    This path builds the adversarial + R1 + path-length objective only (SURVEY.md section 8 scope), so a config that
+    relies on any of the above would silently train something else."""
+    mc, tc = config['model_config'], config['training_config']
+    out = []
+    if not mc.get('vanilla', False):
+        out += [f'{k} (attribute loss)' for k, v in tc.items() if k.endswith('_loss') and isinstance(v, dict)
+                and v.get('enabled')]
+    if (tc.get('augment') or {}).get('enabled'):
+        out.append('augment (ADA)')
+    if tc.get('d_every', 1) != 1:
+        out.append(f"d_every={tc['d_every']}")
+    if (tc.get('transfer_learning_model') or {}).get('enabled'):
+        out.append('transfer_learning_model')
+    return out
+
+
 class GanTrainStep:
     """One process = one GPU = one replica.  ``batch`` is the per-replica batch."""
 
     def __init__(self, generator, discriminator, g_ema=None, batch=16, lr_g=0.002, lr_d=0.002, r1=1.0,
                  d_reg_every=16, g_reg_every=4, path_regularize=2.0, path_batch_shrink=2, mixing=0.0,
-                 g_moving_average=10000, latent_size=512, world_size=1, bucket_mb=32, global_batch=None):
+                 g_moving_average=10000, latent_size=512, world_size=1, bucket_mb=8, global_batch=None):
         self.g, self.d, self.g_ema = generator, discriminator, g_ema
         self.batch, self.world = batch, world_size
         self.global_batch = global_batch or batch * world_size
@@ -304,19 +350,31 @@ class GanTrainStep:
 
     # -- construction from the reference's config files (configs/*.json, `args.json` of a run) -----------------------
     @classmethod
-    def from_config(cls, config, device='cuda', world_size=1, act_dtype=torch.bfloat16, **overrides):
+    def from_config(cls, config, device='cuda', world_size=1, act_dtype=torch.bfloat16, vanilla_only=False, **overrides):
         """Networks and step exactly as `GeneratorTrainer.init_models_and_optim` builds them (gt.py:120-173) from the
         `model_config` / `training_config` sections of a gan-control config (a dict, or the path of `configs/ffhq.json`
         or of a run's `args.json`): Generator / g_ema / Discriminator constructor arguments, split-FC layout from
         `sub_groups_dict`, lazy-regularisation Adam, R1 / path-length weights and cadence, EMA horizon, style mixing.
         `training_config['batch']` is the GLOBAL batch (the reference scatters it over its DataParallel replicas); each
-        of the `world_size` processes gets batch / world_size.  Resumes from `ckpt_config` when enabled (gt.py:175-193)."""
+        of the `world_size` processes gets batch / world_size.  Resumes from `ckpt_config` when enabled (gt.py:175-193).
+        A config that enables objective terms this path does not build (`unbuilt_objective_terms`) raises unless
+        `vanilla_only=True` says the adversarial + R1 + path-length objective alone is what is wanted; the effective
+        objective is recorded in `step.effective_objective` (and in the run's args.json by `train`)."""
         import json
+        import warnings
         from . import modules as M
         if not isinstance(config, dict):
             with open(config) as f:
                 config = json.load(f)
         mc, tc = config['model_config'], config['training_config']
+        dropped = unbuilt_objective_terms(config)
+        if dropped and not vanilla_only:
+            raise NotImplementedError(
+                'this config enables training terms the B200 path does not build: ' + ', '.join(dropped) + '. It would '
+                'train the vanilla objective (adversarial + R1 + path-length) only; pass vanilla_only=True '
+                '(`--vanilla-only`) to do that deliberately.')
+        if dropped:
+            warnings.warn('gan_control_b200: training the vanilla objective only; IGNORED config terms: ' + ', '.join(dropped))
         if mc.get('marge_fc') or mc.get('vae'):
             raise NotImplementedError('marge_fc / vae are not used by any shipped config and are not built')
         if tc.get('mini_batch', tc['batch']) != tc['batch']:
@@ -343,6 +401,8 @@ class GanTrainStep:
         kw.update(overrides)
         step = cls(g, d, g_ema, **kw)
         step.config = config
+        step.effective_objective = {'terms': ['adversarial (non-saturating / logistic)', 'r1', 'path_length'],
+                                    'ignored_config_terms': dropped}
         ck = config.get('ckpt_config') or {}
         if ck.get('enabled'):
             step.load_checkpoint(ck['ckpt'])
@@ -381,7 +441,7 @@ class GanTrainStep:
         self.d_buckets.begin()
         d_loss.backward()
         self.d_buckets.finish()
-        self.d_optim.step(grad_scale=1.0 / self.world)
+        self.d_optim.step(grad_scale=1.0 / self.world, buckets=self.d_buckets)
         self.stats['d_loss'] = d_loss.detach()
         return d_loss.detach()
 
@@ -395,7 +455,7 @@ class GanTrainStep:
         self.d_buckets.begin()
         (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * real_pred[0]).sum().backward()   # gt.py:706
         self.d_buckets.finish()
-        self.d_optim.step(skip_tail=True, grad_scale=1.0 / self.world)                    # set_grad_none gt.py:708
+        self.d_optim.step(skip_tail=True, grad_scale=1.0 / self.world, buckets=self.d_buckets)                    # set_grad_none gt.py:708
         self.stats['r1_loss'] = r1_loss.detach()
         return r1_loss.detach()
 
@@ -410,7 +470,7 @@ class GanTrainStep:
         self.g_buckets.begin()
         g_loss.backward()
         self.g_buckets.finish()
-        self.g_optim.step(ema_decay=self.accum if ema else None, grad_scale=1.0 / self.world)
+        self.g_optim.step(ema_decay=self.accum if ema else None, grad_scale=1.0 / self.world, buckets=self.g_buckets)
         self.stats['g_loss'] = g_loss.detach()
         return g_loss.detach()
 
@@ -432,7 +492,7 @@ class GanTrainStep:
         self.g_buckets.begin()
         weighted.backward()
         self.g_buckets.finish()
-        self.g_optim.step(skip_tail=True, grad_scale=1.0 / self.world)                    # set_grad_none gt.py:594
+        self.g_optim.step(skip_tail=True, grad_scale=1.0 / self.world, buckets=self.g_buckets)                    # set_grad_none gt.py:594
         self.stats['path_loss'] = path_loss.detach()
         return path_loss.detach()
 

@@ -214,3 +214,34 @@ def test_discriminator(cpu_kernels):
     for k in fx.keys('d16.dl.g.'):
         key = k[len('d16.dl.g.'):]
         assert max_rel(reduce_like_golden(params[key].grad), fx.t(k)) < 1e-8, key
+
+
+@pytest.mark.parametrize('batch', [1, 2])
+@pytest.mark.parametrize('form', ['weight', 'activation', 'auto'])
+def test_data_grads_only_matches_plain_grad(cpu_kernels, batch, form):
+    """inside `data_grads_only` the path-length inner gradient d(img.n)/d(latent) must equal the
+    plain autograd.grad at EVERY batch size.  At batch 1 a style-modulated weight is (1,OC,IC,k,k) like a shared one;
+    its gradient carries latent -> style -> weight and must not be skipped."""
+    size, sdim = 16, 32
+    torch.manual_seed(3)
+    g = M.Generator(size, sdim, 2, channel_multiplier=2, conv_transpose=True).double()
+    for m in g.modules():
+        if isinstance(m, M.ModulatedConv2d):
+            m.form = form
+        if isinstance(m, M.NoiseInjection):
+            m.weight.data.fill_(0.3)
+    z = torch.randn(batch, sdim, dtype=F64)
+    noise = [torch.randn(batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), dtype=F64) for i in range(g.num_layers)]
+    pl = torch.randn(batch, 3, size, size, dtype=F64)
+    img, latents = g([z], return_latents=True, noise=noise)
+    plain, = torch.autograd.grad((img * pl).sum(), latents, create_graph=True)
+    img, latents = g([z], return_latents=True, noise=noise)
+    with ops.data_grads_only():
+        only, = torch.autograd.grad((img * pl).sum(), latents, create_graph=True)
+    assert plain.abs().max() > 0
+    assert max_rel(only, plain) < 1e-11
+    # and the double backward through it (what the regulariser trains on)
+    w = g.convs[0].conv.weight
+    gg_plain, = torch.autograd.grad(plain.pow(2).sum(), w)
+    gg_only, = torch.autograd.grad(only.pow(2).sum(), w)
+    assert max_rel(gg_only, gg_plain) < 1e-10

@@ -110,7 +110,11 @@ def test_from_config_matches_reference_construction(name):
     cfg = json.load(open(os.path.join(REF_SRC, 'gan_control', 'configs', name + '.json')))
     cfg['model_config']['size'] = 32
     mc, tc = cfg['model_config'], cfg['training_config']
-    step = GanTrainStep.from_config(cfg, device='cpu', world_size=4, act_dtype=torch.float32)
+    with pytest.raises(NotImplementedError, match='does not build'):     # attribute losses / ADA are not silently dropped
+        GanTrainStep.from_config(cfg, device='cpu', world_size=4, act_dtype=torch.float32)
+    with pytest.warns(UserWarning, match='IGNORED config terms'):
+        step = GanTrainStep.from_config(cfg, device='cpu', world_size=4, act_dtype=torch.float32, vanilla_only=True)
+    assert step.effective_objective['ignored_config_terms']
     bu = MiniBatchUtils(tc['mini_batch'], tc['sub_groups_dict'], total_batch=tc['batch'])
     ref_g = gm.Generator(mc['size'], mc['latent_size'], mc['n_mlp'], channel_multiplier=mc['channel_multiplier'],
                          out_channels=mc['img_channels'], split_fc=mc['split_fc'], marge_fc=mc['marge_fc'],

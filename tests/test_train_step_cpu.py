@@ -218,3 +218,72 @@ def test_checkpoint_wire_format(cpu_kernels, tmp_path):
     g1, d1, g_ema1 = product_run(batch, real, zs, pl_noise, [0, 1])
     for a, b in [(g2, g1), (d2, d1), (g_ema2, g_ema1)]:
         compare(a, b.state_dict(), 1e-12)
+
+
+def test_bucket_launch_order_is_fixed(monkeypatch):
+    """collectives must be issued in bucket-index order whatever order backward fills the buckets in
+    (torch DDP's rule), and no bucket may straddle the head / tail split of the arena."""
+    import gan_control_b200.train_step as TS
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[torch.nn.Linear(64, 64) for _ in range(6)])
+    arena = TS.ParamArena(net, tail=['5.bias'])
+    launched = []
+
+    class Work:
+        def wait(self):
+            pass
+
+    def fake_all_reduce(t, op=None, group=None, async_op=False):
+        launched.append((t.data_ptr() - arena.grad.data_ptr()) // 4)
+        return Work()
+    monkeypatch.setattr(TS.dist, 'all_reduce', fake_all_reduce)
+    buckets = TS.GradBuckets(arena, world_size=2, bucket_mb=64 * 64 * 4 / (1 << 20))
+    assert len(buckets.bucket_range) >= 6
+    assert all(not (lo < arena.split < hi) for lo, hi in buckets.bucket_range)
+    order = [lo for lo, _ in buckets.bucket_range]
+    for perm_seed in range(3):
+        launched.clear()
+        buckets.begin()
+        idx = torch.randperm(len(arena.params), generator=torch.Generator().manual_seed(perm_seed)).tolist()
+        for i in idx[:-2]:                          # two parameters never get a gradient this pass
+            buckets._make_hook(i)(arena.params[i])
+            assert launched == order[:len(launched)]
+        buckets.finish()
+        assert launched == order
+        ranges = [(lo, hi) for lo, hi, _ in buckets.drain()]
+        assert ranges == buckets.bucket_range
+
+
+def _worker_mixing(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from gan_control_b200 import kernels
+    from oracle import kernels_ref
+    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
+                 'gemm_f32', 'adam_ema', 'launch_count']:
+        setattr(kernels, name, getattr(kernels_ref, name))
+    g, g_ema, d = build(4)
+    step = GanTrainStep(g, d, g_ema, batch=4, latent_size=SDIM, world_size=world, bucket_mb=0.05, mixing=0.9)
+    real = rnd(70 + rank, 4, 3, SIZE, SIZE).clamp_(-1, 1)
+    for i in range(2):
+        # ranks deliberately disagree on the mixing coin: rank 0 maps one latent, rank 1 two (tu:19-23)
+        zs = [rnd(200 + 10 * i + rank, 4, SDIM)] if rank == 0 else [rnd(300 + i, 4, SDIM), rnd(400 + i, 4, SDIM)]
+        step.discriminator_step(real, zs)
+        step.generator_step(zs)
+        step.generator_regularize_step(zs[:1] if rank == 0 else [z[:2] for z in zs])
+    torch.save({'g': g.state_dict(), 'd': d.state_dict()}, out + str(rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_replicas_with_style_mixing_stay_in_sync(cpu_kernels, tmp_path):
+    """world_size 2, mixing > 0 with the ranks taking DIFFERENT mixing branches in the same step: the bucketed
+    all-reduces still pair up (fixed launch order) and the replicas end bit-identical."""
+    out = str(tmp_path / 'mix')
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_worker_mixing, args=(2, port, out), nprocs=2, join=True)
+    a, b = torch.load(out + '0'), torch.load(out + '1')
+    for net in ('g', 'd'):
+        for k in a[net]:
+            assert torch.equal(a[net][k], b[net][k]), (net, k)
