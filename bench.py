@@ -2,7 +2,7 @@
 """bench.py -- images/sec of the FFHQ-1024 G+D train step on 1/2/4/8 B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port), really timed
 
 A "step" is one `discriminator_update` + one `generator_update` (generator_trainer.py:351-353) at
 BASELINE.json configs[1]: Generator(1024)/Discriminator(1024), channel_multiplier 2, per-GPU batch
@@ -11,6 +11,7 @@ the lazy regularisers at their real cadence (R1 every 16, path-length every 4 it
 Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -23,8 +24,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'images/sec FFHQ-1024 G+D train step'
 UNIT = 'images/s'
-# algorithmic work per image of the plain step, BASELINE.md section 2: 4*G_f + 8*D_f
-GFLOP_PER_IMG = {1024: 4 * 148.5 + 8 * 153.3, 512: 4 * 119.3 + 8 * 123.2, 256: 4 * 90.2 + 8 * 93.1}
+# algorithmic work per image, BASELINE.md section 2 (G_f, D_f GFLOP forward; min fused traffic MB forward, bf16)
+G_D_GFLOP = {1024: (148.5, 153.3), 512: (119.3, 123.2), 256: (90.2, 93.1)}
+G_D_MB = {1024: (598.0, 728.0), 512: (290.0, 354.0), 256: (138.0, 168.0)}
+REF_BUDGET_S = 240.0          # wall-clock budget of the whole `--impl reference` run (K + W bounded samples)
 
 
 def parse():
@@ -40,6 +43,8 @@ def parse():
     ap.add_argument('--cpu-sample-size', type=int, default=None, help='resolution of the CPU-baseline sample')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-roofline', action='store_true')
+    ap.add_argument('--skip-library-baseline', action='store_true', help='no cuDNN/cuBLAS comparator (gpu_library_baseline)')
+    ap.add_argument('--skip-extra', action='store_true', help='no extra_configs (BASELINE.json configs[2..4] per-GPU workloads)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)')
@@ -88,62 +93,85 @@ def measured_peaks():
 
 
 def workload_config(size, reg, batch, world):
-    """`config` of the JSON line: the same for this repo's arm and for the reference arm"""
+    """`config` of the JSON line: identical for this repo's arm and for the reference arm"""
     return {'workload': f'FFHQ-{size} G+D train step (BASELINE.json configs[1]): Generator({size})+Discriminator({size}) '
                         f'channel_multiplier 2, random init, lazy regularisers at real cadence '
                         f'(R1 /16, path-length /4)' + ('' if reg else ' DISABLED'),
-            'global_batch': batch * world, 'per_gpu_batch': batch, 'parallelism': f'dp{world}'}
+            'global_batch': batch * world, 'per_gpu_batch': batch, 'parallelism': f'dp{world}',
+            'l2': 'inputs larger than L2 (each step streams >10 GB of activations; no explicit flush)'}
+
+
+def reg_counts(first_iter, n_steps, reg=True):
+    its = range(first_iter, first_iter + n_steps)
+    return {'r1_steps': sum(1 for i in its if reg and i % 16 == 0), 'path_length_steps': sum(1 for i in its if reg and i % 4 == 0)}
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(size, threads, reps=1):
-    """Bounded sample of the reference's CPU path (oracle port of gan_model.py, fp32, FUSED=False arithmetic):
-    ONE generator forward + ONE discriminator forward on 1 image at `size`.  The full plain G+D step costs
-    (4*G_f + 8*D_f) / (G_f + D_f) times the FLOPs of this sample (forward, data-gradient
-    and weight-gradient passes cost one forward each), so images/s = 1 / (t_sample * that ratio).  A whole
-    1024^2 step on the box's host cores takes minutes (measured: 259 s on 128 cores), hence the sample."""
+# the reference's CPU path, really timed (oracle port; `oracle/reference_step.py`)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_steps(size, n_timed, n_warm, threads, budget_s, log=None):
+    """`n_warm` + `n_timed` REAL training iterations of the reference arithmetic on the host cores: each is one
+    discriminator_step + one generator_step (forward, backward, Adam, EMA; gt.py:343-369) on a mini-batch of ONE image
+    -- the reference's own gradient-accumulation granularity (mini_batch < batch, gt.py:361,411-436) -- without the lazy
+    regularisers (they would add ~15 %: leaving them out favours the reference).  If the first iteration shows that the
+    run cannot finish inside `budget_s` at `size`, the sample drops to 256x256 (and says so): its per-image cost is
+    LOWER than the benchmark resolution's, again in the reference's favour.  Returns (images/s, ms per iteration, text)."""
     import torch
-    from oracle import params as P, stylegan2_oracle as O
+    from oracle.reference_step import ReferenceStep
     torch.set_num_threads(threads)
-    sd_g = P.seeded_state_dict(P.generator_shapes(size, 512, 8, 2), 1)
-    sd_d = P.seeded_state_dict(P.discriminator_shapes(size, 2), 2)
-    z = torch.randn(1, 512)
+    torch.manual_seed(0)
+    t_start = time.perf_counter()
+
+    def make(sz):
+        return ReferenceStep(sz, 1, 1), torch.randn(1, 3, sz, sz).clamp_(-1, 1)
+    rs, real = make(size)
+    t0 = time.perf_counter()
+    rs.train_step(1, real, regularize=False)
+    first = time.perf_counter() - t0
+    note = ''
+    remaining = n_warm + n_timed - 1
+    if size > 256 and first * max(1, remaining) > budget_s - (time.perf_counter() - t_start):
+        note = (f' (one iteration at {size}x{size} took {first:.1f} s: {n_warm}+{n_timed} of them do not fit the '
+                f'{budget_s:.0f} s budget, so the sample runs at 256x256 -- cheaper per image, in the reference\'s favour)')
+        size = 256
+        rs, real = make(size)
+        rs.train_step(1, real, regularize=False)
+    for _ in range(max(0, n_warm - 1)):
+        rs.train_step(1, real, regularize=False)
     ts = []
-    with torch.no_grad():
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            img = O.generator_forward(sd_g, [z], size)
-            O.discriminator_forward(sd_d, img, size)
-            ts.append(time.perf_counter() - t0)
-    t = min(ts)
-    g_f, d_f = {1024: (148.5, 153.3), 512: (119.3, 123.2), 256: (90.2, 93.1)}.get(size, (148.5, 153.3))
-    ratio = (4 * g_f + 8 * d_f) / (g_f + d_f)
-    return 1.0 / (t * ratio), t, ratio
+    for k in range(n_timed):
+        t0 = time.perf_counter()
+        rs.train_step(1 + k, real, regularize=False)
+        ts.append(time.perf_counter() - t0)
+        if log:
+            log(f'reference iteration {k}: {ts[-1]:.2f} s')
+    t = sum(ts) / len(ts)
+    sample = (f'{n_timed} timed + {n_warm} warm-up REAL training iterations (D step + G step: forward, backward, Adam, EMA; no '
+              f'regulariser steps) of the oracle port of gan_model.py / generator_trainer.py, fp32, mini-batch 1 at '
+              f'{size}x{size}, {t:.2f} s per iteration on {threads} threads' + note)
+    return 1.0 / t, t * 1e3, sample, size
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path on this box's host cores (oracle port; a Python reference
-    cannot travel to the GPU box).  Each of the K steps is one bounded sample (see cpu_reference_sample)."""
+    """--impl reference: rank 0 times the reference's CPU implementation; other ranks exit quietly."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     size = args.cpu_sample_size or args.size
-    reps = max(1, min(args.steps, 2))
-    v, t, ratio = cpu_reference_sample(size, threads, reps=reps)
-    sample = (f'G forward + D forward on 1 image at {size}x{size}, fp32, {t:.1f} s (best of {reps}); scaled to the plain '
-              f'G+D step by its FLOP ratio {ratio:.2f}')
+    v, ms, sample, used = cpu_reference_steps(size, max(1, args.steps), args.warmup, threads, REF_BUDGET_S)
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': t * ratio * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args.size, not args.no_reg, args.batch, args.gpus),
-                           reference_arm='reference FUSED=False arithmetic (oracle port) on the host CPU; every step is a bounded '
-                                         'sample of this workload, see cpu_baseline.sample'),
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'measured': True,
+            'config': workload_config(args.size, not args.no_reg, args.batch, args.gpus),
+            'sample_resolution': used, 'sample_batch': 1,
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# per-layer roofline of the convolution kernels, timed alone WITH their fused epilogue operands
 # ---------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at batch 16, from the `ncu --set full` captures summarised in
 # profiles/r01_ncu_kernels.md (None where the layer has not been captured)
@@ -153,74 +181,84 @@ NCU_TRAFFIC_BYTES = {'conv3x3 256->256 @128x128 batch 16': 135.4e6 + 85.79e6,
                      'conv3x3 32->32 @1024x1024 batch 16': 1.073810e9 + 1.025126e9}
 
 
+def _time_kernel(torch, fn, flush, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts)
+
+
 def conv_roofline(torch, K, dtype, size, batch, peaks):
-    """The dominant kernels = the 3x3 convolutions (conv_fwd_umma_kernel has the largest share of the step,
-    conv_fwd_halo_kernel the second, profiles/).  Each layer class of the resolution is timed alone with CUDA events
-    on the launching stream (inputs >> L2, L2 flushed between launches) against the roofline that bounds it:
-    tensor pipe (algorithmic 2*MAC FLOPs) for >= 64 channels, HBM (input read once + output written once) for the
-    32-channel full-resolution layer.  Returns (headline, all layers)."""
+    """Every 3x3 layer class of the resolution, timed alone with CUDA events on the launching stream (inputs >> L2, L2
+    flushed between launches) as the StyledConv it is on the path: per-sample modulated weights and the fused
+    demodulation / noise / bias / leaky-ReLU epilogue operands.  Forward and weight gradient.  Headline = the layer the
+    metric is quoted on, 32 -> 32 at full resolution: HBM-bound (input read once + output written once) with its
+    tensor-pipe fraction beside it.  Returns (headline, all layers)."""
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-    layers = [(size // 8, 256, 'tensor'), (size // 4, 128, 'tensor'), (size // 2, 64, 'tensor'), (size, 32, 'hbm')]
+    layers = [(size, 32), (size // 2, 64), (size // 4, 128), (size // 8, 256)]
+    hbm, tf = peaks.get('hbm_gbs', 6650.0), peaks.get('bf16_tflops', 1590.0)
     out = []
-    for res, ch, bound in layers:
+    for res, ch in layers:
         x = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
         w = (torch.randn(batch, 3, 3, ch, ch, device='cuda') / (3 * ch ** 0.5)).to(dtype)     # per-sample (modulated) weights
+        gy = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
+        d = torch.rand(batch, ch, device='cuda') + 0.5
+        bias = torch.randn(ch, device='cuda')
+        noise = torch.randn(batch, res, res, device='cuda').to(dtype)
+        nw = torch.full((1,), 0.1, device='cuda')
         flops = 2.0 * batch * res * res * ch * ch * 9
         nbytes = 2.0 * batch * res * res * ch * x.element_size()
-        for _ in range(3):
-            K.conv_fwd(x, w, res, res, 1, 1, 1)
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            K.conv_fwd(x, w, res, res, 1, 1, 1)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sum(ts) / len(ts)
-        what = f'conv3x3 {ch}->{ch} @{res}x{res} batch {batch}'
-        if bound == 'tensor':
-            ach, peak, unit = flops / (ms * 1e-3) / 1e12, peaks.get('bf16_tflops', 1590.0), 'TFLOP/s'
-        else:
-            ach, peak, unit = nbytes / (ms * 1e-3) / 1e9, peaks.get('hbm_gbs', 6650.0), 'GB/s'
-        out.append({'bound': bound, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
-                    'traffic': NCU_TRAFFIC_BYTES.get(what) if batch == 16 else None, 'kernel': what, 'kernel_ms': ms,
-                    'algorithmic_flops': flops, 'algorithmic_bytes': nbytes})
-        del x, w
+        for kind, fn in (('fwd', lambda: K.conv_fwd(x, w, res, res, 1, 1, 1, bias, d, noise, nw, 0.2, 2 ** 0.5)),
+                         ('wgrad', lambda: K.conv_wgrad(x, gy, 3, 3, 1, 1, 1, True))):
+            ms = _time_kernel(torch, fn, flush)
+            what = f'conv3x3 {ch}->{ch} @{res}x{res} batch {batch}'
+            gbs, tfs = nbytes / (ms * 1e-3) / 1e9, flops / (ms * 1e-3) / 1e12
+            bound = 'hbm' if gbs / hbm >= tfs / tf else 'tensor'
+            row = {'bound': bound, 'achieved': gbs if bound == 'hbm' else tfs, 'peak': hbm if bound == 'hbm' else tf,
+                   'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': max(gbs / hbm, tfs / tf),
+                   'traffic': NCU_TRAFFIC_BYTES.get(what) if (batch == 16 and kind == 'fwd') else None,
+                   'kernel': what + (' + fused epilogue (demod, noise, bias, lrelu), per-sample weights' if kind == 'fwd'
+                                     else ' weight gradient (per-sample)'),
+                   'pass': kind, 'kernel_ms': ms, 'algorithmic_flops': flops, 'algorithmic_bytes': nbytes,
+                   'hbm_gbs': gbs, 'frac_hbm': gbs / hbm, 'tensor_tflops': tfs, 'frac_tensor': tfs / tf,
+                   'engine': K.last_conv_engine()}
+            out.append(row)
+        del x, w, gy, noise
     return out[0], out
 
 
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    import __graft_entry__
-    if rank == 0:
-        __graft_entry__.build()
-    if world > 1:
-        dist.barrier()
+# ---------------------------------------------------------------------------------------------
+# one measured configuration of this repo's path
+# ---------------------------------------------------------------------------------------------
+def measure(torch, dist, args, dev, rank, world, size, batch, steps, warmup, fc_groups=None, r1=1.0, lr=0.002, mixing=0.0,
+            reg=True, with_e2e=True, sampler_index=None, ncu_range=False):
+    """Build G / g_ema / D for (size, batch), capture the step variants, time `steps` iterations starting at iteration 1
+    (device-resident input) and -- same window, same cadence -- the host-fed end-to-end variant.  Everything is released
+    before returning."""
     from gan_control_b200 import kernels as K, modules as M
     from gan_control_b200.train_step import GanTrainStep
     act = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
-    size, batch = args.size, args.batch
     torch.manual_seed(1234)          # identical init on every rank (replicas stay in sync by construction)
-    g = M.Generator(size, 512, 8, channel_multiplier=2, conv_transpose=True, act_dtype=act).to(dev)
-    g_ema = M.Generator(size, 512, 8, channel_multiplier=2, conv_transpose=True, act_dtype=act).to(dev)
+    fc = M.FcConfig.from_sub_groups_dict(fc_groups) if fc_groups else None
+
+    def gen():
+        return M.Generator(size, 512, 8, channel_multiplier=2, conv_transpose=True, act_dtype=act, split_fc=fc is not None,
+                           fc_config=fc).to(dev)
+    g, g_ema = gen(), gen()
     d = M.Discriminator(size, channel_multiplier=2, act_dtype=act).to(dev)
-    step = GanTrainStep(g, d, g_ema, batch=batch, world_size=world)
+    step = GanTrainStep(g, d, g_ema, batch=batch, world_size=world, r1=r1, lr_g=lr, lr_d=lr, mixing=mixing)
     torch.manual_seed(1000 + rank)   # independent latents / noise / data per replica
     host_real = torch.randn(batch, 3, size, size).clamp_(-1, 1).pin_memory()
     dev_real = host_real.to(dev)
-    reg = not args.no_reg
+    use_graph = not args.no_graph
 
     def sync():
         if world > 1:
@@ -253,55 +291,168 @@ def run_b200(args):
             ms = float(t)
         return ms / n_steps, K.launch_count() + getattr(step, 'replayed_launches', 0) - n0
 
-    use_graph = not args.no_graph
     if use_graph:
         step.capture(tuple(dev_real.shape))      # runs every step variant twice on a side stream, then captures
     run_step = step.train_step_graphed if use_graph else step.train_step
-    # warm-up (also runs one of each regulariser so every kernel / allocation exists)
-    for it in range(args.warmup):
+    for it in range(warmup):                     # warm-up (one of each regulariser so every kernel / allocation exists)
         run_step(it * 4, dev_real, regularize=reg and it == 0)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(sampler_index) if sampler_index is not None else None
     if sampler:
         sampler.start()
-    if args.ncu_range:
+    if ncu_range:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-    ms_step, launches = timed(args.steps, False, 1)
-    if args.ncu_range:
+    engines0 = K.engine_launches()
+    ms_step, launches = timed(steps, False, 1)
+    if ncu_range:
         torch.cuda.profiler.stop()
     clocks = sampler.summary() if sampler else None
-    ms_e2e, _ = timed(max(1, args.steps // 2), True, 1)
-    ms_plain, _ = timed(max(1, min(args.steps, 4)), False, 1) if False else (None, None)
-    global_batch = batch * world
-    value = global_batch / (ms_step * 1e-3)
-    e2e_value = global_batch / (ms_e2e * 1e-3)
+    engines = {k: v - engines0[k] for k, v in K.engine_launches().items()} if not use_graph else None
+    out = {'ms_per_step': ms_step, 'value': batch * world / (ms_step * 1e-3), 'gpu_launches': launches, 'clocks': clocks,
+           'timed_window': dict(reg_counts(1, steps, reg), first_iteration=1, iterations=steps), 'cuda_graphs': use_graph,
+           'graph_launches': dict(step.graph_launches) if use_graph else None, 'conv_engine_calls': engines}
+    if with_e2e:
+        ms_e2e, _ = timed(steps, True, 1)        # same iteration window (same regulariser steps) as `value`
+        out['e2e'] = {'value': batch * world / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+                      'h2d_bytes_per_step': host_real.numel() * 4, 'd2h_bytes_per_step': 8,
+                      'timed_window': out['timed_window']}
+    sync()
+    if world > 1:
+        # captured graphs hold NCCL collectives: destroying them mid-run can hang (see _finish) -- keep them to the end
+        _KEEP.append((step, g, g_ema, d, host_real, dev_real))
+    del step, g, g_ema, d, run_step, host_real, dev_real
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+_KEEP = []
+
+
+def gpu_library_baseline(torch, size, batch, dev, log):
+    """The reference's FUSED=False arithmetic (oracle port = the same PyTorch ops as gan_model.py) on THIS GPU through
+    cuDNN / cuBLAS: grouped `conv2d(groups=batch)` with materialised per-sample weights, `conv_transpose2d`, the 6-pass
+    `upfirdn2d_native`, separate noise / bias / leaky-ReLU passes, stock autograd, torch.optim.Adam -- the stand-in for the
+    FUSED=True comparator that is not in the reference tree.  Plain iterations (D step + G step) at the
+    benchmark batch, accumulated over mini-batches the way the reference does when a batch does not fit (gt.py:361)."""
+    from oracle.reference_step import ReferenceStep
+    out = {'what': 'reference FUSED=False arithmetic (oracle/reference_step.py) on this GPU via cuDNN/cuBLAS; plain '
+                   'iterations (no regulariser steps), 1 warm-up + 2 timed, CUDA events', 'unit': UNIT}
+    for name, autocast in (('fp32', None), ('bf16_autocast', torch.bfloat16)):
+        mini = batch                  # the whole batch at once when it fits; else the reference's mini-batch accumulation
+        while True:
+            try:
+                torch.manual_seed(0)
+                rs = ReferenceStep(size, batch, mini, device=dev, autocast=autocast)
+                real = torch.randn(batch, 3, size, size, device=dev).clamp_(-1, 1)
+                rs.train_step(1, real, regularize=False)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for k in range(2):
+                    rs.train_step(2 + k, real, regularize=False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 2
+                out[name] = {'value': batch / (ms * 1e-3), 'ms_per_step': ms, 'batch': batch, 'mini_batch': mini,
+                             'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30}
+                log(f'gpu_library_baseline {name}: {out[name]}')
+                break
+            except torch.cuda.OutOfMemoryError:
+                mini //= 2
+                if mini < 1:
+                    out[name] = {'unavailable': 'out of memory at mini-batch 1'}
+                    break
+            finally:
+                rs = real = None
+                gc.collect()
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+    return out
+
+
+AFHQ_GROUPS = {'a': {'place_in_latent': [0, 192]}, 'b': {'place_in_latent': [192, 384]}, 'c': {'place_in_latent': [384, 512]}}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from gan_control_b200 import kernels as K
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
+    size, batch, reg = args.size, args.batch, not args.no_reg
+    main = measure(torch, dist, args, dev, rank, world, size, batch, args.steps, args.warmup, reg=reg,
+                   sampler_index=local_rank if rank == 0 else None, ncu_range=args.ncu_range)
+    log(f'main: {main["value"]:.1f} img/s, e2e {main["e2e"]["value"]:.1f}')
+    extra = []
+    if not args.skip_extra and not args.ncu_range:
+        # the per-GPU workloads of the other BASELINE.json configurations, same run, same timing method
+        for name, kw in (
+                ('configs[2]: FFHQ-1024 DDP, 4 images / GPU, R1 + path-length at cadence', dict(size=1024, batch=4)),
+                ('configs[4]: AFHQ-512 layout (split-FC 192/192/128, r1 0.5, lr 0.0025), 8 images / GPU',
+                 dict(size=512, batch=8, fc_groups=AFHQ_GROUPS, r1=0.5, lr=0.0025))):
+            m = measure(torch, dist, args, dev, rank, world, steps=16, warmup=2, with_e2e=False, **kw)
+            extra.append({'config': name, 'global_batch': kw['batch'] * world, 'per_gpu_batch': kw['batch'], 'n_gpus': world,
+                          'value': m['value'], 'unit': UNIT, 'ms_per_step': m['ms_per_step'], 'steps': 16,
+                          'timed_window': m['timed_window'], 'gpu_launches': m['gpu_launches']})
+            log(f'extra {name}: {m["value"]:.1f} img/s')
     if rank != 0:
         _finish(world)
         return
     peaks, peak_kind = measured_peaks()
+    value = main['value']
+    g_f, d_f = G_D_GFLOP.get(size, (0, 0))
+    g_mb, d_mb = G_D_MB.get(size, (0, 0))
+    tflops = (4 * g_f + 8 * d_f) * value / 1e3
+    gbs = (4 * g_mb + 8 * d_mb) * value / 1e3
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if act == torch.bfloat16 else 'f32', 'data': 'synthetic',
-        'config': dict(workload_config(size, reg, batch, world), cuda_graphs=use_graph,
-                       l2='inputs larger than L2 (each step streams >10 GB of activations; no explicit flush)'),
-        'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
-                'h2d_bytes_per_step': host_real.numel() * 4, 'd2h_bytes_per_step': 8},
-        'gpu_launches': launches,
-        'step_tflops': GFLOP_PER_IMG.get(size, 0) * value / 1e3,
+        'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if args.dtype == 'bf16' else 'f32', 'data': 'synthetic',
+        'config': workload_config(size, reg, batch, world), 'cuda_graphs': main['cuda_graphs'],
+        'timed_window': main['timed_window'], 'clocks': main['clocks'], 'e2e': main['e2e'],
+        'gpu_launches': main['gpu_launches'], 'graph_launches': main['graph_launches'],
+        'conv_engine_calls': main['conv_engine_calls'],
+        # the whole step against the machine: plain-step algorithmic work (4 G_f + 8 D_f, BASELINE.md section 2; the
+        # regulariser steps inside the window add real work that is NOT counted, so this is a lower bound)
+        'roofline_step': {'tflops': tflops, 'frac_sustained': tflops / peaks.get('bf16_tflops_sustained', 1400.0),
+                          'gbs': gbs, 'frac_hbm': gbs / peaks.get('hbm_gbs', 6650.0),
+                          'algorithmic_gflop_per_image': 4 * g_f + 8 * d_f, 'algorithmic_mb_per_image': 4 * g_mb + 8 * d_mb,
+                          'peak_source': peak_kind},
+        'step_tflops': tflops,
     }
+    if extra:
+        line['extra_configs'] = extra
     if not args.skip_roofline:
-        head, layers = conv_roofline(torch, K, act, size, batch, peaks)
+        import torch as _t
+        head, layers = conv_roofline(torch, K, _t.bfloat16 if args.dtype == 'bf16' else _t.float32, size, batch, peaks)
         line['roofline'] = dict(head, peak_source=peak_kind + ' (burst, kernel timed alone)')
         line['roofline_layers'] = layers
+    if not args.skip_library_baseline and world == 1 and not args.ncu_range:
+        line['gpu_library_baseline'] = gpu_library_baseline(torch, size, batch, dev, log)
+        for k in ('fp32', 'bf16_autocast'):
+            v = line['gpu_library_baseline'].get(k, {}).get('value')
+            if v:
+                line['gpu_library_baseline'][k]['speedup_of_this_repo'] = value / v
     if not args.skip_cpu_baseline and world == 1:        # the CPU baseline is reported by the single-GPU run only
         threads = os.cpu_count() or 1
-        csize = args.cpu_sample_size or size
-        v, t, ratio = cpu_reference_sample(csize, threads)
-        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                'sample': f'G forward + D forward on 1 image at {csize}x{csize}, fp32, {t:.1f} s; scaled to the '
-                                          f'plain G+D step by its FLOP ratio {ratio:.2f}'}
+        csize = args.cpu_sample_size or min(size, 256)       # bounded: the full-resolution probe is the reference arm's job
+        v, ms, sample, used = cpu_reference_steps(csize, 3, 1, threads, 60.0)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
+                                'sample_resolution': used}
     print(json.dumps(line), flush=True)
     _finish(world)
 

@@ -7,7 +7,23 @@ namespace b200gan {
 // 0 = automatic (tcgen05 when the shape is eligible), 1 = CUDA-core engine only, 2 = automatic but without
 // the halo-reuse variant (testing / A-B timing)
 static std::atomic<int> g_conv_engine{0};
+// launches per engine (include/b200gan.h B200GAN_ENGINE_*): the evidence that a test / a step ran on the tensor cores
+static std::atomic<uint64_t> g_engine_launches[B200GAN_ENGINE_COUNT];
+static std::atomic<int> g_last_engine{-1};
+static inline int ran(int engine, int rc) {
+    if (rc == 0) {
+        g_engine_launches[engine].fetch_add(1, std::memory_order_relaxed);
+        g_last_engine.store(engine, std::memory_order_relaxed);
+    }
+    return rc;
+}
 }  // namespace b200gan
+
+extern "C" uint64_t b200gan_engine_launches(int engine) {
+    if (engine < 0 || engine >= B200GAN_ENGINE_COUNT) return 0;
+    return b200gan::g_engine_launches[engine].load(std::memory_order_relaxed);
+}
+extern "C" int b200gan_last_conv_engine(void) { return b200gan::g_last_engine.load(std::memory_order_relaxed); }
 
 extern "C" int b200gan_set_conv_engine(int engine) {
     int prev = b200gan::g_conv_engine.exchange(engine & 0xff);
@@ -22,14 +38,14 @@ static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, c
     const int b = g.b;
     const bool packed = g.pack_in || g.pack_out;
     if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
-        return conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st);
+        return ran(B200GAN_ENGINE_FWD_POINTWISE, conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st));
     // the halo kernel's epilogue reads bias / rowscale as float4
     if (g_conv_engine.load() == 0 && b > 0 && (((uintptr_t)bias | (uintptr_t)rowscale) & 15) == 0 &&
         conv_fwd_halo_eligible(dtype, g, x, w, y))
-        return conv_fwd_halo(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st);
+        return ran(B200GAN_ENGINE_FWD_HALO, conv_fwd_halo(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st));
     if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
-        return conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st);
-    return conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st);
+        return ran(B200GAN_ENGINE_FWD_UMMA, conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st));
+    return ran(B200GAN_ENGINE_FWD_SIMT, conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st));
 }
 
 static int conv_wgrad_dispatch(const void* x, const void* gy, float* gw, int dtype, const b200gan::ConvGeom& g,
@@ -38,12 +54,12 @@ static int conv_wgrad_dispatch(const void* x, const void* gy, float* gw, int dty
     const int b = g.b;
     const bool packed = g.pack_in || g.pack_out;
     if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_wgrad_pointwise_eligible(dtype, g, x, gy))
-        return conv_wgrad_pointwise(x, gy, gw, dtype, g, st);
+        return ran(B200GAN_ENGINE_WGRAD_POINTWISE, conv_wgrad_pointwise(x, gy, gw, dtype, g, st));
     if (g_conv_engine.load() == 0 && b > 0 && conv_wgrad_halo_eligible(dtype, g, x, gy))
-        return conv_wgrad_halo(x, gy, gw, g, st);
+        return ran(B200GAN_ENGINE_WGRAD_HALO, conv_wgrad_halo(x, gy, gw, g, st));
     if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_wgrad_umma_eligible(dtype, g, x, gy))
-        return conv_wgrad_umma(x, gy, gw, g, st);
-    return conv_wgrad_simt(x, gy, gw, dtype, g, st);
+        return ran(B200GAN_ENGINE_WGRAD_UMMA, conv_wgrad_umma(x, gy, gw, g, st));
+    return ran(B200GAN_ENGINE_WGRAD_SIMT, conv_wgrad_simt(x, gy, gw, dtype, g, st));
 }
 
 extern "C" int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype, int b, int in_h, int in_w, int ic,

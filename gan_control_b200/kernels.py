@@ -40,6 +40,8 @@ _SIGNATURES = {
     'b200gan_conv_fwd_packed': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
     'b200gan_conv_wgrad_packed': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
     'b200gan_set_conv_engine': ([_i], _i),
+    'b200gan_engine_launches': ([_i], _c.c_uint64),
+    'b200gan_last_conv_engine': ([], _i),
     'b200gan_conv_wgrad': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
     'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
     'b200gan_gemm_f32': ([_vp, _vp, _vp] + [_i] * 8 + [_f, _f, _vp], _i),
@@ -75,6 +77,20 @@ def set_conv_engine(engine):
 
 def launch_count():
     return int(lib().b200gan_launch_count())
+
+
+ENGINES = ('fwd_simt', 'fwd_pointwise', 'fwd_umma', 'fwd_halo', 'wgrad_simt', 'wgrad_pointwise', 'wgrad_umma', 'wgrad_halo')
+
+
+def engine_launches():
+    """{engine name: convolution calls it served so far} (include/b200gan.h B200GAN_ENGINE_*); `fwd_umma`, `fwd_halo`,
+    `wgrad_umma`, `wgrad_halo` are the tcgen05 kernels."""
+    return {name: int(lib().b200gan_engine_launches(i)) for i, name in enumerate(ENGINES)}
+
+
+def last_conv_engine():
+    i = int(lib().b200gan_last_conv_engine())
+    return None if i < 0 else ENGINES[i]
 
 
 def _check(rc, what):

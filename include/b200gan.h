@@ -128,6 +128,22 @@ int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype,
  * gather kernel otherwise; 1 = CUDA-core kernel only; 2 = automatic but without the halo-reuse variant
  * (tests, A/B timing).  Returns the previous value. */
 int b200gan_set_conv_engine(int engine);
+/* Which engine served the convolution calls of this process: per-engine launch counters and the engine of the most
+ * recent call (-1 before the first).  FWD_* count b200gan_conv_fwd / _packed (forward passes AND data gradients, which
+ * are the same gather form), WGRAD_* count b200gan_conv_wgrad / _packed.  UMMA / HALO are the tcgen05 + TMEM + TMA
+ * kernels; POINTWISE the streaming 1x1 kernels for a <= 4-channel side (ToRGB, from_rgb); SIMT the CUDA-core kernel
+ * (fp32 parity engine, odd shapes).  Tests assert on these so that a silent fallback cannot pass as the tensor-core path. */
+#define B200GAN_ENGINE_FWD_SIMT 0
+#define B200GAN_ENGINE_FWD_POINTWISE 1
+#define B200GAN_ENGINE_FWD_UMMA 2
+#define B200GAN_ENGINE_FWD_HALO 3
+#define B200GAN_ENGINE_WGRAD_SIMT 4
+#define B200GAN_ENGINE_WGRAD_POINTWISE 5
+#define B200GAN_ENGINE_WGRAD_UMMA 6
+#define B200GAN_ENGINE_WGRAD_HALO 7
+#define B200GAN_ENGINE_COUNT 8
+uint64_t b200gan_engine_launches(int engine);
+int b200gan_last_conv_engine(void);
 /* Weight gradient of the form above:
  *   gw[wb][ky][kx][o][i] += sum_{b,oy,ox} gy[b][oy][ox][o] * z[b][oy*down+ky-pad0][..][i]
  * gw is fp32, same [wb][kh][kw][oc][ic] layout, must be zero-initialised

@@ -145,7 +145,7 @@ def styled_conv(sd, prefix, x, style, noise, upsample):
                          sd[prefix + 'conv.modulation.weight'], sd[prefix + 'conv.modulation.bias'],
                          True, upsample, sd.get(prefix + 'conv.blur.kernel'))
     if noise is None:
-        noise = torch.randn(y.shape[0], 1, y.shape[2], y.shape[3], dtype=y.dtype)
+        noise = torch.randn(y.shape[0], 1, y.shape[2], y.shape[3], dtype=y.dtype, device=y.device)
     y = y + sd[prefix + 'noise.weight'] * noise
     return fused_leaky_relu(y, sd[prefix + 'activate.bias'])
 

@@ -337,3 +337,83 @@ def test_fused_resampling_layers(dt):
         assert rel_err(a, r) < tol1
     for a, r in zip(gg, ggr):
         assert rel_err(a, r) < tol2
+
+
+def test_train_step_fp32_matches_restated_reference_step():
+    """Three eager training iterations (D step, R1, G step, path length, Adam, EMA) on the GPU in fp32 against the
+    restated generator_trainer.py step on the CPU oracle in fp64 (tests/test_train_step_cpu.py::oracle_run): the
+    parameter UPDATES of both networks and of g_ema agree.  (Adam with beta1 = 0 divides by |g|, so a handful of
+    near-zero gradients may flip sign in fp32: the bound is on the relative L2 of the accumulated update.)"""
+    import copy
+    import test_train_step_cpu as TS
+    from gan_control_b200.train_step import GanTrainStep
+    batch, iters = 4, [0, 1, 2]
+    real, zs, pl_noise = TS.make_inputs(batch)
+    sd_g, sd_d, ema = TS.oracle_run(batch, real, zs, pl_noise, iters)
+    g = TS.FixedNoiseG(TS.SIZE, TS.SDIM, TS.NMLP, channel_multiplier=2, conv_transpose=True)
+    init_g = P.seeded_state_dict(P.generator_shapes(TS.SIZE, TS.SDIM, TS.NMLP, 2), 5)
+    g.load_state_dict(init_g)
+    g.fixed_noise = [TS.rnd(50 + i, batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2)).float().to(DEV) for i in range(g.num_layers)]
+    d = M.Discriminator(TS.SIZE, channel_multiplier=2)
+    init_d = P.seeded_state_dict(P.discriminator_shapes(TS.SIZE, 2), 6)
+    d.load_state_dict(init_d)
+    g, d = g.to(DEV), d.to(DEV)
+    g_ema = copy.deepcopy(g)
+    step = GanTrainStep(g, d, g_ema, batch=batch, latent_size=TS.SDIM)
+    f = lambda t: t.float().to(DEV)
+    for i in iters:
+        z_d, z_g, z_pl = zs[i]
+        step.discriminator_step(f(real), [f(z_d)])
+        if i % 16 == 0:
+            step.discriminator_regularize_step(f(real))
+        do_reg = i % 4 == 0
+        step.generator_step([f(z_g)], ema=not do_reg)
+        if do_reg:
+            step.generator_regularize_step([f(z_pl)], pl_noise=f(pl_noise))
+            step.ema_arena.data.mul_(step.accum).add_(step.g_arena.data, alpha=1 - step.accum)
+    torch.cuda.synchronize()
+    errs = {}
+    for name, module, ref, init in [('g', g, sd_g, init_g), ('d', d, sd_d, init_d), ('g_ema', g_ema, ema, init_g)]:
+        num = den = 0.0
+        for k, p in module.named_parameters():
+            upd_ref = ref[k].detach().double() - init[k].double()
+            upd = p.detach().cpu().double() - init[k].double()
+            num += float((upd - upd_ref).pow(2).sum())
+            den += float(upd_ref.pow(2).sum())
+        errs[name] = (num / max(den, 1e-300)) ** 0.5
+        print(f'train step fp32 on GPU vs restated reference step: {name} update rel-L2 err {errs[name]:.2e}')
+    # measured on B200: g 1.5e-2, d 6.6e-3, g_ema 5.5e-2 (the EMA update is a 3e-4 fraction of g's: a difference of nearly equal numbers)
+    assert errs['g'] < 5e-2 and errs['d'] < 5e-2 and errs['g_ema'] < 1.5e-1, errs
+
+
+def test_graphed_step_equals_eager_step():
+    """CUDA-graph replay of the four step variants == the eager step: same seed, same synthetic batch, three
+    iterations incl. both regularisers; losses and parameters agree (fp32 activations).  Not bit-exact: the weight
+    gradients accumulate with fp32 atomics (order varies run to run) and Adam with beta1 = 0 amplifies that noise."""
+    import copy
+    from gan_control_b200.train_step import GanTrainStep
+    outs = []
+    for graphed in (False, True):
+        torch.manual_seed(7)
+        g = M.Generator(16, 64, 3, channel_multiplier=2, conv_transpose=True).to(DEV)
+        d = M.Discriminator(16, channel_multiplier=2).to(DEV)
+        step = GanTrainStep(g, d, copy.deepcopy(g), batch=4, latent_size=64)
+        real = torch.randn(4, 3, 16, 16, device=DEV).clamp_(-1, 1)
+        if graphed:
+            step.capture(tuple(real.shape), warmup=1)
+        run = step.train_step_graphed if graphed else step.train_step
+        torch.manual_seed(99)
+        losses = []
+        for i in (0, 1, 2):
+            d_loss, g_loss = run(i, real)
+            losses.append((float(d_loss), float(g_loss)))
+        torch.cuda.synchronize()
+        outs.append((losses, step.g_arena.data.clone(), step.d_arena.data.clone(), step.ema_arena.data.clone()))
+    (l0, g0, d0, e0), (l1, g1, d1, e1) = outs
+    print('eager losses', l0, 'graphed losses', l1)
+    for a, b in zip(l0, l1):
+        assert abs(a[0] - b[0]) < 2e-2 * max(1.0, abs(a[0])) and abs(a[1] - b[1]) < 2e-2 * max(1.0, abs(a[1]))
+    for a, b in [(g0, g1), (d0, d1), (e0, e1)]:
+        err = float((a - b).norm() / a.norm())
+        print(f'graphed vs eager parameters rel-L2 {err:.2e}')
+        assert err < 2e-3
