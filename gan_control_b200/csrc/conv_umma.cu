@@ -191,22 +191,46 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int r = q * 32 + lane;
         const int w_l = r % p.TW, h_l = (r / p.TW) % p.TH, n_l = r / (p.TW * p.TH);
         const float nw = (p.noise != nullptr && p.noise_w != nullptr) ? *p.noise_w : 0.f;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const float g = p.gain, gs = p.gain * p.slope;
+        const bool fast_act = g > 0.f && p.slope >= 0.f && p.slope <= 1.f;   // gain*lrelu(u) = max(g*u, g*slope*u)
+        // side inputs (bias / rowscale as float4) need 16-byte aligned rows
+        const bool vec_side = ((((uintptr_t)p.bias | (uintptr_t)p.rowscale) & 15) == 0) && (p.OC % 4 == 0);
+        // this thread's output pixel of a tile; the raw noise bits of the NEXT tile are requested while the current
+        // one is drained (the load's DRAM latency used to sit between the accumulator wait and the first store)
+        auto pixel_of = [&](int tile, int& n, int& oy, int& ox, int& ocb, bool& zero_tile) -> bool {
             const TileCoord t = decode_tile(p, tile);
             const FwdPhase& P = p.phase[t.phase];
+            n = t.n0 + n_l;
+            const int j = t.h0 + h_l, i = t.w0 + w_l;
+            oy = j * p.os + P.py;
+            ox = i * p.os + P.px;
+            ocb = t.ocb;
+            zero_tile = P.ntaps == 0;
+            return r < p.rows && n < p.B && j < P.ph && i < P.pw && oy < p.OH && ox < p.OW;
+        };
+        uint32_t nraw = 0u;
+        auto fetch_noise = [&](int tile) {
+            if (p.noise == nullptr || tile >= p.total_tiles) return;
+            int n, oy, ox, ocb;
+            bool zt;
+            if (pixel_of(tile, n, oy, ox, ocb, zt))
+                nraw = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.noise) + ((int64_t)n * p.OH + oy) * p.OW + ox);
+        };
+        int it = 0;
+        fetch_noise(blockIdx.x);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int n, oy, ox, ocb;
+            bool zero_tile;
+            const bool valid = pixel_of(tile, n, oy, ox, ocb, zero_tile);
             const int acc = it & 1, acc_par = (it >> 1) & 1;
             mbar_wait(tfull + acc, acc_par);
             tc_fence_after();
-            const int n = t.n0 + n_l, j = t.h0 + h_l, i = t.w0 + w_l;
-            const int oy = j * p.os + P.py, ox = i * p.os + P.px;
-            const bool valid = r < p.rows && n < p.B && j < P.ph && i < P.pw && oy < p.OH && ox < p.OW;
-            const bool zero_tile = P.ntaps == 0;
             const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
-            __nv_bfloat16* dst = p.y + pix * p.OC + t.ocb * p.BN;
-            const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
-            const float* rs = p.rowscale ? p.rowscale + (int64_t)(valid ? n : 0) * p.OC + t.ocb * p.BN : nullptr;
-            const float* bs = p.bias ? p.bias + t.ocb * p.BN : nullptr;
+            __nv_bfloat16* dst = p.y + pix * p.OC + ocb * p.BN;
+            const float nz = (valid && p.noise) ? nw * __uint_as_float(nraw << 16) : 0.f;
+            fetch_noise(tile + gridDim.x);
+            const float* rs = p.rowscale ? p.rowscale + (int64_t)(valid ? n : 0) * p.OC + ocb * p.BN : nullptr;
+            const float* bs = p.bias ? p.bias + ocb * p.BN : nullptr;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
                 float v[16];
@@ -218,12 +242,34 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 }
                 if (valid) {
                     if (p.has_ep) {
+                        float rr[16], bb[16];
+                        if (vec_side) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float u = v[e];
-                            if (rs) u *= rs[c0 + e];
-                            u += nz + (bs ? bs[c0 + e] : 0.f);
-                            v[e] = p.gain * (u > 0.f ? u : u * p.slope);
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 r4 = rs ? __ldg(reinterpret_cast<const float4*>(rs + c0) + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+                                const float4 b4 = bs ? __ldg(reinterpret_cast<const float4*>(bs + c0) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                rr[4 * e] = r4.x; rr[4 * e + 1] = r4.y; rr[4 * e + 2] = r4.z; rr[4 * e + 3] = r4.w;
+                                bb[4 * e] = b4.x; bb[4 * e + 1] = b4.y; bb[4 * e + 2] = b4.z; bb[4 * e + 3] = b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                rr[e] = rs ? rs[c0 + e] : 1.f;
+                                bb[e] = bs ? bs[c0 + e] : 0.f;
+                            }
+                        }
+                        if (fast_act) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const float u = fmaf(v[e], rr[e], nz + bb[e]);
+                                v[e] = fmaxf(u * g, u * gs);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const float u = fmaf(v[e], rr[e], nz + bb[e]);
+                                v[e] = g * (u > 0.f ? u : u * p.slope);
+                            }
                         }
                     }
                     uint32_t pk[8];

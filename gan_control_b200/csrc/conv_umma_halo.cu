@@ -54,23 +54,26 @@ struct HaloParams {
     __nv_bfloat16* y;
 };
 
-// 16 accumulator columns of one pixel -> epilogue -> 32 bytes of bf16.  rs / bs: 16 floats each, 16-byte aligned
-// (warp-uniform addresses: four broadcast LDG.128 each instead of 16 scalar loads).
-__device__ __forceinline__ void epilogue_store16(const HaloParams& p, float (&v)[16], __nv_bfloat16* dst, const float* rs,
-                                                 const float* bs, float nz) {
+// 16 accumulator columns of one pixel -> epilogue -> 32 bytes of bf16.  r / b: this chunk's demodulation scales and
+// biases, already in registers.
+template <bool ROW>
+__device__ __forceinline__ void epilogue_math_store16(const HaloParams& p, float (&v)[16], __nv_bfloat16* dst,
+                                                      const float (&r)[16], const float (&b)[16], float nz) {
     if (p.has_ep) {
-        float r[16], b[16];
+        // gain * lrelu(u) = max(g*u, g*slope*u) for gain > 0, 0 <= slope <= 1 (every use on the path): FFMA, FMUL, FMNMX
+        const float g = p.gain, gs = p.gain * p.slope;
+        if (g > 0.f && p.slope >= 0.f && p.slope <= 1.f) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float4 r4 = rs ? __ldg(reinterpret_cast<const float4*>(rs) + e) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float4 b4 = bs ? __ldg(reinterpret_cast<const float4*>(bs) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            r[4 * e] = r4.x; r[4 * e + 1] = r4.y; r[4 * e + 2] = r4.z; r[4 * e + 3] = r4.w;
-            b[4 * e] = b4.x; b[4 * e + 1] = b4.y; b[4 * e + 2] = b4.z; b[4 * e + 3] = b4.w;
-        }
+            for (int e = 0; e < 16; ++e) {
+                const float u = ROW ? fmaf(v[e], r[e], nz + b[e]) : v[e] + (nz + b[e]);
+                v[e] = fmaxf(u * g, u * gs);
+            }
+        } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const float u = fmaf(v[e], r[e], nz + b[e]);
-            v[e] = p.gain * (u > 0.f ? u : u * p.slope);
+            for (int e = 0; e < 16; ++e) {
+                const float u = ROW ? fmaf(v[e], r[e], nz + b[e]) : v[e] + (nz + b[e]);
+                v[e] = g * (u > 0.f ? u : u * p.slope);
+            }
         }
     }
     uint32_t pk[8];
@@ -82,6 +85,16 @@ __device__ __forceinline__ void epilogue_store16(const HaloParams& p, float (&v)
     uint4* d4 = reinterpret_cast<uint4*>(dst);
     d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+// 16 floats through four 16-byte loads (global via the read-only path, or shared memory: warp-uniform = broadcast)
+template <bool GLOBAL>
+__device__ __forceinline__ void load16(const float* src, float (&o)[16], float fill) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float4 t = make_float4(fill, fill, fill, fill);
+        if (src) t = GLOBAL ? __ldg(reinterpret_cast<const float4*>(src) + e) : *(reinterpret_cast<const float4*>(src) + e);
+        o[4 * e] = t.x; o[4 * e + 1] = t.y; o[4 * e + 2] = t.z; o[4 * e + 3] = t.w;
+    }
 }
 
 // KDIM = 3 or 1 (kernel size), ROWB = 128 or 64 (bytes per pixel row of a channel chunk = swizzle width): both
@@ -102,10 +115,16 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint64_t* tempty = tfull + kHaloAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kHaloAcc);
 
+    __shared__ __align__(16) float s_bias[128];          // physical output channels (<= 128)
+    __shared__ __align__(16) float s_rs[2][128];         // demodulation row of the sample each epilogue group is on
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_x);
         prefetch_tensormap(&map_w);
+    }
+    {
+        const int ch = p.pack_out ? p.CQ : p.OC;
+        if ((int)threadIdx.x < ch) s_bias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
@@ -253,8 +272,75 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int r = q * 32 + lane;
         const int w_l = r % kHTW, h_l = r / kHTW;
         const float nw = (p.noise != nullptr && p.noise_w != nullptr) ? *p.noise_w : 0.f;
+        // ncu (profiles/r02_ncu_halo_epilogue.md): the per-pixel noise value was loaded before the accumulator wait but
+        // CONSUMED there too (nw * noise), so the warp sat on the DRAM latency of that 2-byte load every tile: 25 % of
+        // all stall samples of the kernel on one instruction, 0.15 ms of 0.72 ms.  Now the raw bits of the NEXT tile's
+        // noise are requested while the current tile is drained and only converted after the next accumulator wait.
+        uint32_t nraw0 = 0u, nraw1 = 0u;
+        const int ch_phys = p.pack_out ? p.CQ : p.OC, gt = (warp & 3) * 32 + lane;      // thread within the group
+        float* my_rs = s_rs[group];
+        const float* bs_sm = p.bias ? s_bias : nullptr;
+        int rs_n = -1;
+        // Where the per-channel side inputs come from (measured, profiles/r02_epilogue_cost.md): at 64 physical output
+        // channels the bias and the current sample's demodulation row are staged in shared memory (0.434 -> 0.385 ms for
+        // the full StyledConv epilogue at 64 -> 64 @512^2); with <= 32 channels the MMAs are bound by the shared-memory
+        // port (N <= 32: 40 clk of operand fetch per instruction) and LDS wavefronts are taken from them: the read-only
+        // global path (L1 hits) is faster there (0.57 vs 0.65 ms).  A register-resident bias row spilled (168 registers).
+        const bool side_smem = ch_phys > 32;
+        auto chunk = [&](uint32_t taddr, int col, __nv_bfloat16* dst, int c0, const float* rs_g, float nz, bool valid) {
+            float v[16], r16[16], b16[16];
+            if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)col, v);
+            if (valid && !(p.dbg & 4)) {
+                if (side_smem) {
+                    load16<false>(p.rowscale ? my_rs + c0 : nullptr, r16, 1.f);
+                    load16<false>(bs_sm ? bs_sm + c0 : nullptr, b16, 0.f);
+                } else {
+                    load16<true>(rs_g ? rs_g + c0 : nullptr, r16, 1.f);
+                    load16<true>(p.bias ? p.bias + c0 : nullptr, b16, 0.f);
+                }
+                epilogue_math_store16<true>(p, v, dst + c0, r16, b16, nz);
+            }
+        };
+        // rowscale[n][:] -> shared memory when this group moves on to another sample (all four warps of a group walk
+        // the same tiles, so they arrive here in the same iteration: a 128-thread named barrier, id 1 / 2)
+        auto stage_rowscale = [&](int n) {
+            if (p.rowscale == nullptr || n == rs_n) return;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");      // everyone is done reading the old row
+            if (gt < ch_phys) my_rs[gt] = p.rowscale[(int64_t)n * ch_phys + gt];
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+            rs_n = n;
+        };
+        // address of this thread's noise sample(s) of `tile` (null when the tile / the pixel does not exist)
+        auto noise_ptr = [&](int tile) -> const __nv_bfloat16* {
+            if (p.noise == nullptr || tile >= p.total_tiles) return nullptr;
+            uint32_t n, t, th, tw;
+            p.div_img.divmod((uint32_t)tile, n, t);
+            p.div_tw.divmod(t, th, tw);
+            const int oy = (int)th * kHTH + h_l, ox = (int)tw * kHTW + w_l;
+            if (oy >= p.OH || ox >= p.OW) return nullptr;
+            if (!p.pack_out) return p.noise + ((int64_t)n * p.OH + oy) * p.OW + ox;
+            return p.noise + ((int64_t)n * (2 * p.OH) + 2 * oy) * (2 * p.OW) + 2 * ox;
+        };
+        // two-level prefetch: the line is pulled into L2 four of this group's tiles ahead (no register cost), the value
+        // into a register one tile ahead
+        auto fetch_noise = [&](int tile) {
+            if (const __nv_bfloat16* far = noise_ptr(tile + 6 * (int)gridDim.x)) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
+                if (p.pack_out) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + 2 * p.OW));
+            }
+            const __nv_bfloat16* q = noise_ptr(tile);
+            if (q == nullptr) return;
+            if (!p.pack_out) {
+                nraw0 = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(q));
+            } else {
+                nraw0 = __ldg(reinterpret_cast<const uint32_t*>(q));
+                nraw1 = __ldg(reinterpret_cast<const uint32_t*>(q + 2 * p.OW));
+            }
+        };
         int it = group;
-        for (int tile = blockIdx.x + group * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+        const int first = blockIdx.x + group * gridDim.x;
+        fetch_noise(first);
+        for (int tile = first; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
             uint32_t n, t, th, tw;
             p.div_img.divmod((uint32_t)tile, n, t);
             p.div_tw.divmod(t, th, tw);
@@ -265,37 +351,31 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             if (!p.pack_out) {
                 const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
                 __nv_bfloat16* dst = p.y + pix * p.OC;
-                const float nz = (valid && p.noise) ? nw * __bfloat162float(p.noise[pix]) : 0.f;
-                const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
+                if (side_smem) stage_rowscale((int)n);
+                const float* rs_g = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
                 mbar_wait(tfull + acc, acc_par);
                 tc_fence_after();
-                for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                    float v[16];
-                    if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)c0, v);
-                    if (valid && !(p.dbg & 4)) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz);
-                }
+                const float nz = (valid && p.noise) ? nw * __uint_as_float(nraw0 << 16) : 0.f;
+                fetch_noise(tile + 2 * gridDim.x);
+                for (int c0 = 0; c0 < p.BN; c0 += 16) chunk(taddr, c0, dst, c0, rs_g, nz, valid);
             } else {
                 // depth-to-space: accumulator columns [(py*2+px)*CQ + c] of view pixel (oy, ox) are channel c of the
                 // physical pixel (2*oy+py, 2*ox+px); bias / rowscale / noise follow the physical tensor
-                const float* rs = p.rowscale ? p.rowscale + (int64_t)n * p.CQ : nullptr;
+                if (side_smem) stage_rowscale((int)n);
+                const float* rs_g = p.rowscale ? p.rowscale + (int64_t)n * p.CQ : nullptr;
                 const int64_t pix0 = ((int64_t)n * (2 * p.OH) + 2 * oy) * (2 * p.OW) + 2 * ox;
-                float nz[4] = {0.f, 0.f, 0.f, 0.f};
-                if (valid && p.noise) {
-                    const __nv_bfloat162 n0 = *reinterpret_cast<const __nv_bfloat162*>(p.noise + pix0);
-                    const __nv_bfloat162 n1 = *reinterpret_cast<const __nv_bfloat162*>(p.noise + pix0 + 2 * p.OW);
-                    nz[0] = nw * __low2float(n0); nz[1] = nw * __high2float(n0);
-                    nz[2] = nw * __low2float(n1); nz[3] = nw * __high2float(n1);
-                }
                 mbar_wait(tfull + acc, acc_par);
                 tc_fence_after();
+                float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid && p.noise) {
+                    nz[0] = nw * __uint_as_float(nraw0 << 16); nz[1] = nw * __uint_as_float(nraw0 & 0xffff0000u);
+                    nz[2] = nw * __uint_as_float(nraw1 << 16); nz[3] = nw * __uint_as_float(nraw1 & 0xffff0000u);
+                }
+                fetch_noise(tile + 2 * gridDim.x);
 #pragma unroll
                 for (int ph = 0; ph < 4; ++ph) {
                     __nv_bfloat16* dst = p.y + (pix0 + (ph >> 1) * (2 * p.OW) + (ph & 1)) * p.CQ;
-                    for (int c0 = 0; c0 < p.CQ; c0 += 16) {
-                        float v[16];
-                        if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)(ph * p.CQ + c0), v);
-                        if (valid && !(p.dbg & 4)) epilogue_store16(p, v, dst + c0, rs ? rs + c0 : nullptr, p.bias ? p.bias + c0 : nullptr, nz[ph]);
-                    }
+                    for (int c0 = 0; c0 < p.CQ; c0 += 16) chunk(taddr, ph * p.CQ + c0, dst, c0, rs_g, nz[ph], valid);
                 }
             }
             tc_fence_before();
@@ -414,10 +494,10 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (attr_dev != cur_dev) {
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
         attr_dev = cur_dev;
     }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();

@@ -43,6 +43,8 @@ _SIGNATURES = {
     'b200gan_engine_launches': ([_i], _c.c_uint64),
     'b200gan_last_conv_engine': ([], _i),
     'b200gan_conv_wgrad': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
+    'b200gan_modweight_fwd': ([_vp] * 5 + [_i] * 6 + [_f, _i, _i, _vp], _i),
+    'b200gan_modweight_bwd': ([_vp] * 7 + [_i] * 5 + [_f, _i, _i, _vp], _i),
     'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
     'b200gan_gemm_f32': ([_vp, _vp, _vp] + [_i] * 8 + [_f, _f, _vp], _i),
     'b200gan_mapping_fwd': ([_vp, _vp, _vp] + [_i] * 6 + [_vp], _i),
@@ -308,6 +310,46 @@ def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False, pack_x=Fal
                 _check(lib().b200gan_conv_wgrad(_ptr(x), _ptr(gy), _ptr(gw), _dt(x), b, h, wd, ic, oh, ow, oc, kh, kw, up,
                                                 down, pad0, int(per_sample), _stream()), 'conv_wgrad')
     return gw
+
+
+def modweight_fwd(weight, s, scale, demodulate, flip, dtype, want_adjoint=False):
+    """ModulatedConv2d's per-sample weights in one kernel (include/b200gan.h): weight (OC,IC,KH,KW) fp32, s (B,IC) fp32 ->
+    wk (B,KH,KW,OC,IC) `dtype` (K-major operand of conv_fwd), wk_adjoint (B,KH,KW,IC,OC) or None, d (B,OC) fp32 or None."""
+    _cuda(weight, s)
+    weight, s = _f32c(weight), _f32c(s)
+    oc, ic, kh, kw = weight.shape
+    b = s.shape[0]
+    assert s.shape[1] == ic
+    wk = torch.empty((b, kh, kw, oc, ic), dtype=dtype, device=s.device)
+    wkt = torch.empty((b, kh, kw, ic, oc), dtype=dtype, device=s.device) if want_adjoint else None
+    d = torch.empty((b, oc), dtype=torch.float32, device=s.device) if demodulate else None
+    if b:
+        with torch.cuda.device(s.device):
+            _check(lib().b200gan_modweight_fwd(_ptr(weight), _ptr(s), _ptr(d), _ptr(wk), _ptr(wkt), _dt(wk), b, oc, ic, kh, kw,
+                                               float(scale), int(bool(demodulate)), int(bool(flip)), _stream()), 'modweight_fwd')
+    return wk, wkt, d
+
+
+def modweight_bwd(g, weight, s, d, scale, demodulate, flip, want_gs=True, want_gw=True):
+    """First-order backward of modweight_fwd: g (B,KH,KW,OC,IC) fp32 -> (gs (B,IC) | None, gweight (OC,IC,KH,KW) | None)."""
+    _cuda(g, weight, s, d)
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    weight, s, d = _f32c(weight), _f32c(s), _f32c(d)
+    oc, ic, kh, kw = weight.shape
+    b = s.shape[0]
+    assert g.shape == (b, kh, kw, oc, ic)
+    need_gs = want_gs or (want_gw and demodulate)
+    gs = torch.zeros((b, ic), dtype=torch.float32, device=s.device) if need_gs else None
+    e = torch.empty((b, oc), dtype=torch.float32, device=s.device) if demodulate else None
+    gw = torch.empty((oc, ic, kh, kw), dtype=torch.float32, device=s.device) if want_gw else None
+    if b:
+        with torch.cuda.device(s.device):
+            _check(lib().b200gan_modweight_bwd(_ptr(g), _ptr(weight), _ptr(s), _ptr(d), _ptr(gs), _ptr(e), _ptr(gw), b, oc, ic,
+                                               kh, kw, float(scale), int(bool(demodulate)), int(bool(flip)), _stream()),
+                   'modweight_bwd')
+    elif gw is not None:
+        gw.zero_()
+    return (gs if want_gs else None), gw
 
 
 def linear_fwd(x, w, bias, scale, bias_mul, act):

@@ -190,6 +190,33 @@ class ModulatedConv2d(nn.Module):                                             # 
         x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
         return x, wk, d, True
 
+    def demod_coeff(self, s):
+        """d[b,o] = rsqrt(sum_{i,k} (scale*W*s)^2 + 1e-8) (gm.py:287-289) as a (B,IC)x(IC,OC) product"""
+        w = self.weight[0] * self.scale
+        return torch.rsqrt(ops._Gemm.apply(s * s, w.pow(2).sum((2, 3)), False, True, 1.0) + 1e-8)
+
+    def fused(self, input, style, noise=None, noise_w=None, bias=None, slope=1.0, gain=1.0, transpose=False):
+        """The layer through `ops.mod_conv` (first-order passes only, ops.first_order): weight path, convolution and
+        epilogue in two kernels.  transpose=True: the stride-2 transposed convolution of the upsampling layer
+        (gm.py:301-306) WITHOUT its blur (the caller fuses that with the epilogue); then no epilogue here.
+        Returns (y, d): d is None unless the demodulation is still to be applied by the caller (activation-modulated
+        transposed convolution)."""
+        batch, in_channel, height, width = input.shape
+        s = self.modulation(style)                                            # (B, IC) fp32, gm.py:284
+        k = self.kernel_size
+        geom = dict(flip=True, up=2, pad0=k - 1, out_hw=((height - 1) * 2 + k, (width - 1) * 2 + k)) if transpose \
+            else dict(pad0=self.padding)
+        if self._weight_form(height, width):
+            # per-sample weights with the demodulation folded in (what the reference itself convolves with, gm.py:289)
+            y = ops.mod_conv(input, s, self.weight, None, noise, noise_w, bias, self.scale, self.demodulate, slope=slope,
+                             gain=gain, **geom)
+            return y, None
+        x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
+        d = self.demod_coeff(s) if self.demodulate else None
+        if transpose:
+            return ops.mod_conv(x, None, self.weight, scale=self.scale, **geom), d
+        return ops.mod_conv(x, None, self.weight, d, noise, noise_w, bias, self.scale, slope=slope, gain=gain, **geom), None
+
     # Above this many input channels the upsampling layer is bound by the tensor pipe, not by HBM, and the fused
     # single-pass form (4x the MMA work of the transposed convolution, no (2H+1)^2 intermediate) stops paying.
     FUSE_UP_MAX_IN_CHANNELS = 64
@@ -269,9 +296,14 @@ class StyledConv(nn.Module):                                                  # 
                                      self.activate.bias, 1, 1, 1, out_hw=(input.shape[2], input.shape[3]),
                                      slope=self.activate.negative_slope, gain=self.activate.scale, pack_out=True,
                                      param_weight=shared)
+        if ops.fused_prep() and not conv.upsample:
+            if noise is None:
+                noise = input.new_empty(input.shape[0], 1, input.shape[2], input.shape[3]).normal_()
+            return conv.fused(input, style, noise, self.noise.weight, self.activate.bias, self.activate.negative_slope,
+                              self.activate.scale)[0]
         if conv.upsample:
             # transposed conv -> [blur + demod scale + noise + bias + leaky-ReLU*sqrt(2)] in one pass
-            z, d = conv.raw(input, style, blur=False)
+            z, d = conv.fused(input, style, transpose=True) if ops.fused_prep() else conv.raw(input, style, blur=False)
             oh, ow = input.shape[2] * 2, input.shape[3] * 2
             if noise is None:
                 noise = z.new_empty(z.shape[0], 1, oh, ow).normal_()
@@ -298,8 +330,11 @@ class ToRGB(nn.Module):                                                       # 
         self.bias = nn.Parameter(torch.zeros(1, out_channels, 1, 1))
 
     def forward(self, input, style, skip=None):
-        out = self.conv(input, style)
-        out = out + self.bias.to(out.dtype)
+        if ops.fused_prep():
+            out = self.conv.fused(input, style, bias=self.bias)[0]            # 1x1 modulated conv + bias in one kernel
+        else:
+            out = self.conv(input, style)
+            out = out + self.bias.to(out.dtype)
         if skip is not None:
             out = out + self.upsample(skip)
         return out
@@ -566,6 +601,16 @@ class ConvLayer(nn.Sequential):                                               # 
             mods = mods[1:]
         conv = mods[0]
         stride = conv.stride if stride is None else stride
+        if ops.fused_prep():
+            # weight scaling + layout, convolution, bias + leaky-ReLU and all gradients as single kernels (ops.mod_conv)
+            if len(mods) == 1:
+                bias = None if conv.bias is None else conv.bias * out_scale
+                return ops.mod_conv(x, None, conv.weight, bias=bias, scale=conv.scale * out_scale, down=stride, pad0=conv.padding)
+            act = mods[1]
+            bias = act.bias if isinstance(act, FusedLeakyReLU) else None
+            gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
+            return _plain_if_tiny(ops.mod_conv(x, None, conv.weight, bias=bias, scale=conv.scale, down=stride, pad0=conv.padding,
+                                               slope=act.negative_slope, gain=gain * out_scale))
         if len(mods) == 1:                                   # no activation (ResBlock.skip): scale the weights
             w = (conv.weight * (conv.scale * out_scale)).unsqueeze(0)
             y = ops.conv_gather(x, w, 1, stride, conv.padding, param_weight=True)

@@ -79,6 +79,29 @@ def _param_grads():
     return not _DATA_GRADS_ONLY
 
 
+_FIRST_ORDER = False
+
+
+class first_order:
+    """Context for passes whose backward is FIRST-ORDER ONLY (the plain discriminator / generator steps,
+    generator_trainer.py:407-436, 645-667): layers may then use `mod_conv`, whose weight (de)modulation, convolution,
+    epilogue and all their gradients are single hand-written kernels but whose backward is not itself differentiable.
+    The regularisation steps (R1, path length: `create_graph=True`) stay outside and run the closed op algebra.
+    Without autograd (inference, the generator pass of the discriminator step) the fused ops are used automatically."""
+
+    def __enter__(self):
+        global _FIRST_ORDER
+        self.prev, _FIRST_ORDER = _FIRST_ORDER, True
+
+    def __exit__(self, *exc):
+        global _FIRST_ORDER
+        _FIRST_ORDER = self.prev
+
+
+def fused_prep():
+    return _FIRST_ORDER or not torch.is_grad_enabled()
+
+
 # ---------------------------------------------------------------------------------------------
 # per-(sample, channel) scale and dot product: the differentiable pieces of the epilogue backward
 # ---------------------------------------------------------------------------------------------
@@ -334,6 +357,8 @@ def _kernel_layout(w, dtype):
     """(Bw,OC,IC,KH,KW) parameter layout -> (Bw,KH,KW,OC,IC) K-major operand in `dtype`, contiguous.
     One strided-read / cast / dense-write kernel (`.to(dtype).contiguous()` on the permuted view is two)."""
     v = w.detach().permute(0, 3, 4, 1, 2)
+    if v.dtype == dtype and v.is_contiguous():
+        return v                                               # already a view of a K-major operand
     return torch.empty(v.shape, dtype=dtype, device=w.device).copy_(v)
 
 
@@ -449,6 +474,91 @@ class _ConvEpilogue(Function):
         if need[1] and (not param_weight or _param_grads()):      # skipped only when the caller declared it parameter-only
             gw = _ConvWgrad.apply(x, gconv, up, down, pad0, kh, kw, w.shape[0] > 1, pack_in, pack_out).to(w.dtype)
         return gx, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None, None
+
+
+_ONES = {}
+
+
+def _ones_row(ic, like):
+    key = (ic, like.device)
+    if key not in _ONES:
+        _ONES[key] = torch.ones(1, ic, dtype=torch.float32, device=like.device)
+    return _ONES[key]
+
+
+class _ModConv(Function):
+    """y = gain*lrelu(conv(x, w_eff)*d_ext[b,o] + nw*noise + bias[o]),  w_eff[b] = scale*weight*s[b]*demod[b]
+    -- a whole ModulatedConv2d / StyledConv / ToRGB / ConvLayer with its weight path (gm.py:284-289, 152-160):
+    forward = `modweight_fwd` (per-sample weights straight into the K-major operand, demodulation folded in) + ONE
+    convolution kernel with the fused epilogue; backward = fused epilogue backward, data-gradient convolution on the
+    adjoint operand written by the same forward kernel, weight-gradient convolution, `modweight_bwd` (style and
+    parameter gradients incl. the demodulation terms).  FIRST ORDER ONLY (see `first_order`).
+    s = None: shared weights (EqualConv2d);  demod folds rsqrt(sum w^2) into the weights (weight-modulated form);
+    d_ext: demodulation applied to the OUTPUT instead (activation-modulated form, modules.ModulatedConv2d)."""
+
+    @staticmethod
+    def forward(ctx, x, s, weight, d_ext, noise, noise_w, bias, scale, demod, flip, up, down, pad0, out_h, out_w, slope, gain):
+        oc, ic, kh, kw = weight.shape[-4:]
+        w4 = weight.reshape(oc, ic, kh, kw)
+        sk = s if s is not None else _ones_row(ic, x)
+        has_ep = bias is not None or d_ext is not None or noise is not None or slope != 1.0 or gain != 1.0
+        wk, wkt, d = K.modweight_fwd(w4, sk, scale, demod, flip, x.dtype, want_adjoint=ctx.needs_input_grad[0])
+        bias_k = None if bias is None else bias.reshape(-1)
+        y = K.conv_fwd(_nhwc(x), wk, out_h, out_w, up, down, pad0, bias_k, d_ext, noise, noise_w, slope, gain)
+        ctx.cfg = (scale, demod, flip, up, down, pad0, x.shape[2], x.shape[3], slope, gain, has_ep)
+        ctx.save_for_backward(x, s, weight, d_ext, noise, noise_w, bias, y if has_ep else None, wkt, d)
+        return _nchw(y)
+
+    @staticmethod
+    def backward(ctx, gy):
+        if torch.is_grad_enabled():
+            raise RuntimeError('mod_conv is first-order only: run create_graph=True passes (R1 / path length) outside '
+                               '`ops.first_order()` so that the layers use the closed, twice-differentiable op algebra')
+        x, s, weight, d_ext, noise, noise_w, bias, y, wkt, d = ctx.saved_tensors
+        scale, demod, flip, up, down, pad0, h, wd, slope, gain, has_ep = ctx.cfg
+        need = ctx.needs_input_grad
+        oc, ic, kh, kw = weight.shape[-4:]
+        gx = gs = gw = gd = gnoise = gnw = gb = None
+        gyn = _nhwc(gy)
+        if has_ep:
+            gconv, gd_, gb_, gnw_ = K.epilogue_bwd(gyn, y, d_ext, noise, noise_w if noise is not None else None,
+                                                   None if bias is None else bias.reshape(-1), slope, gain,
+                                                   want_gd=d_ext is not None and need[3], want_gb=bias is not None and need[6],
+                                                   want_gnw=noise is not None and need[5])
+            if gd_ is not None:
+                gd = gd_.to(d_ext.dtype)
+            if gb_ is not None:
+                gb = gb_.reshape(bias.shape).to(bias.dtype)
+            if gnw_ is not None:
+                gnw = gnw_.reshape(noise_w.shape).to(noise_w.dtype)
+            if noise is not None and need[4]:
+                gz = K.bias_act_bwd(gyn, y, None, slope, gain)
+                gnoise = (up32(gz).sum(-1).unsqueeze(1) * up32(noise_w)).to(noise.dtype)
+        else:
+            gconv = gyn
+        if need[0]:
+            gx = _nchw(K.conv_fwd(gconv, wkt, h, wd, down, up, kh - 1 - pad0))
+        if (need[1] and s is not None) or need[2]:
+            gwk = K.conv_wgrad(_nhwc(x), gconv, kh, kw, up, down, pad0, s is not None)
+            sk = s if s is not None else _ones_row(ic, x)
+            gs_, gw_ = K.modweight_bwd(gwk, weight.reshape(oc, ic, kh, kw), sk, d, scale, demod, flip,
+                                       want_gs=need[1] and s is not None, want_gw=need[2])
+            if gs_ is not None:
+                gs = gs_.to(s.dtype)
+            if gw_ is not None:
+                gw = gw_.reshape(weight.shape).to(weight.dtype)
+        return gx, gs, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None, None
+
+
+def mod_conv(x, s, weight, d_ext=None, noise=None, noise_w=None, bias=None, scale=1.0, demod=False, flip=False, up=1, down=1,
+             pad0=0, out_hw=None, slope=1.0, gain=1.0):
+    """See _ModConv.  weight: the parameter, (OC,IC,KH,KW) or (1,OC,IC,KH,KW); s: (B,IC) styles or None."""
+    if out_hw is None:
+        kh, kw = weight.shape[-2:]
+        zh, zw = (x.shape[2] - 1) * up + 1, (x.shape[3] - 1) * up + 1
+        out_hw = ((zh + 2 * pad0 - kh) // down + 1, (zw + 2 * pad0 - kw) // down + 1)
+    return _ModConv.apply(x, s, weight, d_ext, noise, noise_w, bias, float(scale), bool(demod), bool(flip), up, down, pad0,
+                          out_hw[0], out_hw[1], float(slope), float(gain))
 
 
 def _view_hw(x, w, up, down, pad0, pack_in):

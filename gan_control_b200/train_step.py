@@ -26,7 +26,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import kernels as K
-from .ops import data_grads_only, up32
+from .ops import data_grads_only, first_order, up32
 
 
 # ---------------------------------------------------------------------------------------------
@@ -434,13 +434,14 @@ class GanTrainStep:
         self.d_arena.zero_grad()
         with torch.no_grad():
             fake_img, _ = self.g(noise)
-        fake_pred, _ = self.d(fake_img)
-        real_pred, _ = self.d(real_img)
-        d_loss = d_logistic_loss(real_pred, fake_pred)
-        d_loss = d_loss / self.global_batch          # gt.py:656 `d_loss.div_(len(mini_real_img))`, kept
-        self.d_buckets.begin()
-        d_loss.backward()
-        self.d_buckets.finish()
+        with first_order():                          # plain step: no double backward -> fused single-kernel layers
+            fake_pred, _ = self.d(fake_img)
+            real_pred, _ = self.d(real_img)
+            d_loss = d_logistic_loss(real_pred, fake_pred)
+            d_loss = d_loss / self.global_batch      # gt.py:656 `d_loss.div_(len(mini_real_img))`, kept
+            self.d_buckets.begin()
+            d_loss.backward()
+            self.d_buckets.finish()
         self.d_optim.step(grad_scale=1.0 / self.world, buckets=self.d_buckets)
         self.stats['d_loss'] = d_loss.detach()
         return d_loss.detach()
@@ -464,12 +465,13 @@ class GanTrainStep:
         self.requires_grad(self.g, True)
         self.requires_grad(self.d, False)
         self.g_arena.zero_grad()
-        fake_img, _ = self.g(noise)
-        fake_pred, _ = self.d(fake_img)
-        g_loss = g_nonsaturating_loss(fake_pred)
-        self.g_buckets.begin()
-        g_loss.backward()
-        self.g_buckets.finish()
+        with first_order():
+            fake_img, _ = self.g(noise)
+            fake_pred, _ = self.d(fake_img)
+            g_loss = g_nonsaturating_loss(fake_pred)
+            self.g_buckets.begin()
+            g_loss.backward()
+            self.g_buckets.finish()
         self.g_optim.step(ema_decay=self.accum if ema else None, grad_scale=1.0 / self.world, buckets=self.g_buckets)
         self.stats['g_loss'] = g_loss.detach()
         return g_loss.detach()

@@ -174,6 +174,25 @@ int b200gan_conv_wgrad_packed(const void* x, const void* gy, float* gw, int dtyp
                               int kh, int kw, int pad0, int w_per_sample, int pack_x, int pack_gy,
                               void* stream);
 
+/* ---- weight (de)modulation -------------------------------------------------
+ * Replaces the weight path of `ModulatedConv2d.forward` gm.py:284-289 (`scale * weight * style`, `rsqrt(sum w^2 +
+ * 1e-8)`, `weight * demod`: five broadcast / reduction passes over a (B,OC,IC,k,k) tensor) by ONE kernel that writes
+ * the per-sample weights straight into the K-major operand layout of b200gan_conv_fwd:
+ *   wk[b][tap'][o][i] = scale * weight[o][i][tap] * s[b][i] * d[b][o],   d[b][o] = rsqrt(sum_{i,tap} (scale*weight*s)^2 + 1e-8)
+ * (d = 1 when !demodulate; tap' = kh*kw-1-tap when `flip`: the gather form of `conv_transpose2d`, gm.py:301-306).
+ * weight: fp32 [oc][ic][kh][kw] (the parameter); s: fp32 [b][ic] (the modulation EqualLinear's output, gm.py:284);
+ * d (may be NULL): fp32 [b][oc] written; wk: `dtype` [b][kh*kw][oc][ic]; wk_adjoint (may be NULL): `dtype`
+ * [b][kh*kw][ic][oc] with the taps reversed relative to wk = the operand of the data-gradient convolution.  kh*kw <= 9. */
+int b200gan_modweight_fwd(const float* weight, const float* s, float* d, void* wk, void* wk_adjoint, int dtype,
+                          int b, int oc, int ic, int kh, int kw, float scale, int demodulate, int flip, void* stream);
+/* First-order backward of the above given g = dL/dwk (fp32, wk's layout: the output of b200gan_conv_wgrad with
+ * w_per_sample): gs[b][ic] (zero-initialised by the caller, atomic accumulation) and / or gweight[oc][ic][kh][kw]
+ * (written).  d: the forward's output; e: fp32 [b][oc] scratch (demodulation only; written by the style pass and read by
+ * the weight pass, so gweight with demodulation needs gs too). */
+int b200gan_modweight_bwd(const float* g, const float* weight, const float* s, const float* d, float* gs, float* e,
+                          float* gweight, int b, int oc, int ic, int kh, int kw, float scale, int demodulate, int flip,
+                          void* stream);
+
 /* ---- dense layers ------------------------------------------------------------
  * Replaces `EqualLinear.forward` gm.py:189-197 (`F.linear` + bias*lr_mul
  * [+ fused_leaky_relu]):  y[m][n] = act( scale * sum_k x[m][k] w[n][k] + bias[n]*bias_mul )

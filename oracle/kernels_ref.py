@@ -13,6 +13,10 @@ The product never imports this module.
 import torch
 import torch.nn.functional as F
 
+# every `gan_control_b200.kernels` entry point that has a stand-in here (what the CPU tests monkeypatch)
+STAND_INS = ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
+             'gemm_f32', 'adam_ema', 'launch_count', 'modweight_fwd', 'modweight_bwd']
+
 
 def _gather_pad(z, pad0_y, pad0_x, need_h, need_w):
     """zero-extend / crop so that index 0 of the result is z-index -pad0 and the extent is need_*"""
@@ -162,6 +166,33 @@ def conv_wgrad(x, gy, kh, kw, up=1, down=1, pad0=0, per_sample=False, pack_x=Fal
         y = conv_fwd(x.detach(), w, gy.shape[1], gy.shape[2], up, down, pad0)
         gw, = torch.autograd.grad(y, w, gy.detach())
     return gw if x.dtype == torch.float64 else gw.float()
+
+
+def _modweight(weight, s, scale, demodulate, flip):
+    """(B,OC,IC,KH,KW) per-sample weights and d, in the dtype of `weight` (gm.py:284-289)"""
+    w = scale * weight.unsqueeze(0) * s.to(weight.dtype)[:, None, :, None, None]
+    d = None
+    if demodulate:
+        d = torch.rsqrt(w.pow(2).sum((2, 3, 4)) + 1e-8)
+        w = w * d[:, :, None, None, None]
+    if flip:
+        w = w.flip(3, 4)
+    return w, d
+
+
+def modweight_fwd(weight, s, scale, demodulate, flip, dtype, want_adjoint=False):
+    w, d = _modweight(weight.detach(), s.detach(), scale, demodulate, flip)
+    wk = w.permute(0, 3, 4, 1, 2).to(dtype).contiguous()
+    wkt = w.flip(3, 4).transpose(1, 2).permute(0, 3, 4, 1, 2).to(dtype).contiguous() if want_adjoint else None
+    return wk, wkt, d
+
+
+def modweight_bwd(g, weight, s, d, scale, demodulate, flip, want_gs=True, want_gw=True):
+    with torch.enable_grad():
+        wq, sq = weight.detach().clone().requires_grad_(True), s.detach().clone().requires_grad_(True)
+        w, _ = _modweight(wq, sq, scale, demodulate, flip)
+        gw, gs = torch.autograd.grad(w.permute(0, 3, 4, 1, 2), (wq, sq), g.to(w.dtype))
+    return (gs if want_gs else None), (gw if want_gw else None)
 
 
 def linear_fwd(x, w, bias, scale, bias_mul, act):

@@ -36,9 +36,16 @@ if which in packed:
             K.conv_fwd(x, w, h, h, 1, 1, 1, pack_in=pin, pack_out=pout)
     torch.cuda.synchronize()
     sys.exit(0)
+ep = len(sys.argv) > 2 and sys.argv[2] == 'ep'        # as a StyledConv: per-sample weights + demod / noise / bias / lrelu epilogue
+if ep:
+    w = (torch.randn(B, k, k, oc, ic, device=dev) / (k * ic ** 0.5)).to(bf)
+    d, bias = torch.rand(B, oc, device=dev) + 0.5, torch.randn(oc, device=dev)
+    noise, nw = torch.randn(B, oh, oh, device=dev).to(bf), torch.full((1,), 0.1, device=dev)
 for _ in range(2):
     if wgrad:
         K.conv_wgrad(x, gy, k, k, up, down, pad0, False)
+    elif ep:
+        K.conv_fwd(x, w, oh, oh, up, down, pad0, bias, d, noise, nw, 0.2, 2 ** 0.5)
     else:
         K.conv_fwd(x, w, oh, oh, up, down, pad0)
 torch.cuda.synchronize()

@@ -29,7 +29,6 @@ def cpu_kernels(monkeypatch):
     such switch."""
     from gan_control_b200 import kernels
     from oracle import kernels_ref
-    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad',
-                 'linear_fwd', 'gemm_f32', 'adam_ema', 'launch_count']:
+    for name in kernels_ref.STAND_INS:
         monkeypatch.setattr(kernels, name, getattr(kernels_ref, name))
     return kernels_ref

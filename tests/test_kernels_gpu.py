@@ -436,3 +436,35 @@ def test_conv_packed(case):
         close(y_ep, ref_ep, dt, f'packed fwd+epilogue engine {engine}')
         err = float((gw.cpu().double() - gwr).abs().max() / gwr.abs().max())
         assert err < 2e-4, f'packed wgrad engine {engine} rel err {err:.2e}'
+
+
+# ---- weight (de)modulation kernels ------------------------------------------------------------------------------
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('cfg', [
+    # b, oc, ic, k, demod, flip
+    (3, 5, 4, 3, True, False), (2, 32, 32, 3, True, True), (16, 64, 64, 3, True, False), (4, 3, 32, 1, False, False),
+    (1, 64, 32, 3, False, False), (2, 128, 256, 3, True, False), (1, 64, 3, 1, False, False), (2, 40, 24, 3, True, True),
+])
+def test_modweight(cfg, dt):
+    b, oc, ic, k, demod, flip = cfg
+    w = rnd(120, oc, ic, k, k).float()
+    s = (rnd(121, b, ic) * 0.5 + 1.0).float()
+    scale = 1.0 / (ic * k * k) ** 0.5
+    wk, wkt, d = K.modweight_fwd(w.cuda(), s.cuda(), scale, demod, flip, dt, want_adjoint=True)
+    rk, rkt, rd = R.modweight_fwd(w.double(), s.double(), scale, demod, flip, torch.float64, want_adjoint=True)
+    assert wk.dtype == dt and wk.shape == rk.shape and wkt.shape == rkt.shape
+    close(wk, rk, dt, 'wk')
+    close(wkt, rkt, dt, 'wk adjoint')
+    if demod:
+        assert float((d.cpu().double() - rd).abs().max() / rd.abs().max()) < 1e-5
+    else:
+        assert d is None
+    wk2, wkt2, _ = K.modweight_fwd(w.cuda(), s.cuda(), scale, demod, flip, dt, want_adjoint=False)
+    assert wkt2 is None and torch.equal(wk2, wk)
+    g = rnd(122, b, k, k, oc, ic).float()
+    gs, gw = K.modweight_bwd(g.cuda(), w.cuda(), s.cuda(), d, scale, demod, flip)
+    rgs, rgw = R.modweight_bwd(g.double(), w.double(), s.double(), rd, scale, demod, flip)
+    assert float((gs.cpu().double() - rgs).abs().max() / rgs.abs().max()) < 2e-5, 'gs'
+    assert float((gw.cpu().double() - rgw).abs().max() / rgw.abs().max()) < 2e-5, 'gweight'
+    gs2, gw2 = K.modweight_bwd(g.cuda(), w.cuda(), s.cuda(), d, scale, demod, flip, want_gs=False, want_gw=True)
+    assert gs2 is None and float((gw2 - gw).abs().max()) <= 1e-6 * float(gw.abs().max())

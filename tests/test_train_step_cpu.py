@@ -156,8 +156,7 @@ def _worker(rank, world, port, out):
     torch.set_num_threads(2)
     from gan_control_b200 import kernels
     from oracle import kernels_ref
-    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
-                 'gemm_f32', 'adam_ema', 'launch_count']:
+    for name in kernels_ref.STAND_INS:
         setattr(kernels, name, getattr(kernels_ref, name))
     real, zs, pl_noise = make_inputs(4 * world)
     g, d, g_ema = product_run(4, real, zs, pl_noise, [0, 1], world=world, rank=rank)
@@ -260,8 +259,7 @@ def _worker_mixing(rank, world, port, out):
     torch.set_num_threads(2)
     from gan_control_b200 import kernels
     from oracle import kernels_ref
-    for name in ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
-                 'gemm_f32', 'adam_ema', 'launch_count']:
+    for name in kernels_ref.STAND_INS:
         setattr(kernels, name, getattr(kernels_ref, name))
     g, g_ema, d = build(4)
     step = GanTrainStep(g, d, g_ema, batch=4, latent_size=SDIM, world_size=world, bucket_mb=0.05, mixing=0.9)
