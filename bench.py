@@ -371,6 +371,10 @@ def gpu_library_baseline(torch, size, batch, dev, log):
     return out
 
 
+# configs/metfaces.json `sub_groups_dict` (place_in_latent) and configs/afhq.json (192 / 192 / 128)
+METFACES_GROUPS = {'id': {'place_in_latent': [0, 128]}, 'expression': {'place_in_latent': [128, 192]},
+                   'orientation': {'place_in_latent': [192, 256]}, 'age': {'place_in_latent': [256, 320]},
+                   'style': {'place_in_latent': [320, 448]}, 'other': {'place_in_latent': [448, 512]}}
 AFHQ_GROUPS = {'a': {'place_in_latent': [0, 192]}, 'b': {'place_in_latent': [192, 384]}, 'c': {'place_in_latent': [384, 512]}}
 
 
@@ -402,6 +406,8 @@ def run_b200(args):
         # the per-GPU workloads of the other BASELINE.json configurations, same run, same timing method
         for name, kw in (
                 ('configs[2]: FFHQ-1024 DDP, 4 images / GPU, R1 + path-length at cadence', dict(size=1024, batch=4)),
+                ('configs[3]: MetFaces-1024 layout (split-FC 128/64/64/64/128/64, r1 2), style mixing 0.9 drawn on the device '
+                 'and captured in the CUDA graphs, 4 images / GPU', dict(size=1024, batch=4, fc_groups=METFACES_GROUPS, r1=2.0, mixing=0.9)),
                 ('configs[4]: AFHQ-512 layout (split-FC 192/192/128, r1 0.5, lr 0.0025), 8 images / GPU',
                  dict(size=512, batch=8, fc_groups=AFHQ_GROUPS, r1=0.5, lr=0.0025))):
             m = measure(torch, dist, args, dev, rank, world, steps=16, warmup=2, with_e2e=False, **kw)

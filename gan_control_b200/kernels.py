@@ -26,6 +26,10 @@ class FcLayer(ctypes.Structure):
                 ('out_off', _i), ('scale', _f), ('bias_mul', _f)]
 
 
+class FcLayerGrad(ctypes.Structure):
+    _fields_ = [('gw', _vp), ('gb', _vp)]
+
+
 _SIGNATURES = {
     'b200gan_version': ([], _i),
     'b200gan_last_error': ([], _c.c_char_p),
@@ -48,6 +52,7 @@ _SIGNATURES = {
     'b200gan_linear_fwd': ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _i, _vp], _i),
     'b200gan_gemm_f32': ([_vp, _vp, _vp] + [_i] * 8 + [_f, _f, _vp], _i),
     'b200gan_mapping_fwd': ([_vp, _vp, _vp] + [_i] * 6 + [_vp], _i),
+    'b200gan_mapping_bwd': ([_vp] * 6 + [_i] * 6 + [_vp], _i),
     'b200gan_adam_ema': ([_vp, _vp, _vp, _vp, _vp, _i64] + [_f] * 4 + [_vp, _f, _f, _vp], _i),
 }
 
@@ -398,6 +403,24 @@ def mapping_fwd(z, layer_table, n_groups, n_layers, row_width, normalize):
             _check(lib().b200gan_mapping_fwd(_ptr(z), _ptr(acts), _ptr(layer_table), n_groups, n_layers, batch, z_dim,
                                              row_width, int(normalize), _stream()), 'mapping_fwd')
     return acts
+
+
+def mapping_bwd(z, acts, g_out, layer_table, grad_table, n_groups, n_layers, row_width, normalize, want_dz=False):
+    """Backward of mapping_fwd in one cooperative kernel.  g_out (B, out_width) = dL/d(acts[n_layers][:, :out_width]); the
+    parameter gradients are WRITTEN where `grad_table` (uint8 CUDA tensor of n_layers*n_groups FcLayerGrad) points.
+    Returns dz (B, z_dim) or None."""
+    _cuda(z, acts, g_out, layer_table, grad_table)
+    z = _f32c(z)
+    batch, z_dim = z.shape
+    gbuf = torch.zeros((2, batch, row_width), dtype=torch.float32, device=z.device)
+    gbuf[0, :, :g_out.shape[1]] = g_out
+    dz = torch.empty_like(z) if want_dz else None
+    if batch:
+        with torch.cuda.device(z.device):
+            _check(lib().b200gan_mapping_bwd(_ptr(z), _ptr(acts), _ptr(gbuf), _ptr(layer_table), _ptr(grad_table), _ptr(dz),
+                                             n_groups, n_layers, batch, z_dim, row_width, int(normalize), _stream()),
+                   'mapping_bwd')
+    return dz
 
 
 def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, bias_corr, ema_decay=0.0, grad_scale=1.0):

@@ -489,10 +489,12 @@ class Generator(nn.Module):                                                   # 
         return [(0, self.style_dim, [m for m in self.style if isinstance(m, EqualLinear)])]
 
     def map_styles(self, z):
-        """z -> w.  Without autograd (inference, the discriminator step's generator pass) the whole mapping
-        network is ONE persistent kernel; with autograd the per-layer differentiable path runs."""
-        if z.is_cuda and z.ndim == 2 and not torch.is_grad_enabled() and z.dtype == torch.float32:
-            return ops.mapping_forward(_cached_fc_table(self, self._mapping_groups, z.device), z.contiguous(), normalize=True)
+        """z -> w: the whole mapping network is ONE persistent kernel (and one more for its backward, ops._MappingFn)"""
+        if z.is_cuda and z.ndim == 2 and z.dtype == torch.float32:
+            tbl = _cached_fc_table(self, self._mapping_groups, z.device)
+            if not torch.is_grad_enabled():
+                return ops.mapping_forward(tbl, z.contiguous(), normalize=True)
+            return ops.mapping_apply(tbl, z.contiguous(), normalize=True)
         return self.style(z)
 
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
@@ -719,7 +721,9 @@ class FcStack(nn.Module):                                    # models/controller
         self.fc_stack = nn.Sequential(*layers)
 
     def forward(self, x):
-        if x.is_cuda and x.ndim == 2 and not torch.is_grad_enabled() and x.dtype == torch.float32:
+        if x.is_cuda and x.ndim == 2 and x.dtype == torch.float32:
             tbl = _cached_fc_table(self, lambda: [(0, self.in_dim, list(self.fc_stack))], x.device)
-            return ops.mapping_forward(tbl, x.contiguous(), normalize=False)
+            if not torch.is_grad_enabled():
+                return ops.mapping_forward(tbl, x.contiguous(), normalize=False)
+            return ops.mapping_apply(tbl, x.contiguous(), normalize=False)
         return self.fc_stack(x)

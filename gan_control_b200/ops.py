@@ -730,6 +730,7 @@ def build_fc_table(groups, device):
     assert n_layers >= 1 and all(len(g[2]) == n_layers for g in groups)
     table = (K.FcLayer * (n_groups * n_layers))()
     keep, row_width, out_width, in_offs = [], 0, 0, None
+    keep_params, scales = [], []
     for l in range(n_layers):
         off = 0
         for gi, (lo, hi, layers) in enumerate(groups):
@@ -737,6 +738,8 @@ def build_fc_table(groups, device):
             w, b = lin.weight.detach(), lin.bias.detach()
             assert w.is_contiguous() and b.is_contiguous() and w.dtype == torch.float32
             keep += [w, b]
+            keep_params += [lin.weight, lin.bias]
+            scales.append((float(lin.scale), float(lin.lr_mul)))
             e = table[l * n_groups + gi]
             e.w, e.bias = w.data_ptr(), b.data_ptr()
             e.in_dim, e.out_dim = w.shape[1], w.shape[0]
@@ -750,10 +753,91 @@ def build_fc_table(groups, device):
         in_offs = [table[l * n_groups + gi].out_off for gi in range(n_groups)]
     raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(device)
     return {'table': raw, 'n_groups': n_groups, 'n_layers': n_layers, 'row_width': row_width, 'out_width': out_width,
-            'key': tuple(t.data_ptr() for t in keep), 'keep': keep}
+            'key': tuple(t.data_ptr() for t in keep), 'keep': keep, 'keep_params': keep_params,
+            'geom': {'n_layers': n_layers, 'slices': [(lo, hi) for lo, hi, _ in groups], 'scales': scales}}
 
 
 def mapping_forward(tbl, z, normalize=True):
     """Whole mapping network / MultiFcStack / FcStack forward in ONE cooperative kernel (no autograd)."""
     acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize)
     return acts[tbl['n_layers'], :, :tbl['out_width']]
+
+
+def _grad_table(tbl, device):
+    """flat gradient buffer for every weight / bias of the table + the device array of pointers into it (built once per
+    table: a CUDA-graph capture must not contain its H2D copy)"""
+    if 'grad_table' not in tbl:
+        params = tbl['keep']                                   # [w, b, w, b, ...] in table (layer-major) order
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=device)
+        gt = (K.FcLayerGrad * (len(params) // 2))()
+        views, off = [], 0
+        for j in range(0, len(params), 2):
+            w, b = params[j], params[j + 1]
+            gt[j // 2].gw = flat.data_ptr() + 4 * off
+            views.append((off, w.shape))
+            off += w.numel()
+            gt[j // 2].gb = flat.data_ptr() + 4 * off
+            views.append((off, b.shape))
+            off += b.numel()
+        tbl['grad_flat'], tbl['grad_views'] = flat, views
+        tbl['grad_table'] = torch.frombuffer(bytearray(bytes(gt)), dtype=torch.uint8).to(device)
+    return tbl['grad_table']
+
+
+def _mapping_reference(z, params, geom, normalize):
+    """the same network with the differentiable per-layer ops (used only for a create_graph backward)"""
+    outs, j = [], 0
+    n_layers = geom['n_layers']
+    cols = []
+    for gi, (lo, hi) in enumerate(geom['slices']):
+        x = z[:, lo:hi]
+        if normalize:
+            x = x * torch.rsqrt(torch.mean(x * x, dim=1, keepdim=True) + 1e-8)
+        cols.append(x)
+    for l in range(n_layers):
+        for gi in range(len(cols)):
+            w, b = params[2 * (l * len(cols) + gi)], params[2 * (l * len(cols) + gi) + 1]
+            scale, lr_mul = geom['scales'][l * len(cols) + gi]
+            cols[gi] = equal_linear(cols[gi], w, b, scale, lr_mul, True)
+    return torch.cat(cols, dim=1)
+
+
+class _MappingFn(Function):
+    """z -> w through `b200gan_mapping_fwd`, gradients through `b200gan_mapping_bwd`: the whole mapping network
+    (gm.py:633-642), split-FC MultiFcStack (gm.py:489-502) or controller FcStack is one kernel each way under autograd
+    (the per-layer path costs 8..56 launches forward and ~6 per layer backward)."""
+
+    @staticmethod
+    def forward(ctx, z, tbl, normalize, *params):
+        acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize)
+        ctx.tbl, ctx.normalize = tbl, normalize
+        ctx.save_for_backward(z, acts, *params)
+        return acts[tbl['n_layers'], :, :tbl['out_width']].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        z, acts, *params = ctx.saved_tensors
+        tbl, normalize = ctx.tbl, ctx.normalize
+        need_z = ctx.needs_input_grad[0]
+        if torch.is_grad_enabled():
+            # double backward: recompute with the closed op algebra (never hit by the training steps: the path-length
+            # regulariser differentiates w.r.t. the latents, i.e. ABOVE the mapping network)
+            with torch.enable_grad():
+                w = _mapping_reference(z, params, tbl['geom'], normalize)
+                ins = [t for t in [z] + list(params) if t.requires_grad]
+                grads = iter(torch.autograd.grad(w, ins, g, create_graph=True, allow_unused=True))
+            return tuple([next(grads) if z.requires_grad else None, None, None] +
+                         [next(grads) if p.requires_grad else None for p in params])
+        gt = _grad_table(tbl, z.device)
+        dz = K.mapping_bwd(z, acts, g.contiguous().float(), tbl['table'], gt, tbl['n_groups'], tbl['n_layers'], tbl['row_width'],
+                           normalize, want_dz=need_z)
+        flat = tbl['grad_flat'].clone()        # the shared buffer is overwritten by the next backward of this table
+        outs = []
+        for i, (off, shape) in enumerate(tbl['grad_views']):
+            outs.append(flat[off:off + math.prod(shape)].view(shape) if ctx.needs_input_grad[3 + i] else None)
+        return (dz, None, None) + tuple(outs)
+
+
+def mapping_apply(tbl, z, normalize=True):
+    """differentiable `mapping_forward`"""
+    return _MappingFn.apply(z, tbl, normalize, *tbl['keep_params'])

@@ -420,6 +420,27 @@ class GanTrainStep:
             return list(torch.randn(2, batch, self.latent_size, device=self.device).unbind(0))
         return [torch.randn(batch, self.latent_size, device=self.device)]
 
+    def _styles(self, batch, noise=None):
+        """What the generator is called with: (styles, kwargs).  Explicit `noise` (a list of z, tests) is passed through.
+        Otherwise style mixing (tu:19-23 + gm.py:762-769) is drawn ON THE DEVICE: both latents are always mapped, the
+        mixing coin and the crossover index are device scalars and every layer selects its latent with a mask -- the same
+        distribution as the reference's host-side `random.random() < mixing` / `random.randint(1, n_latent - 1)`, but
+        with a fixed launch sequence, so the step can be captured in a CUDA graph and every rank issues the same
+        kernels / collectives whatever it draws."""
+        if noise is not None:
+            return noise, {}
+        dtype = self.mean_path_length.dtype                    # fp32 (fp64 only in the CPU algebra tests)
+        if self.mixing <= 0:
+            return [torch.randn(batch, self.latent_size, device=self.device, dtype=dtype)], {}
+        z = torch.randn(2, batch, self.latent_size, device=self.device, dtype=dtype)
+        w1, w2 = self.g.map_styles(z[0]), self.g.map_styles(z[1])
+        n = self.g.n_latent
+        mix = torch.rand((), device=self.device) < self.mixing
+        index = torch.randint(1, n, (), device=self.device)                           # uniform on 1 .. n_latent - 1
+        first = (torch.arange(n, device=self.device) < index) | ~mix
+        latent = torch.where(first.view(1, n, 1), w1.unsqueeze(1), w2.unsqueeze(1))
+        return [latent], {'input_is_latent': True}
+
     def _mean_over_ranks(self, t):
         if self.world > 1:
             t = t.clone()
@@ -428,12 +449,13 @@ class GanTrainStep:
         return t
 
     # -- discriminator ------------------------------------------------------------------------
-    def discriminator_step(self, real_img, noise):
+    def discriminator_step(self, real_img, noise=None):
         self.requires_grad(self.g, False)
         self.requires_grad(self.d, True)
         self.d_arena.zero_grad()
         with torch.no_grad():
-            fake_img, _ = self.g(noise)
+            styles, kw = self._styles(self.batch, noise)
+            fake_img, _ = self.g(styles, **kw)
         with first_order():                          # plain step: no double backward -> fused single-kernel layers
             fake_pred, _ = self.d(fake_img)
             real_pred, _ = self.d(real_img)
@@ -461,12 +483,13 @@ class GanTrainStep:
         return r1_loss.detach()
 
     # -- generator ----------------------------------------------------------------------------
-    def generator_step(self, noise, ema=True):
+    def generator_step(self, noise=None, ema=True):
         self.requires_grad(self.g, True)
         self.requires_grad(self.d, False)
         self.g_arena.zero_grad()
         with first_order():
-            fake_img, _ = self.g(noise)
+            styles, kw = self._styles(self.batch, noise)
+            fake_img, _ = self.g(styles, **kw)
             fake_pred, _ = self.d(fake_img)
             g_loss = g_nonsaturating_loss(fake_pred)
             self.g_buckets.begin()
@@ -481,9 +504,8 @@ class GanTrainStep:
         self.requires_grad(self.d, False)
         self.g_arena.zero_grad()
         path_batch = max(1, self.batch // self.path_batch_shrink)
-        if noise is None:
-            noise = self.mixing_noise(path_batch)
-        fake_img, latents = self.g(noise, return_latents=True)
+        styles, kw = self._styles(path_batch, noise)
+        fake_img, latents = self.g(styles, return_latents=True, **kw)
         path_loss, new_mean, path_lengths = g_path_regularize(
             fake_img, latents, self.mean_path_length, pl_noise=pl_noise,
             all_reduce_mean=self._mean_over_ranks if self.world > 1 else None)
@@ -544,13 +566,11 @@ class GanTrainStep:
 
     # -- one iteration (gt.py:343-353: discriminator_update, generator_update) ------------------------
     def train_step(self, i, real_img, regularize=True):
-        noise = self.mixing_noise(self.batch)
-        d_loss = self.discriminator_step(real_img, noise)
+        d_loss = self.discriminator_step(real_img)
         if regularize and i % self.d_reg_every == 0:
             self.discriminator_regularize_step(real_img)
-        noise = self.mixing_noise(self.batch)
         do_g_reg = regularize and i % self.g_reg_every == 0
-        g_loss = self.generator_step(noise, ema=not do_g_reg)
+        g_loss = self.generator_step(ema=not do_g_reg)
         if do_g_reg:
             self.generator_regularize_step()
             # accumulate() runs once per iteration after both G updates (gt.py:362-369)
@@ -563,9 +583,7 @@ class GanTrainStep:
     #    four step variants are captured once and replayed --------------------------------------------
     def capture(self, real_shape, warmup=2):
         """Capture discriminator_step / generator_step (+ their regularised variants) into CUDA graphs
-        reading from a static image buffer.  Requires mixing == 0 (style mixing draws host-side
-        randomness per step, tu:19-23)."""
-        assert self.mixing == 0, 'graph capture needs mixing=0 (host-side random control flow)'
+        reading from a static image buffer.  Style mixing is drawn on the device (`_styles`), so it is captured too."""
         self.static_real = torch.zeros(real_shape, device=self.device)
         snapshot = self._snapshot()          # the warm-up runs are real optimiser steps on a dummy batch: undone below
         side = torch.cuda.Stream()
@@ -618,13 +636,13 @@ class GanTrainStep:
 
     def _variant(self, name):
         if name == 'd':
-            self.discriminator_step(self.static_real, self.mixing_noise(self.batch))
+            self.discriminator_step(self.static_real)
         elif name == 'd_reg':
             self.discriminator_regularize_step(self.static_real)
         elif name == 'g':
-            self.generator_step(self.mixing_noise(self.batch), ema=True)
+            self.generator_step(ema=True)
         else:   # generator step without EMA, path-length step, then the iteration's single EMA update
-            self.generator_step(self.mixing_noise(self.batch), ema=False)
+            self.generator_step(ema=False)
             self.generator_regularize_step()
             if self.ema_arena is not None:
                 self.ema_arena.data.mul_(self.accum).add_(self.g_arena.data, alpha=1 - self.accum)

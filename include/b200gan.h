@@ -226,6 +226,17 @@ typedef struct {
 int b200gan_mapping_fwd(const float* z, float* acts, const b200gan_fc_layer* layers,
                         int n_groups, int n_layers, int batch, int z_dim, int row_width,
                         int normalize, void* stream);
+/* First-order backward of the whole mapping network in one cooperative kernel (autograd through gm.py:633-642 / 489-502
+ * issues ~6 launches per EqualLinear).  acts: the forward's buffer.  gbuf: fp32 scratch [2][batch][row_width]; the caller
+ * stores dL/d(acts[n_layers]) in gbuf[0] (it is overwritten).  grads: DEVICE array parallel to `layers` naming where each
+ * layer's weight / bias gradient is WRITTEN (NULL = skip).  dz (may be NULL): [batch][z_dim] gradient of the input. */
+typedef struct {
+    float* gw;           /* [out_dim][in_dim] */
+    float* gb;           /* [out_dim] */
+} b200gan_fc_layer_grad;
+int b200gan_mapping_bwd(const float* z, const float* acts, float* gbuf, const b200gan_fc_layer* layers,
+                        const b200gan_fc_layer_grad* grads, float* dz, int n_groups, int n_layers, int batch,
+                        int z_dim, int row_width, int normalize, void* stream);
 
 /* ---- optimiser ------------------------------------------------------------------
  * Adam step as `torch.optim.Adam` (gt.py:161-173; eps added after the bias-corrected sqrt) fused with

@@ -459,3 +459,83 @@ def test_fused_first_order_path_matches_op_algebra(dt):
     worst = max((rel_err(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0)
     print(f'fused vs op algebra ({dt}): image {rel_err(i1, i0):.2e}, worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})')
     assert worst[0] < tol_g, worst
+
+
+def test_mapping_network_under_autograd():
+    """`ops._MappingFn` (one cooperative kernel forward, one backward) against the per-layer path: w, dL/dz and every
+    parameter gradient for the vanilla stack, the split-FC MultiFcStack and the controller FcStack; then a double
+    backward through it (recomputed with the op algebra)."""
+    fx = Fixture('networks')
+    for name, fcg in [('g16', None), ('g16split', GROUPS)]:
+        size, sdim, n_mlp, seed = [int(v) for v in fx.np(name + '.cfg')]
+        g = M.Generator(size, sdim, n_mlp, channel_multiplier=2, conv_transpose=True, split_fc=fcg is not None,
+                        fc_config=_fc_config(fcg) if fcg else None)
+        g.load_state_dict(P.seeded_state_dict(P.generator_shapes(size, sdim, n_mlp, 2, fcg), seed))
+        g.to(DEV)
+        params = [p for p in g.style.parameters()]
+        gout = rnd(seed + 7, 5, sdim).to(DEV)
+        res = []
+        for fast in (True, False):
+            z = rnd(seed * 10 + 3, 5, sdim).to(DEV).requires_grad_(True)
+            w = g.map_styles(z) if fast else g.style(z)
+            grads = torch.autograd.grad(w, [z] + params, gout)
+            res.append((w.detach(), grads))
+        (w1, g1), (w0, g0) = res
+        assert max_rel(w1, w0) < 1e-5
+        worst = max(max_rel(a, b) for a, b in zip(g1, g0))
+        print(f'{name}: mapping kernel under autograd, worst gradient max-rel err {worst:.2e}')
+        assert worst < 1e-4
+        # double backward (create_graph): d/dparams of |dw/dz . gout|^2
+        z = rnd(seed * 10 + 4, 3, sdim).to(DEV).requires_grad_(True)
+        outs = []
+        for fast in (True, False):
+            w = g.map_styles(z) if fast else g.style(z)
+            gz, = torch.autograd.grad(w, z, gout[:3], create_graph=True)
+            outs.append(torch.autograd.grad(gz.pow(2).sum(), params[0])[0])
+        assert max_rel(outs[0], outs[1]) < 1e-4
+    fxs = Fixture('fcstack')
+    n_mlp, din, mid, dout, seed = [int(v) for v in fxs.np('cfg')]
+    m = M.FcStack(0.01, n_mlp, din, mid, dout)
+    m.load_state_dict(P.seeded_state_dict(P.fc_stack_shapes(n_mlp, din, mid, dout), seed))
+    m.to(DEV)
+    x = fxs.t('x', torch.float32, DEV).requires_grad_(True)
+    gy = rnd(5, *fxs.t('y').shape).to(DEV)
+    ga = torch.autograd.grad(m(x), [x] + list(m.parameters()), gy)
+    gb = torch.autograd.grad(m.fc_stack(x), [x] + list(m.parameters()), gy)
+    assert max(max_rel(a, b) for a, b in zip(ga, gb)) < 1e-4
+
+
+def test_generator_step_launch_count_drops_with_the_mapping_kernel():
+    """the G pass that trains the mapping network runs it as 2 kernels instead of ~6 launches per EqualLinear"""
+    from gan_control_b200 import kernels as K
+    torch.manual_seed(0)
+    g = M.Generator(16, 512, 8, channel_multiplier=2, conv_transpose=True).to(DEV)
+    z = torch.randn(4, 512, device=DEV)
+    counts = []
+    for fast in (True, False):
+        n0 = K.launch_count()
+        w = g.map_styles(z) if fast else g.style(z)
+        w.sum().backward()
+        counts.append(K.launch_count() - n0)
+    print('libb200gan launches for mapping fwd+bwd: kernel path', counts[0], 'per-layer path', counts[1])
+    assert counts[0] <= 2 and counts[1] - counts[0] >= 25     # (library launches only; the per-layer path adds torch kernels on top)
+
+
+def test_style_mixing_is_captured_in_cuda_graphs():
+    """BASELINE.json configs[3] (style mixing 0.9): the mixing coin / crossover index are device-side draws, so the four
+    step variants capture and replay; replays draw fresh mixing decisions (losses differ) and train (parameters move)."""
+    from gan_control_b200.train_step import GanTrainStep
+    import copy
+    torch.manual_seed(11)
+    groups = {'a': {'place_in_latent': [0, 32]}, 'b': {'place_in_latent': [32, 64]}}
+    fc = M.FcConfig.from_sub_groups_dict(groups)
+    g = M.Generator(16, 64, 3, channel_multiplier=2, conv_transpose=True, act_dtype=torch.bfloat16, split_fc=True, fc_config=fc).to(DEV)
+    d = M.Discriminator(16, channel_multiplier=2, act_dtype=torch.bfloat16).to(DEV)
+    step = GanTrainStep(g, d, copy.deepcopy(g), batch=4, latent_size=64, mixing=0.9, r1=2.0)
+    real = torch.randn(4, 3, 16, 16, device=DEV).clamp_(-1, 1)
+    step.capture(tuple(real.shape), warmup=1)
+    p0 = step.g_arena.data.clone()
+    losses = [tuple(float(v) for v in step.train_step_graphed(i, real)) for i in (0, 1, 2, 3, 4)]
+    torch.cuda.synchronize()
+    assert all(np.isfinite(v) for pair in losses for v in pair) and len({round(p[1], 6) for p in losses}) > 1
+    assert torch.isfinite(step.g_arena.data).all() and float((step.g_arena.data - p0).abs().max()) > 0

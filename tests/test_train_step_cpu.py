@@ -285,3 +285,23 @@ def test_two_replicas_with_style_mixing_stay_in_sync(cpu_kernels, tmp_path):
     for net in ('g', 'd'):
         for k in a[net]:
             assert torch.equal(a[net][k], b[net][k]), (net, k)
+
+
+@pytest.mark.parametrize('mixing,seed', [(1.0, 3), (1.0, 4), (0.5, 5), (0.5, 6), (0.5, 7)])
+def test_device_side_style_mixing_equals_reference_mixing(cpu_kernels, mixing, seed):
+    """`GanTrainStep._styles` draws the mixing coin and the crossover index as device scalars and selects per layer with a
+    mask (so the step is CUDA-graph capturable): the image equals `Generator([z1, z2], inject_index=index)` resp.
+    `Generator([z1])` (gm.py:754-769, tu:19-23) for the same draws."""
+    g, g_ema, d = build(4)
+    step = GanTrainStep(g, d, g_ema, batch=4, latent_size=SDIM, mixing=mixing)
+    torch.manual_seed(seed)
+    styles, kw = step._styles(4)
+    torch.manual_seed(seed)
+    z = torch.randn(2, 4, SDIM, dtype=F64)
+    mix = bool(torch.rand(()) < mixing)
+    index = int(torch.randint(1, g.n_latent, ()))
+    assert kw == {'input_is_latent': True} and styles[0].shape == (4, g.n_latent, SDIM)
+    img, _ = g(styles, **kw)
+    ref, _ = g([z[0], z[1]], inject_index=index) if mix else g([z[0]])
+    assert float((img - ref).abs().max()) < 1e-12
+    assert 1 <= index <= g.n_latent - 1
