@@ -46,6 +46,9 @@ def parse():
     ap.add_argument('--skip-library-baseline', action='store_true', help='no cuDNN/cuBLAS comparator (gpu_library_baseline)')
     ap.add_argument('--skip-extra', action='store_true', help='no extra_configs (BASELINE.json configs[2..4] per-GPU workloads)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
+    ap.add_argument('--config', type=int, default=1, choices=[1, 5],
+                    help='1: the train-step metric (default).  5: BASELINE.json configs[4] inference half -- controller '
+                         'FcStack sweep over the 1000 control vectors + gen_batch_by_controls at 512x512')
     ap.add_argument('--ncu-range', action='store_true',
                     help='bracket the timed region with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)')
     return ap.parse_args()
@@ -474,9 +477,65 @@ def _finish(world):
         os._exit(0)
 
 
+def run_config5(args):
+    """BASELINE.json configs[4], inference half: AFHQ layout (3 groups 192/192/128, split-FC mapping) at 512^2, controller
+    FcStack(lr_mlp=0.01, n_mlp=4, in_dim=3, mid_dim=512, out_dim=192) (configs/controller_configs/afhq/
+    default_w_latent_controller.json) swept over the 1000 `orientation` control vectors of the reference's fixture
+    resources/ffhq_1K_attributes_samples_df.pkl (committed as tests/golden/config5_controls.npz), its `latents_w` as the
+    base w.  Two numbers: latents/s of the controller alone, images/s of `gen_batch_by_controls` (CUDA-graphed synthesis)."""
+    import numpy as np
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    from gan_control_b200 import modules as M
+    from gan_control_b200.inference import Controller
+    groups = {'id': {'place_in_latent': [0, 192]}, 'orientation': {'place_in_latent': [192, 384]}, 'other': {'place_in_latent': [384, 512]}}
+    fx = np.load(os.path.join(ROOT, 'tests', 'golden', 'config5_controls.npz'))
+    ori = torch.from_numpy(fx['orientation']).cuda()
+    w_base = torch.from_numpy(fx['latents_w'].astype(np.float32)).cuda()
+    torch.manual_seed(0)
+    g = M.Generator(512, 512, 8, channel_multiplier=2, conv_transpose=True, split_fc=True,
+                    fc_config=M.FcConfig.from_sub_groups_dict(groups), act_dtype=torch.bfloat16)
+    out = {}
+    for graphs in (True, False):
+        c = Controller(generator=g, sub_groups_dict=groups, fc_controls={'orientation': M.FcStack(0.01, 4, 3, 512, 192)},
+                       cuda_graphs=graphs)
+        bs = 50
+
+        def sweep():
+            for i in range(0, 1000, bs):
+                c.gen_batch_by_controls(latent=w_base[i:i + bs], input_is_latent=True, normalize=False, orientation=ori[i:i + bs])
+
+        def timed(fn, reps):
+            for _ in range(max(3, args.warmup)):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        with torch.no_grad():
+            ms_ctl = timed(lambda: c.fc_controls['orientation'](ori), 20)
+            ms_gen = timed(sweep, max(1, args.steps // 8))
+        out['cuda_graphs' if graphs else 'eager'] = {'controller_latents_per_s': 1000 / ms_ctl * 1e3,
+                                                     'gen_batch_by_controls_images_per_s': 1000 / ms_gen * 1e3,
+                                                     'ms_per_1000_images': ms_gen}
+    best = out['cuda_graphs']
+    print(json.dumps({'metric': 'images/sec gen_batch_by_controls 512x512 over the 1K control vectors (BASELINE.json configs[4])',
+                      'value': best['gen_batch_by_controls_images_per_s'], 'unit': UNIT, 'n_gpus': 1, 'higher_is_better': True,
+                      'dtype': 'bf16', 'data': 'reference fixture ffhq_1K_attributes_samples_df.pkl (orientation, latents_w); '
+                      'random-init weights', 'config': {'workload': 'configs[4] controller EqualLinear inference sweep (1K latents), '
+                                                                    'batches of 50'}, 'detail': out}), flush=True)
+
+
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.config == 5 and a.impl != 'reference':
+        run_config5(a)
+    elif a.impl == 'reference':
         run_reference(a)
     else:
         run_b200(a)

@@ -17,26 +17,26 @@ struct ConvGeom {
     int pack_in = 0, pack_out = 0;
 };
 
-int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
-                  const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
-                  cudaStream_t st);
+// the epilogue of every forward engine (include/b200gan.h b200gan_conv_epilogue)
+typedef b200gan_conv_epilogue ConvEp;
+static inline bool ep_active(const ConvEp& e) {
+    return e.bias || e.rowscale || e.noise || e.addend || e.gate || e.slope != 1.f || e.gain != 1.f;
+}
+
+int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const ConvEp& ep, cudaStream_t st);
 // streaming 1x1 kernels for a <= 4-channel side (conv_pointwise.cu)
 bool conv_fwd_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y);
-int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
-                       const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
-                       cudaStream_t st);
+int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const ConvEp& ep, cudaStream_t st);
 bool conv_wgrad_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy);
 int conv_wgrad_pointwise(const void* x, const void* gy, float* gw, int dtype, const ConvGeom& g, cudaStream_t st);
 // tcgen05 engine (conv_umma.cu)
 bool conv_fwd_umma_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y);
-int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias, const float* rowscale,
-                  const void* noise, const float* noise_w, float slope, float gain, cudaStream_t st);
+int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, const ConvEp& ep, cudaStream_t st);
 bool conv_wgrad_umma_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy);
 int conv_wgrad_umma(const void* x, const void* gy, float* gw, const ConvGeom& g, cudaStream_t st);
 // halo-reuse variant for <= 64-channel stride-1 layers (conv_umma_halo.cu)
 bool conv_fwd_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y);
-int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias, const float* rowscale,
-                  const void* noise, const float* noise_w, float slope, float gain, cudaStream_t st);
+int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, const ConvEp& ep, cudaStream_t st);
 bool conv_wgrad_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy);
 int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g, cudaStream_t st);
 int conv_wgrad_simt(const void* x, const void* gy, float* gw, int dtype, const ConvGeom& g, cudaStream_t st);

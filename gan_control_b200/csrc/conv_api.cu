@@ -32,20 +32,19 @@ extern "C" int b200gan_set_conv_engine(int engine) {
 
 
 static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, const b200gan::ConvGeom& g,
-                             const float* bias, const float* rowscale, const void* noise, const float* noise_w,
-                             float slope, float gain, cudaStream_t st) {
+                             const b200gan::ConvEp& ep, cudaStream_t st) {
     using namespace b200gan;
     const int b = g.b;
     const bool packed = g.pack_in || g.pack_out;
     if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
-        return ran(B200GAN_ENGINE_FWD_POINTWISE, conv_fwd_pointwise(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st));
+        return ran(B200GAN_ENGINE_FWD_POINTWISE, conv_fwd_pointwise(x, w, y, dtype, g, ep, st));
     // the halo kernel's epilogue reads bias / rowscale as float4
-    if (g_conv_engine.load() == 0 && b > 0 && (((uintptr_t)bias | (uintptr_t)rowscale) & 15) == 0 &&
+    if (g_conv_engine.load() == 0 && b > 0 && (((uintptr_t)ep.bias | (uintptr_t)ep.rowscale | (uintptr_t)ep.addend | (uintptr_t)ep.gate) & 15) == 0 &&
         conv_fwd_halo_eligible(dtype, g, x, w, y))
-        return ran(B200GAN_ENGINE_FWD_HALO, conv_fwd_halo(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st));
+        return ran(B200GAN_ENGINE_FWD_HALO, conv_fwd_halo(x, w, y, g, ep, st));
     if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
-        return ran(B200GAN_ENGINE_FWD_UMMA, conv_fwd_umma(x, w, y, g, bias, rowscale, noise, noise_w, slope, gain, st));
-    return ran(B200GAN_ENGINE_FWD_SIMT, conv_fwd_simt(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, st));
+        return ran(B200GAN_ENGINE_FWD_UMMA, conv_fwd_umma(x, w, y, g, ep, st));
+    return ran(B200GAN_ENGINE_FWD_SIMT, conv_fwd_simt(x, w, y, dtype, g, ep, st));
 }
 
 static int conv_wgrad_dispatch(const void* x, const void* gy, float* gw, int dtype, const b200gan::ConvGeom& g,
@@ -67,7 +66,24 @@ extern "C" int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype
                                 int w_per_sample, const float* bias, const float* rowscale, const void* noise,
                                 const float* noise_w, float slope, float gain, void* stream) {
     b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
-    return conv_fwd_dispatch(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
+    const b200gan::ConvEp ep{bias, rowscale, noise, noise_w, slope, gain, nullptr, nullptr};
+    return conv_fwd_dispatch(x, w, y, dtype, g, ep, (cudaStream_t)stream);
+}
+
+extern "C" int b200gan_conv_fwd_ex(const void* x, const void* w, void* y, int dtype, int b, int in_h, int in_w, int ic,
+                                   int out_h, int out_w, int oc, int kh, int kw, int up, int down, int pad0,
+                                   int w_per_sample, int pack_in, int pack_out, const b200gan_conv_epilogue* epilogue,
+                                   void* stream) {
+    b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, up, down, pad0, w_per_sample};
+    g.pack_in = pack_in != 0;
+    g.pack_out = pack_out != 0;
+    if ((g.pack_in || g.pack_out) && (up != 1 || down != 1)) {
+        b200gan::set_error("conv_fwd_ex: packed views need up = down = 1");
+        return B200GAN_EINVAL;
+    }
+    b200gan::ConvEp ep{nullptr, nullptr, nullptr, nullptr, 1.f, 1.f, nullptr, nullptr};
+    if (epilogue) ep = *epilogue;
+    return conv_fwd_dispatch(x, w, y, dtype, g, ep, (cudaStream_t)stream);
 }
 
 extern "C" int b200gan_conv_fwd_packed(const void* x, const void* w, void* y, int dtype, int b, int in_h, int in_w,
@@ -78,7 +94,8 @@ extern "C" int b200gan_conv_fwd_packed(const void* x, const void* w, void* y, in
     b200gan::ConvGeom g{b, in_h, in_w, ic, out_h, out_w, oc, kh, kw, 1, 1, pad0, w_per_sample};
     g.pack_in = pack_in != 0;
     g.pack_out = pack_out != 0;
-    return conv_fwd_dispatch(x, w, y, dtype, g, bias, rowscale, noise, noise_w, slope, gain, (cudaStream_t)stream);
+    const b200gan::ConvEp ep{bias, rowscale, noise, noise_w, slope, gain, nullptr, nullptr};
+    return conv_fwd_dispatch(x, w, y, dtype, g, ep, (cudaStream_t)stream);
 }
 
 extern "C" int b200gan_conv_wgrad(const void* x, const void* gy, float* gw, int dtype, int b, int in_h, int in_w,

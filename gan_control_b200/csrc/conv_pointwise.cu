@@ -15,13 +15,18 @@ struct PwEpilogue {
     const void* noise;
     const float* noise_w;
     float slope, gain;
+    const void* addend;      // output-shaped (include/b200gan.h b200gan_conv_epilogue)
+    const void* gate;        // output-shaped: backward mode
     int on;
 };
 
+// output element (pix, o) of `oc_total` channels
 template <typename T>
 __device__ __forceinline__ float pw_epilogue(const PwEpilogue& e, float v, int b, int oc_total, int o, int64_t pix, float nz) {
     if (!e.on) return v;
+    if (e.addend) v += io<T>::ld((const T*)e.addend + pix * oc_total + o);
     if (e.rowscale) v *= e.rowscale[(int64_t)b * oc_total + o];
+    if (e.gate) return v * (io<T>::ld((const T*)e.gate + pix * oc_total + o) > 0.f ? e.gain : e.gain * e.slope);
     v += nz + (e.bias ? e.bias[o] : 0.f);
     return e.gain * (v > 0.f ? v : v * e.slope);
 }
@@ -167,11 +172,8 @@ bool conv_fwd_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, co
     return false;
 }
 
-int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
-                       const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
-                       cudaStream_t st) {
-    PwEpilogue ep{bias, rowscale, noise, noise_w, slope, gain,
-                  (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0};
+int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const ConvEp& e, cudaStream_t st) {
+    PwEpilogue ep{e.bias, e.rowscale, e.noise, e.noise_w, e.slope, e.gain, e.addend, e.gate, ep_active(e) ? 1 : 0};
     const int npix = g.out_h * g.out_w;
     return B200_DISPATCH(dtype, [&] {
         constexpr int V = 16 / sizeof(T);

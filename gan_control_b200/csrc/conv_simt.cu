@@ -62,9 +62,14 @@ __device__ __forceinline__ void load4(const T* p, int valid, bool vec, float out
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(
-    const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y, ConvGeom g,
-    const float* __restrict__ bias, const float* __restrict__ rowscale, const T* __restrict__ noise,
-    const float* __restrict__ noise_w, float slope, float gain, int vec_in, int vec_out) {
+    const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y, ConvGeom g, ConvEp ep, int vec_in, int vec_out) {
+    const float* __restrict__ bias = ep.bias;
+    const float* __restrict__ rowscale = ep.rowscale;
+    const T* __restrict__ noise = (const T*)ep.noise;
+    const float* __restrict__ noise_w = ep.noise_w;
+    const T* __restrict__ addend = (const T*)ep.addend;
+    const T* __restrict__ gate = (const T*)ep.gate;
+    const float slope = ep.slope, gain = ep.gain;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int t = threadIdx.x;
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(
     }
     // epilogue
     const float nw = (noise != nullptr && noise_w != nullptr) ? *noise_w : 0.f;
-    const bool has_ep = bias || rowscale || noise || slope != 1.f || gain != 1.f;
+    const bool has_ep = bias || rowscale || noise || addend || gate || slope != 1.f || gain != 1.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int pix = m0 + tm * 4 + i;
@@ -129,7 +134,8 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(
         int pch0;
         const int oc_phys = g.pack_out ? g.oc >> 2 : g.oc;
         const int o0 = n0 + tn * 4 < g.oc ? n0 + tn * 4 : 0;                  // 4 consecutive channels share a phase
-        T* dst = y + out_offset(g, b, pix / g.out_w, pix % g.out_w, o0, ppix, pch0);
+        const int64_t doff = out_offset(g, b, pix / g.out_w, pix % g.out_w, o0, ppix, pch0);
+        T* dst = y + doff;
         const float nz = noise ? nw * io<T>::ld(noise + ppix) : 0.f;
         Pack<T, 4> o;
 #pragma unroll
@@ -137,9 +143,14 @@ __global__ void __launch_bounds__(256) conv_fwd_simt_kernel(
             const int o_ch = n0 + tn * 4 + j;
             float v = acc[i][j];
             if (has_ep && o_ch < g.oc) {
+                if (addend) v += io<T>::ld(addend + doff + j);
                 if (rowscale) v *= rowscale[(int64_t)b * oc_phys + pch0 + j];
-                v += nz + (bias ? bias[pch0 + j] : 0.f);
-                v = gain * (v > 0.f ? v : v * slope);
+                if (gate) {
+                    v *= io<T>::ld(gate + doff + j) > 0.f ? gain : gain * slope;
+                } else {
+                    v += nz + (bias ? bias[pch0 + j] : 0.f);
+                    v = gain * (v > 0.f ? v : v * slope);
+                }
             }
             io<T>::st(&o.v[j], v);
         }
@@ -238,9 +249,7 @@ static int check_geom(const ConvGeom& g, const char* who) {
     return 0;
 }
 
-int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const float* bias,
-                  const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
-                  cudaStream_t st) {
+int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGeom& g, const ConvEp& ep, cudaStream_t st) {
     if (int e = check_geom(g, "conv_fwd")) return e;
     if (g.b == 0) return 0;
     return B200_DISPATCH(dtype, [&] {
@@ -249,8 +258,7 @@ int conv_fwd_simt(const void* x, const void* w, void* y, int dtype, const ConvGe
         const size_t a4 = 4 * sizeof(T);
         int vec_in = g.ic % 4 == 0 && (uintptr_t)x % a4 == 0 && (uintptr_t)w % a4 == 0;
         int vec_out = g.oc % 4 == 0 && (uintptr_t)y % a4 == 0;
-        conv_fwd_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, bias, rowscale,
-                                                      (const T*)noise, noise_w, slope, gain, vec_in, vec_out);
+        conv_fwd_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, g, ep, vec_in, vec_out);
         count_launch();
         return check_launch("conv_fwd_simt");
     });

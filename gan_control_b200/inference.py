@@ -8,6 +8,11 @@ Same method names, arguments and return values (`gen_batch`, `gen_batch_by_contr
 entry; controllers in `<dir>/<group>*/` with a `controller` entry).  Differences: no `nn.DataParallel`
 wrapper (one process per GPU), the eval forward runs without autograd so the mapping network is the single
 persistent kernel, activations are bf16 channels-last by default.
+
+Fast path: without autograd every layer runs as `ops.mod_conv` (weight (de)modulation in one
+kernel + one convolution kernel with the fused noise / bias / activation epilogue, nothing saved for a backward pass),
+ToRGB carries its bias in the convolution epilogue, and the whole synthesis network is captured ONCE per batch size in a
+CUDA graph (`cuda_graphs=True`, CUDA only) that later calls replay: ~70 launches become one graph launch.
 """
 import json
 import os
@@ -24,8 +29,10 @@ def _latest_checkpoint(model_dir):
 
 class Inference:
     def __init__(self, model_dir=None, *, generator=None, sub_groups_dict=None, latent_size=512, device='cuda',
-                 act_dtype=torch.bfloat16):
+                 act_dtype=torch.bfloat16, cuda_graphs=True):
         self.device = torch.device(device)
+        self.cuda_graphs = bool(cuda_graphs) and self.device.type == 'cuda'
+        self._graphs = {}
         if model_dir is not None:
             generator, sub_groups_dict, latent_size, self.config, self.ckpt_iter = self.retrieve_model(
                 model_dir, device=self.device, act_dtype=act_dtype)
@@ -71,6 +78,42 @@ class Inference:
     def reset_noise(self):
         self.noise = self.model.make_noise(device=self.device)
 
+    # -- synthesis network, CUDA-graphed per batch size ---------------------------------------------------------------
+    @torch.no_grad()
+    def synthesize(self, latent, noise=None):
+        """image = synthesis(W+ latent (B, n_latent, style_dim) or w (B, style_dim), noise list | None = fresh noise)
+        (`Generator.forward` after the mapping network, gm.py:754-801)."""
+        g = self.model
+        if latent.ndim == 2:
+            latent = latent.unsqueeze(1).repeat(1, g.n_latent, 1)
+        if not self.cuda_graphs:
+            return g.synthesis(latent, noise if noise is not None else [None] * g.num_layers)
+        batch = latent.shape[0]
+        entry = self._graphs.get(batch)
+        if entry is None:
+            st_latent = torch.zeros(batch, g.n_latent, g.style_dim, device=self.device)
+            st_noise = [torch.zeros(batch, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=self.device)
+                        for i in range(g.num_layers)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                       # warm-up outside the capture (lazy allocations, tables)
+                g.synthesis(st_latent, st_noise)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st_out = g.synthesis(st_latent, st_noise)
+            entry = self._graphs[batch] = (graph, st_latent, st_noise, st_out)
+        graph, st_latent, st_noise, st_out = entry
+        st_latent.copy_(latent)
+        for dst, src in zip(st_noise, noise if noise is not None else [None] * len(st_noise)):
+            if src is None:
+                dst.normal_()                                   # NoiseInjection's fresh draw (gm.py:343)
+            else:
+                dst.copy_(src.expand_as(dst))
+        graph.replay()
+        return st_out.clone()
+
     @staticmethod
     def expend_noise(noise, batch_size):
         return [n.repeat(batch_size, 1, 1, 1) for n in noise]
@@ -111,7 +154,10 @@ class Inference:
             for key, (lo, hi) in self.place_in_latent_dict.items():
                 mean = self.mean_w_latents[key].to(self.device)
                 latent[..., lo:hi] = truncation * (latent[..., lo:hi] - mean) + mean
-        tensor, latent_w = self.model([latent], return_latents=True, input_is_latent=input_is_latent, noise=injection_noise)
+        latent_w = latent if input_is_latent else self.model.map_styles(latent)
+        if latent_w.ndim == 2:
+            latent_w = latent_w.unsqueeze(1).repeat(1, self.model.n_latent, 1)       # gm.py:757-760
+        tensor = self.synthesize(latent_w, injection_noise)
         if normalize:
             tensor = tensor.float().mul(0.5).add(0.5).clamp(min=0., max=1.).cpu()
         return tensor, latent, latent_w
@@ -171,7 +217,7 @@ class Controller(Inference):
                     else self.fc_controls[group_key]
                 latent_w = self.insert_group_w_latent(latent_w, ctl(value), group_key)
         injection_noise = self.expend_noise(self.noise, latent.shape[0]) if static_noise else None
-        tensor, _ = self.model([latent_w], input_is_latent=True, noise=injection_noise)
+        tensor = self.synthesize(latent_w, injection_noise)
         if normalize:
             tensor = tensor.float().mul(0.5).add(0.5).clamp(min=0., max=1.).cpu()
         return tensor, latent, latent_w

@@ -123,6 +123,29 @@ int b200gan_conv_fwd(const void* x, const void* w, void* y, int dtype,
                      int kh, int kw, int up, int down, int pad0, int w_per_sample,
                      const float* bias, const float* rowscale, const void* noise, const float* noise_w,
                      float slope, float gain, void* stream);
+/* The same convolution with the full epilogue description.  Beyond b200gan_conv_fwd's operands:
+ *   addend: a tensor of the OUTPUT's shape and dtype added to the accumulator first -- the residual sum of ResBlock
+ *           `(out + skip) / sqrt(2)` gm.py:920, ToRGB's `out + skip` gm.py:433, and in the backward pass the gradient that
+ *           another consumer of the same tensor contributes (what autograd would add in a separate pass);
+ *   gate:   a tensor of the OUTPUT's shape and dtype: BACKWARD mode.  The convolution is then a data gradient whose
+ *           result is the gradient w.r.t. the output y of a bias + leaky-ReLU layer, and `gate` is that saved y:
+ *               out = (acc + addend) * rowscale[b][o] * gain * (gate > 0 ? 1 : slope)
+ *           i.e. the activation backward of the PRODUCER layer (`fused_leaky_relu` gm.py:39-41 from its output, SURVEY
+ *           App. A.4) is applied here instead of in a pass of its own.  bias / noise are ignored in gate mode.
+ * pack_in / pack_out as in b200gan_conv_fwd_packed (0 / 0 = plain). */
+typedef struct {
+    const float* bias;       /* [oc]      or NULL */
+    const float* rowscale;   /* [b][oc]   or NULL */
+    const void* noise;       /* [b][out pixels], `dtype`, or NULL */
+    const float* noise_w;    /* [1]       or NULL */
+    float slope, gain;
+    const void* addend;      /* output-shaped, `dtype`, or NULL */
+    const void* gate;        /* output-shaped, `dtype`, or NULL */
+} b200gan_conv_epilogue;
+int b200gan_conv_fwd_ex(const void* x, const void* w, void* y, int dtype,
+                        int b, int in_h, int in_w, int ic, int out_h, int out_w, int oc,
+                        int kh, int kw, int up, int down, int pad0, int w_per_sample, int pack_in, int pack_out,
+                        const b200gan_conv_epilogue* epilogue, void* stream);
 /* Engine selection for the convolution family: 0 (default) = tcgen05/TMEM implicit GEMM whenever the
  * shape qualifies (bf16, IC = 32 or a multiple of 8 >= 64, OC a multiple of 16, k <= 3x3), CUDA-core
  * gather kernel otherwise; 1 = CUDA-core kernel only; 2 = automatic but without the halo-reuse variant

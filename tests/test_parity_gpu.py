@@ -539,3 +539,45 @@ def test_style_mixing_is_captured_in_cuda_graphs():
     torch.cuda.synchronize()
     assert all(np.isfinite(v) for pair in losses for v in pair) and len({round(p[1], 6) for p in losses}) > 1
     assert torch.isfinite(step.g_arena.data).all() and float((step.g_arena.data - p0).abs().max()) > 0
+
+
+@pytest.mark.parametrize('graphs', [False, True])
+def test_inference_front_end_on_gpu(graphs):
+    """SURVEY.md 8(f) row 1 on the GPU: `Inference.gen_batch` / `Controller.gen_batch_by_controls`
+    (inference/inference.py:54-92, inference/controller.py:30-54) through the fused no-grad layers, with and without the
+    CUDA-graphed synthesis network, against the oracle: split-FC mapping, static noise, truncation toward the per-group
+    mean latents, a controller overwriting its group's slice of w, W+ input."""
+    import test_inference_cpu as TI
+    from gan_control_b200.inference import Controller
+    g, sd = TI.make_generator()
+    ctl = M.FcStack(0.01, 3, 3, 32, 16)
+    ctl_sd = P.seeded_state_dict(P.fc_stack_shapes(3, 3, 32, 16), 78)
+    ctl.load_state_dict(ctl_sd)
+    c = Controller(generator=g, sub_groups_dict=TI.GROUPS, latent_size=TI.SDIM, device=DEV, act_dtype=torch.float32,
+                   fc_controls={'pose': ctl}, cuda_graphs=graphs)
+    cpu = lambda ts: [t.cpu() for t in ts]
+    z = TI.rnd(1, 3, TI.SDIM)
+    for rep in range(2):                                                # second call replays the captured graph
+        img, lat, lat_w = c.gen_batch(latent=z.clone().to(DEV), normalize=False)
+        ref = O.generator_forward(sd, [z], TI.SIZE, TI.FCG, noise=cpu(c.expend_noise(c.noise, 3)))
+        assert max_rel(img, ref) < TOL and lat_w.shape == (3, 2 * 3 - 2, TI.SDIM)
+    c.calc_mean_w_latents(n_batches=2, batch=64)
+    img_t, _, _ = c.gen_batch(latent=z.clone().to(DEV), normalize=True, truncation=0.7)
+    w = O.mapping_network(sd, z, TI.FCG)
+    w_t = c.mean_w_latent + 0.7 * (w - c.mean_w_latent)
+    ref_t = O.generator_forward(sd, [w_t], TI.SIZE, TI.FCG, noise=cpu(c.expend_noise(c.noise, 3)), input_is_latent=True)
+    assert max_rel(img_t, ref_t.mul(0.5).add(0.5).clamp(0, 1)) < TOL
+    pose = TI.rnd(2, 3, 3)
+    img_c, _, w_c = c.gen_batch_by_controls(latent=w.clone().to(DEV), input_is_latent=True, normalize=False, pose=pose.to(DEV))
+    w_ref = w.clone()
+    w_ref[:, 24:40] = O.fc_stack(ctl_sd, 'fc_stack.', pose, normalize=False)
+    assert max_rel(w_c, w_ref) < 1e-4
+    ref_c = O.generator_forward(sd, [w_ref], TI.SIZE, TI.FCG, noise=cpu(c.expend_noise(c.noise, 3)), input_is_latent=True)
+    assert max_rel(img_c, ref_c) < TOL
+    img_p, _, _ = c.gen_batch(latent=lat_w.clone(), input_is_latent=True, normalize=False, static_noise=True)
+    assert max_rel(img_p, O.generator_forward(sd, [z], TI.SIZE, TI.FCG, noise=cpu(c.expend_noise(c.noise, 3)))) < TOL
+    # fresh noise per call when static_noise=False (gm.py:343): two calls differ, both finite
+    a, _, _ = c.gen_batch(latent=z.clone().to(DEV), normalize=False, static_noise=False)
+    b, _, _ = c.gen_batch(latent=z.clone().to(DEV), normalize=False, static_noise=False)
+    assert torch.isfinite(a).all() and float((a - b).abs().max()) > 0
+    assert bool(c._graphs) == graphs
