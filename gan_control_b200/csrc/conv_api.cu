@@ -36,13 +36,15 @@ static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, c
     using namespace b200gan;
     const int b = g.b;
     const bool packed = g.pack_in || g.pack_out;
+    // the tcgen05 epilogues read the output-shaped side inputs (addend / gate) as 16-byte vectors
+    const bool side_ok = (((uintptr_t)ep.addend | (uintptr_t)ep.gate) & 15) == 0;
     if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_fwd_pointwise_eligible(dtype, g, x, w, y))
         return ran(B200GAN_ENGINE_FWD_POINTWISE, conv_fwd_pointwise(x, w, y, dtype, g, ep, st));
     // the halo kernel's epilogue reads bias / rowscale as float4
-    if (g_conv_engine.load() == 0 && b > 0 && (((uintptr_t)ep.bias | (uintptr_t)ep.rowscale | (uintptr_t)ep.addend | (uintptr_t)ep.gate) & 15) == 0 &&
+    if (g_conv_engine.load() == 0 && b > 0 && side_ok && (((uintptr_t)ep.bias | (uintptr_t)ep.rowscale) & 15) == 0 &&
         conv_fwd_halo_eligible(dtype, g, x, w, y))
         return ran(B200GAN_ENGINE_FWD_HALO, conv_fwd_halo(x, w, y, g, ep, st));
-    if (!packed && g_conv_engine.load() != 1 && b > 0 && conv_fwd_umma_eligible(dtype, g, x, w, y))
+    if (!packed && g_conv_engine.load() != 1 && b > 0 && side_ok && conv_fwd_umma_eligible(dtype, g, x, w, y))
         return ran(B200GAN_ENGINE_FWD_UMMA, conv_fwd_umma(x, w, y, g, ep, st));
     return ran(B200GAN_ENGINE_FWD_SIMT, conv_fwd_simt(x, w, y, dtype, g, ep, st));
 }

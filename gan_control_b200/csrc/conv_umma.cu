@@ -57,6 +57,8 @@ struct FwdParams {
     const float* noise_w;
     float slope, gain;
     int has_ep;
+    const __nv_bfloat16* addend;     // output-shaped side inputs (include/b200gan.h b200gan_conv_epilogue)
+    const __nv_bfloat16* gate;
     __nv_bfloat16* y;
 };
 
@@ -232,7 +234,12 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const float* rs = p.rowscale ? p.rowscale + (int64_t)(valid ? n : 0) * p.OC + ocb * p.BN : nullptr;
             const float* bs = p.bias ? p.bias + ocb * p.BN : nullptr;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
+            const int64_t side0 = pix * p.OC + ocb * p.BN;           // this pixel's row of the output-shaped side tensors
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                // side loads first: their latency overlaps the TMEM read of the chunk
+                Side16 s_add, s_gate;
+                if (valid && p.addend) s_add = side_load16(p.addend + side0 + c0);
+                if (valid && p.gate) s_gate = side_load16(p.gate + side0 + c0);
                 float v[16];
                 if (!zero_tile) {
                     tmem_ld_x16(taddr + (uint32_t)c0, v);
@@ -241,7 +248,25 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     for (int e = 0; e < 16; ++e) v[e] = 0.f;
                 }
                 if (valid) {
-                    if (p.has_ep) {
+                    if (p.gate) {
+                        // backward mode: (acc + addend) * rowscale * gain * act'(gate)
+                        float rr[16];
+                        if (vec_side) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 r4 = rs ? __ldg(reinterpret_cast<const float4*>(rs + c0) + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+                                rr[4 * e] = r4.x; rr[4 * e + 1] = r4.y; rr[4 * e + 2] = r4.z; rr[4 * e + 3] = r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) rr[e] = rs ? rs[c0 + e] : 1.f;
+                        }
+                        side_apply16(v, p.addend ? &s_add : nullptr, &s_gate, rr, g, gs);
+                    } else if (p.has_ep) {
+                        if (p.addend) {
+                            float one[16];
+                            side_apply16(v, &s_add, nullptr, one, 1.f, 1.f);
+                        }
                         float rr[16], bb[16];
                         if (vec_side) {
 #pragma unroll
@@ -357,9 +382,12 @@ bool conv_fwd_umma_eligible(int dtype, const ConvGeom& g, const void* x, const v
     return tensor_map_encoder() != nullptr;
 }
 
-int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias,
-                  const float* rowscale, const void* noise, const float* noise_w, float slope, float gain,
-                  cudaStream_t st) {
+int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, const ConvEp& ep, cudaStream_t st) {
+    const float* bias = ep.bias;
+    const float* rowscale = ep.rowscale;
+    const void* noise = ep.noise;
+    const float* noise_w = ep.noise_w;
+    const float slope = ep.slope, gain = ep.gain;
     FwdParams p;
     memset(&p, 0, sizeof(p));
     p.B = g.b; p.OH = g.out_h; p.OW = g.out_w; p.OC = g.oc; p.IC = g.ic;
@@ -447,7 +475,9 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.tmem_cols = next_pow2(2 * p.BN);
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
     p.slope = slope; p.gain = gain;
-    p.has_ep = (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0;
+    p.has_ep = ep_active(ep) ? 1 : 0;
+    p.addend = (const __nv_bfloat16*)ep.addend;
+    p.gate = (const __nv_bfloat16*)ep.gate;
     p.y = (__nv_bfloat16*)y;
 
     // ---- tensor maps ----

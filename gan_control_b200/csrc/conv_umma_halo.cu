@@ -50,16 +50,18 @@ struct HaloParams {
     const float* noise_w;
     float slope, gain;
     int has_ep;
+    const __nv_bfloat16* addend;         // output-shaped side inputs (include/b200gan.h b200gan_conv_epilogue)
+    const __nv_bfloat16* gate;
     int dbg;                             // B200GAN_HALO_DEBUG (timing experiments only): 1 no MMA, 2 no TMA loads, 4 no stores, 8 no tcgen05.ld
     __nv_bfloat16* y;
 };
 
 // 16 accumulator columns of one pixel -> epilogue -> 32 bytes of bf16.  r / b: this chunk's demodulation scales and
 // biases, already in registers.
-template <bool ROW>
+template <bool ROW, bool SIDE>
 __device__ __forceinline__ void epilogue_math_store16(const HaloParams& p, float (&v)[16], __nv_bfloat16* dst,
                                                       const float (&r)[16], const float (&b)[16], float nz) {
-    if (p.has_ep) {
+    if (p.has_ep && !(SIDE && p.gate != nullptr)) {
         // gain * lrelu(u) = max(g*u, g*slope*u) for gain > 0, 0 <= slope <= 1 (every use on the path): FFMA, FMUL, FMNMX
         const float g = p.gain, gs = p.gain * p.slope;
         if (g > 0.f && p.slope >= 0.f && p.slope <= 1.f) {
@@ -99,7 +101,10 @@ __device__ __forceinline__ void load16(const float* src, float (&o)[16], float f
 
 // KDIM = 3 or 1 (kernel size), ROWB = 128 or 64 (bytes per pixel row of a channel chunk = swizzle width): both
 // compile-time so that the MMA-issuing warp's tap loop is straight-line code with immediate descriptor offsets.
-template <int KDIM, int ROWB>
+// SIDE: the epilogue reads output-shaped side inputs (addend / gate).  A template parameter because the epilogue warps'
+// instruction count is on the critical path of the 32-channel layers (profiles/r02_epilogue_cost.md): the plain forward
+// kernel must not carry the side-input code (it cost 0.72 -> 0.82 ms when it was a run-time branch).
+template <int KDIM, int ROWB, bool SIDE>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ HaloParams p) {
@@ -289,6 +294,14 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const bool side_smem = ch_phys > 32;
         auto chunk = [&](uint32_t taddr, int col, __nv_bfloat16* dst, int c0, const float* rs_g, float nz, bool valid) {
             float v[16], r16[16], b16[16];
+            // output-shaped side inputs (the gradient another consumer contributes, the producer's saved output): their
+            // loads are issued before the TMEM read so that the two latencies overlap
+            Side16 s_add, s_gate;
+            if (SIDE) {
+                const int64_t soff = (dst - p.y) + c0;
+                if (valid && p.addend) s_add = side_load16(p.addend + soff);
+                if (valid && p.gate) s_gate = side_load16(p.gate + soff);
+            }
             if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)col, v);
             if (valid && !(p.dbg & 4)) {
                 if (side_smem) {
@@ -298,7 +311,9 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     load16<true>(rs_g ? rs_g + c0 : nullptr, r16, 1.f);
                     load16<true>(p.bias ? p.bias + c0 : nullptr, b16, 0.f);
                 }
-                epilogue_math_store16<true>(p, v, dst + c0, r16, b16, nz);
+                if (SIDE && (p.addend || p.gate))
+                    side_apply16(v, p.addend ? &s_add : nullptr, p.gate ? &s_gate : nullptr, r16, p.gain, p.gain * p.slope);
+                epilogue_math_store16<true, SIDE>(p, v, dst + c0, r16, b16, nz);
             }
         };
         // rowscale[n][:] -> shared memory when this group moves on to another sample (all four warps of a group walk
@@ -337,9 +352,32 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 nraw1 = __ldg(reinterpret_cast<const uint32_t*>(q + 2 * p.OW));
             }
         };
+        // the output-shaped side inputs (addend / gate) of a tile two of this group's tiles ahead are pulled into L2: the
+        // per-chunk loads in `chunk` then see an L2 hit instead of a DRAM round trip in the middle of the epilogue
+        auto prefetch_side = [&](int tile) {
+            if (!SIDE || (p.addend == nullptr && p.gate == nullptr) || tile >= p.total_tiles) return;
+            uint32_t n, t, th, tw;
+            p.div_img.divmod((uint32_t)tile, n, t);
+            p.div_tw.divmod(t, th, tw);
+            const int oy = (int)th * kHTH + h_l, ox = (int)tw * kHTW + w_l;
+            if (oy >= p.OH || ox >= p.OW) return;
+            const int nph = p.pack_out ? 4 : 1;
+            for (int ph = 0; ph < nph; ++ph) {
+                const int64_t off = p.pack_out
+                    ? ((((int64_t)n * (2 * p.OH) + 2 * oy + (ph >> 1)) * (2 * p.OW) + 2 * ox + (ph & 1)) * p.CQ)
+                    : ((((int64_t)n * p.OH + oy) * p.OW + ox) * p.OC);
+                const int bytes = (p.pack_out ? p.CQ : p.OC) * 2;
+                for (int bo = 0; bo < bytes; bo += 128) {
+                    if (p.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.addend + off) + bo));
+                    if (p.gate) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.gate + off) + bo));
+                }
+            }
+        };
         int it = group;
         const int first = blockIdx.x + group * gridDim.x;
         fetch_noise(first);
+        prefetch_side(first);
+        prefetch_side(first + 2 * (int)gridDim.x);
         for (int tile = first; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
             uint32_t n, t, th, tw;
             p.div_img.divmod((uint32_t)tile, n, t);
@@ -357,6 +395,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 tc_fence_after();
                 const float nz = (valid && p.noise) ? nw * __uint_as_float(nraw0 << 16) : 0.f;
                 fetch_noise(tile + 2 * gridDim.x);
+                prefetch_side(tile + 4 * (int)gridDim.x);
                 for (int c0 = 0; c0 < p.BN; c0 += 16) chunk(taddr, c0, dst, c0, rs_g, nz, valid);
             } else {
                 // depth-to-space: accumulator columns [(py*2+px)*CQ + c] of view pixel (oy, ox) are channel c of the
@@ -372,6 +411,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     nz[2] = nw * __uint_as_float(nraw1 << 16); nz[3] = nw * __uint_as_float(nraw1 & 0xffff0000u);
                 }
                 fetch_noise(tile + 2 * gridDim.x);
+                prefetch_side(tile + 4 * (int)gridDim.x);
 #pragma unroll
                 for (int ph = 0; ph < 4; ++ph) {
                     __nv_bfloat16* dst = p.y + (pix0 + (ph >> 1) * (2 * p.OW) + (ph & 1)) * p.CQ;
@@ -435,8 +475,12 @@ bool conv_fwd_halo_eligible(int dtype, const ConvGeom& g, const void* x, const v
     return tensor_map_encoder() != nullptr;
 }
 
-int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, const float* bias, const float* rowscale,
-                  const void* noise, const float* noise_w, float slope, float gain, cudaStream_t st) {
+int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, const ConvEp& ep, cudaStream_t st) {
+    const float* bias = ep.bias;
+    const float* rowscale = ep.rowscale;
+    const void* noise = ep.noise;
+    const float* noise_w = ep.noise_w;
+    const float slope = ep.slope, gain = ep.gain;
     HaloParams p;
     memset(&p, 0, sizeof(p));
     p.B = g.b; p.H = g.in_h; p.W = g.in_w; p.OC = g.oc; p.IC = g.ic; p.OH = g.out_h; p.OW = g.out_w;
@@ -459,7 +503,9 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.tmem_cols = cols;
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
     p.slope = slope; p.gain = gain;
-    p.has_ep = (bias || rowscale || noise || slope != 1.f || gain != 1.f) ? 1 : 0;
+    p.has_ep = ep_active(ep) ? 1 : 0;
+    p.addend = (const __nv_bfloat16*)ep.addend;
+    p.gate = (const __nv_bfloat16*)ep.gate;
     p.y = (__nv_bfloat16*)y;
     if (const char* e = getenv("B200GAN_HALO_DEBUG")) p.dbg = atoi(e);
 
@@ -494,17 +540,28 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (attr_dev != cur_dev) {
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
-        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<3, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + 1.5 KB static
+        cudaFuncSetAttribute(conv_fwd_halo_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         attr_dev = cur_dev;
     }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    if (g.kh == 3 && p.row_bytes == 128) conv_fwd_halo_kernel<3, 128><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
-    else if (g.kh == 3)                  conv_fwd_halo_kernel<3, 64><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
-    else if (p.row_bytes == 128)         conv_fwd_halo_kernel<1, 128><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
-    else                                 conv_fwd_halo_kernel<1, 64><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);
+    const bool side = p.addend != nullptr || p.gate != nullptr;
+#define B200_HALO_LAUNCH(KD, RB)                                                                            \
+    do {                                                                                                    \
+        if (side) conv_fwd_halo_kernel<KD, RB, true><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);    \
+        else      conv_fwd_halo_kernel<KD, RB, false><<<grid, kHaloThreads, smem, st>>>(map_x, map_w, p);   \
+    } while (0)
+    if (g.kh == 3 && p.row_bytes == 128) B200_HALO_LAUNCH(3, 128);
+    else if (g.kh == 3)                  B200_HALO_LAUNCH(3, 64);
+    else if (p.row_bytes == 128)         B200_HALO_LAUNCH(1, 128);
+    else                                 B200_HALO_LAUNCH(1, 64);
+#undef B200_HALO_LAUNCH
     count_launch();
     return check_launch("conv_fwd_halo");
 }

@@ -151,6 +151,41 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float v[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- epilogue side inputs: 16 consecutive bf16 of an output-shaped tensor (addend / gate, include/b200gan.h) ----------
+struct Side16 {
+    uint4 a, b;
+};
+__device__ __forceinline__ Side16 side_load16(const __nv_bfloat16* p) {
+    Side16 s;
+    s.a = __ldg(reinterpret_cast<const uint4*>(p));
+    s.b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    return s;
+}
+__device__ __forceinline__ void side_unpack16(const Side16& s, float (&o)[16]) {
+    const uint32_t w[8] = {s.a.x, s.a.y, s.a.z, s.a.w, s.b.x, s.b.y, s.b.z, s.b.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        o[2 * e] = __uint_as_float(w[e] << 16);
+        o[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+}
+// v = (v + addend) [gate mode: * r * (gate > 0 ? g : gs)]; the forward activation is applied by the caller otherwise
+__device__ __forceinline__ void side_apply16(float (&v)[16], const Side16* addend, const Side16* gate, const float (&r)[16],
+                                             float g, float gs) {
+    if (addend) {
+        float a[16];
+        side_unpack16(*addend, a);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] += a[e];
+    }
+    if (gate) {
+        float y[16];
+        side_unpack16(*gate, y);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] *= r[e] * (y[e] > 0.f ? g : gs);
+    }
+}
+
 // ---- descriptors ---------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address [0,14),
 // LBO [16,30), SBO [32,46) (all >> 4), version = 1 at [46,48), layout type at [61,64).

@@ -26,6 +26,11 @@ class FcLayer(ctypes.Structure):
                 ('out_off', _i), ('scale', _f), ('bias_mul', _f)]
 
 
+class ConvEpilogue(ctypes.Structure):
+    _fields_ = [('bias', _vp), ('rowscale', _vp), ('noise', _vp), ('noise_w', _vp), ('slope', _f), ('gain', _f),
+                ('addend', _vp), ('gate', _vp)]
+
+
 class FcLayerGrad(ctypes.Structure):
     _fields_ = [('gw', _vp), ('gb', _vp)]
 
@@ -42,6 +47,7 @@ _SIGNATURES = {
     'b200gan_reduce_nhwc': ([_vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
     'b200gan_conv_fwd': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
     'b200gan_conv_fwd_packed': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp, _vp, _vp, _vp, _f, _f, _vp], _i),
+    'b200gan_conv_fwd_ex': ([_vp, _vp, _vp, _i] + [_i] * 15 + [_vp, _vp], _i),
     'b200gan_conv_wgrad_packed': ([_vp, _vp, _vp, _i] + [_i] * 13 + [_vp], _i),
     'b200gan_set_conv_engine': ([_i], _i),
     'b200gan_engine_launches': ([_i], _c.c_uint64),
@@ -251,12 +257,15 @@ def reduce_nhwc(a, b=None, per_channel=True, per_sample_channel=False, pixw=None
 
 
 def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None, noise=None, noise_w=None,
-             slope=1.0, gain=1.0, pack_in=False, pack_out=False):
+             slope=1.0, gain=1.0, pack_in=False, pack_out=False, addend=None, gate=None):
     """x: (B,H,W,IC) contiguous; w: (Bw,KH,KW,OC,IC) contiguous, same dtype; -> (B,out_h,out_w,OC).
     pack_in / pack_out: the convolution runs between space-to-depth views (include/b200gan.h): x is then the plain
     (B,2H,2W,IC/4) tensor, and / or the result is the plain (B,2*out_h,2*out_w,OC/4) tensor; out_h, out_w and the
-    channel counts of `w` are the LOGICAL (view) sizes."""
-    _cuda(x, w, bias, rowscale, noise, noise_w)
+    channel counts of `w` are the LOGICAL (view) sizes.
+    addend / gate: tensors of the OUTPUT's shape and dtype (include/b200gan.h b200gan_conv_epilogue): `addend` is added to
+    the accumulator first; with `gate` (the saved output of the producer layer) the call is a data gradient that also
+    applies that layer's activation backward: (acc + addend) * rowscale * gain * (gate > 0 ? 1 : slope)."""
+    _cuda(x, w, bias, rowscale, noise, noise_w, addend, gate)
     assert x.ndim == 4 and w.ndim == 5 and x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
     b, h, wd, ic = x.shape
     if pack_in:
@@ -274,6 +283,15 @@ def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None,
         noise = noise.detach().to(x.dtype).contiguous()
         assert noise.numel() == b * y.shape[1] * y.shape[2]
     if y.numel() == 0:
+        return y
+    if addend is not None or gate is not None:
+        for t in (addend, gate):
+            assert t is None or (t.shape == y.shape and t.dtype == y.dtype and t.is_contiguous()), 'side input != output shape'
+        ep = ConvEpilogue(_ptr(bias), _ptr(rowscale), _ptr(noise), _ptr(noise_w), float(slope), float(gain), _ptr(addend), _ptr(gate))
+        with torch.cuda.device(x.device):
+            _check(lib().b200gan_conv_fwd_ex(_ptr(x), _ptr(w), _ptr(y), _dt(x), b, h, wd, ic, out_h, out_w, oc, kh, kw, up, down,
+                                             pad0, int(bw > 1), int(pack_in), int(pack_out), ctypes.byref(ep), _stream()),
+                   'conv_fwd_ex')
         return y
     with torch.cuda.device(x.device):
         if pack_in or pack_out:

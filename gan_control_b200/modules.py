@@ -576,9 +576,10 @@ class ConvLayer(nn.Sequential):                                               # 
 
     FUSE_DOWN_MAX_IN_CHANNELS = 32
 
-    def forward(self, input, out_scale=1.0):
+    def forward(self, input, out_scale=1.0, defer_gate=False):
         """[Blur] -> conv (+ bias + leaky-ReLU fused into the convolution's epilogue).  `out_scale`
-        multiplies the result (ResBlock folds its 1/sqrt(2) into both branches this way)."""
+        multiplies the result (ResBlock folds its 1/sqrt(2) into both branches this way).  defer_gate: see ops.mod_conv
+        (only honoured on the fused first-order path; the caller must then pass `in_gate` to every consumer)."""
         mods = list(self)
         x = input
         stride = None
@@ -612,7 +613,7 @@ class ConvLayer(nn.Sequential):                                               # 
             bias = act.bias if isinstance(act, FusedLeakyReLU) else None
             gain = act.scale if isinstance(act, FusedLeakyReLU) else SQRT2
             return _plain_if_tiny(ops.mod_conv(x, None, conv.weight, bias=bias, scale=conv.scale, down=stride, pad0=conv.padding,
-                                               slope=act.negative_slope, gain=gain * out_scale))
+                                               slope=act.negative_slope, gain=gain * out_scale, defer_gate=defer_gate))
         if len(mods) == 1:                                   # no activation (ResBlock.skip): scale the weights
             w = (conv.weight * (conv.scale * out_scale)).unsqueeze(0)
             y = ops.conv_gather(x, w, 1, stride, conv.padding, param_weight=True)
@@ -643,7 +644,26 @@ class ResBlock(nn.Module):                                                    # 
         self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
         self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
 
-    def forward(self, input):
+    def fusable(self, input):
+        """the whole block as one autograd node (ops.res_block): first-order passes, standard 3x3 / 4-tap geometry"""
+        c1, c2, sk = self.conv1, self.conv2, self.skip
+        return (ops.fused_prep() and input.shape[2] % 2 == 0 and input.shape[3] % 2 == 0 and input.shape[2] >= 4
+                and len(c1) == 2 and isinstance(c1[1], FusedLeakyReLU) and len(c2) == 3 and isinstance(c2[2], FusedLeakyReLU)
+                and len(sk) == 2 and sk[1].bias is None and c2[0].kernel.shape == (4, 4)
+                and c1[1].negative_slope == c2[2].negative_slope and c1[1].scale == c2[2].scale)
+
+    def forward(self, input, in_gate=None):
+        """in_gate=(slope, gain): `input` is the output of a layer that deferred its activation backward to us
+        (ops.mod_conv `defer_gate`); only legal when the block is `fusable`."""
+        if self.fusable(input):
+            c1, c2, sk = self.conv1, self.conv2, self.skip
+            fuse_down = c2.fuse_down
+            return _plain_if_tiny(ops.res_block(
+                input, c1[0].weight, c1[1].bias, c2[1].weight, c2[2].bias, sk[1].weight, c2[0].kernel,
+                c2.fir_toeplitz if fuse_down else c2[0].kernel, c1[0].scale, c2[1].scale, sk[1].scale,
+                slope=c1[1].negative_slope, gain=c1[1].scale, fuse_down=fuse_down, pad_blur2=c2[0].pad[0], pad_blur_s=sk[0].pad[0],
+                in_gate=in_gate))
+        assert in_gate is None, 'a deferred activation gate reached a ResBlock that cannot apply it'
         # (conv2(conv1(x)) + skip(x)) / sqrt(2) (gm.py:920) with the scale folded into both branches:
         # one elementwise pass instead of two
         out = self.conv2(self.conv1(input), out_scale=1 / SQRT2)
@@ -679,7 +699,20 @@ class Discriminator(nn.Module):                                               # 
 
     def forward(self, input):
         x = input.to(dtype=self.act_dtype, memory_format=torch.channels_last)
-        out = self.convs(x)
+        blocks = list(self.convs)
+        if (ops.fused_prep() and torch.is_grad_enabled() and len(blocks) > 1 and isinstance(blocks[1], ResBlock)
+                and isinstance(blocks[0], ConvLayer) and len(blocks[0]) == 2 and isinstance(blocks[0][1], FusedLeakyReLU)):
+            # from_rgb defers its leaky-ReLU backward to the first ResBlock, whose conv1 data-gradient epilogue applies it
+            # together with the sum of the two gradient contributions (ops._ResBlockFn)
+            y0 = blocks[0](x, defer_gate=True)
+            if blocks[1].fusable(y0):
+                out = blocks[1](y0, in_gate=(blocks[0][1].negative_slope, blocks[0][1].scale))
+            else:                                                    # (cannot happen for the standard sizes; stay correct)
+                out = blocks[1](blocks[0](x))
+            for blk in blocks[2:]:
+                out = blk(out)
+        else:
+            out = self.convs(x)
         return self._forward_split(out, self.final_conv, self.final_linear), None
 
     def _forward_split(self, out, final_conv, final_linear):                  # gm.py:1003-1016

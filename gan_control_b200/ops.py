@@ -497,8 +497,11 @@ class _ModConv(Function):
     d_ext: demodulation applied to the OUTPUT instead (activation-modulated form, modules.ModulatedConv2d)."""
 
     @staticmethod
-    def forward(ctx, x, s, weight, d_ext, noise, noise_w, bias, scale, demod, flip, up, down, pad0, out_h, out_w, slope, gain):
+    def forward(ctx, x, s, weight, d_ext, noise, noise_w, bias, scale, demod, flip, up, down, pad0, out_h, out_w, slope, gain,
+                defer_gate=False, in_gate=None):
         oc, ic, kh, kw = weight.shape[-4:]
+        assert not defer_gate or (d_ext is None and noise is None), 'a deferred gate needs a plain bias + leaky-ReLU epilogue'
+        ctx.gates = (defer_gate, in_gate)
         w4 = weight.reshape(oc, ic, kh, kw)
         sk = s if s is not None else _ones_row(ic, x)
         has_ep = bias is not None or d_ext is not None or noise is not None or slope != 1.0 or gain != 1.0
@@ -520,7 +523,14 @@ class _ModConv(Function):
         oc, ic, kh, kw = weight.shape[-4:]
         gx = gs = gw = gd = gnoise = gnw = gb = None
         gyn = _nhwc(gy)
-        if has_ep:
+        defer_gate, in_gate = ctx.gates
+        if has_ep and defer_gate:
+            # the consumers of y applied this layer's activation backward in their data-gradient epilogues (`in_gate`):
+            # gy IS the gradient of the convolution output; only the bias reduction is left
+            gconv = gyn
+            if bias is not None and need[6]:
+                gb = K.reduce_nhwc(gconv, None, per_channel=True)[0].reshape(bias.shape).to(bias.dtype)
+        elif has_ep:
             gconv, gd_, gb_, gnw_ = K.epilogue_bwd(gyn, y, d_ext, noise, noise_w if noise is not None else None,
                                                    None if bias is None else bias.reshape(-1), slope, gain,
                                                    want_gd=d_ext is not None and need[3], want_gb=bias is not None and need[6],
@@ -537,7 +547,10 @@ class _ModConv(Function):
         else:
             gconv = gyn
         if need[0]:
-            gx = _nchw(K.conv_fwd(gconv, wkt, h, wd, down, up, kh - 1 - pad0))
+            if in_gate is None:
+                gx = _nchw(K.conv_fwd(gconv, wkt, h, wd, down, up, kh - 1 - pad0))
+            else:   # x is the output of a deferred-gate layer: its activation backward rides in this epilogue
+                gx = _nchw(K.conv_fwd(gconv, wkt, h, wd, down, up, kh - 1 - pad0, slope=in_gate[0], gain=in_gate[1], gate=_nhwc(x)))
         if (need[1] and s is not None) or need[2]:
             gwk = K.conv_wgrad(_nhwc(x), gconv, kh, kw, up, down, pad0, s is not None)
             sk = s if s is not None else _ones_row(ic, x)
@@ -547,18 +560,134 @@ class _ModConv(Function):
                 gs = gs_.to(s.dtype)
             if gw_ is not None:
                 gw = gw_.reshape(weight.shape).to(weight.dtype)
-        return gx, gs, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None, None
+        return gx, gs, gw, gd, gnoise, gnw, gb, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def mod_conv(x, s, weight, d_ext=None, noise=None, noise_w=None, bias=None, scale=1.0, demod=False, flip=False, up=1, down=1,
-             pad0=0, out_hw=None, slope=1.0, gain=1.0):
-    """See _ModConv.  weight: the parameter, (OC,IC,KH,KW) or (1,OC,IC,KH,KW); s: (B,IC) styles or None."""
+             pad0=0, out_hw=None, slope=1.0, gain=1.0, defer_gate=False, in_gate=None):
+    """See _ModConv.  weight: the parameter, (OC,IC,KH,KW) or (1,OC,IC,KH,KW); s: (B,IC) styles or None.
+    defer_gate: EVERY consumer of the result promises to apply this layer's leaky-ReLU backward itself (`in_gate=(slope,
+    gain)` on its side, from the saved output = its own input), so this layer's backward receives the gradient of the
+    convolution output directly and the separate activation-backward pass disappears."""
     if out_hw is None:
         kh, kw = weight.shape[-2:]
         zh, zw = (x.shape[2] - 1) * up + 1, (x.shape[3] - 1) * up + 1
         out_hw = ((zh + 2 * pad0 - kh) // down + 1, (zw + 2 * pad0 - kw) // down + 1)
     return _ModConv.apply(x, s, weight, d_ext, noise, noise_w, bias, float(scale), bool(demod), bool(flip), up, down, pad0,
-                          out_hw[0], out_hw[1], float(slope), float(gain))
+                          out_hw[0], out_hw[1], float(slope), float(gain), bool(defer_gate), in_gate)
+
+
+class _ResBlockFn(Function):
+    """The discriminator's ResBlock (gm.py:893-922) as ONE autograd node with a hand-scheduled first-order backward:
+
+        y1  = sqrt2*lrelu(conv3x3(x, W1) + b1)                                          conv1   (gm.py:901)
+        y2  = lrelu(conv3x3_s2(blur(y1), W2) + b2)          [* sqrt2 / sqrt2]            conv2   (gm.py:902, 857-872)
+        out = conv1x1_s2(blur(x), Ws) / sqrt2 + y2                                       skip + residual (gm.py:907-920)
+
+    What the node buys over the per-layer graph: the residual sum rides in the skip convolution's epilogue (`addend`);
+    in the backward pass the two gradient contributions to x are summed in conv1's data-gradient epilogue instead of by
+    autograd, and if x itself is the output of a deferred-gate layer (from_rgb) its activation backward rides there too
+    (measured at 32 ch @1024^2: +0.37 ms on the convolution against 0.46 + 0.62 ms for the two separate passes,
+    profiles/r02_side_inputs.md).  FIRST ORDER ONLY (see `first_order`)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, ws, taps, toeplitz, cfg):
+        scale1, scale2, scale_s, slope, gain, fuse_down, pad_blur2, pad_blur_s, in_gate = cfg
+        xn = _nhwc(x)
+        bsz, h, wd, c = xn.shape
+        oc = w2.shape[0]
+        need_x = ctx.needs_input_grad[0]
+        ones_c = _ones_row(c, x)
+        inv = 1.0 / SQRT2
+        wk1, wk1t, _ = K.modweight_fwd(w1, ones_c, scale1, False, False, x.dtype, want_adjoint=need_x)
+        y1 = K.conv_fwd(xn, wk1, h, wd, 1, 1, 1, b1, None, None, None, slope, gain)
+        t = None
+        if fuse_down:
+            w2c = composite_down((w2.detach() * scale2).unsqueeze(0), toeplitz)        # (1, OC, 4C, 3, 3)
+            wk2 = _kernel_layout(w2c, x.dtype)
+            y2 = K.conv_fwd(y1, wk2, h // 2, wd // 2, 1, 1, 1, b2, None, None, None, slope, gain * inv, pack_in=True)
+            wk2t = _kernel_layout(_flip_t(w2c), x.dtype)
+        else:
+            t = K.upfirdn2d(y1, taps, 1, 1, pad_blur2, pad_blur2, h + 1, wd + 1, True)
+            wk2, wk2t, _ = K.modweight_fwd(w2, ones_c, scale2, False, False, x.dtype, want_adjoint=True)
+            y2 = K.conv_fwd(t, wk2, h // 2, wd // 2, 1, 2, 0, b2, None, None, None, slope, gain * inv)
+        xs = K.upfirdn2d(xn, taps, 1, 2, pad_blur_s, pad_blur_s, h // 2, wd // 2, True)
+        wks, wkst, _ = K.modweight_fwd(ws, ones_c, scale_s * inv, False, False, x.dtype, want_adjoint=need_x)
+        out = K.conv_fwd(xs, wks, h // 2, wd // 2, 1, 1, 0, addend=y2)
+        ctx.cfg = cfg
+        ctx.save_for_backward(x, w1, b1, w2, b2, ws, taps, toeplitz, y1, y2, xs, t, wk1t, wk2t, wkst)
+        return _nchw(out)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        if torch.is_grad_enabled():
+            raise RuntimeError('the fused ResBlock is first-order only (see ops.first_order)')
+        x, w1, b1, w2, b2, ws, taps, toeplitz, y1, y2, xs, t, wk1t, wk2t, wkst = ctx.saved_tensors
+        scale1, scale2, scale_s, slope, gain, fuse_down, pad_blur2, pad_blur_s, in_gate = ctx.cfg
+        need = ctx.needs_input_grad
+        xn, g = _nhwc(x), _nhwc(g_out)
+        bsz, h, wd, c = xn.shape
+        oc = w2.shape[0]
+        inv = 1.0 / SQRT2
+        ones_c = _ones_row(c, x)
+        gx = gw1 = gb1 = gw2 = gb2 = gws = None
+        # conv2's activation backward (its output feeds the residual sum, so nobody else could do it) + bias gradient
+        gz2, _, gb2_, _ = K.epilogue_bwd(g, y2, None, None, None, b2, slope, gain * inv, want_gd=False, want_gb=need[4],
+                                         want_gnw=False)
+        if gb2_ is not None:
+            gb2 = gb2_.to(b2.dtype)
+        # skip branch: 1x1 data gradient, then the adjoint of the decimating FIR
+        gskip = None
+        if need[0]:
+            gxs = K.conv_fwd(g, wkst, h // 2, wd // 2, 1, 1, 0)
+            kh = taps.shape[0]
+            gskip = K.upfirdn2d(gxs, taps, 2, 1, kh - 1 - pad_blur_s, kh - 1 - pad_blur_s, h, wd, False)
+        if need[5]:
+            gws = K.modweight_bwd(K.conv_wgrad(xs, g, 1, 1, 1, 1, 0, False), ws, ones_c, None, scale_s * inv, False, False,
+                                  want_gs=False)[1].to(ws.dtype)
+        # conv2: data gradient (carrying conv1's activation backward where one kernel produces it) and weight gradient
+        if fuse_down:
+            # (measured, profiles/r02_side_inputs.md: in the depth-to-space epilogue a gate costs +0.48 ms at 32 ch @1024^2,
+            # more than the separate activation-backward pass, 0.63 ms incl. the bias reduction it would still need)
+            gy1 = K.conv_fwd(gz2, wk2t, h // 2, wd // 2, 1, 1, 1, pack_out=True)
+            gz1, _, gb1_, _ = K.epilogue_bwd(gy1, y1, None, None, None, b1, slope, gain, want_gd=False, want_gb=need[2],
+                                             want_gnw=False)
+            if gb1_ is not None:
+                gb1 = gb1_.to(b1.dtype)
+            if need[3]:
+                gw2c = K.conv_wgrad(y1, gz2, 3, 3, 1, 1, 1, False, pack_x=True).permute(0, 3, 4, 1, 2)
+                with torch.enable_grad():
+                    wq = w2.detach().requires_grad_(True)
+                    gw2, = torch.autograd.grad(composite_down((wq * scale2).unsqueeze(0), toeplitz), wq, gw2c.to(wq.dtype))
+        else:
+            kh = taps.shape[0]
+            gt = K.conv_fwd(gz2, wk2t, h + 1, wd + 1, 2, 1, 2)                         # adjoint of the stride-2 convolution
+            gy1 = K.upfirdn2d(gt, taps, 1, 1, kh - 1 - pad_blur2, kh - 1 - pad_blur2, h, wd, False)
+            gz1, _, gb1_, _ = K.epilogue_bwd(gy1, y1, None, None, None, b1, slope, gain, want_gd=False, want_gb=need[2],
+                                             want_gnw=False)
+            if gb1_ is not None:
+                gb1 = gb1_.to(b1.dtype)
+            if need[3]:
+                gw2 = K.modweight_bwd(K.conv_wgrad(t, gz2, 3, 3, 1, 2, 0, False), w2, ones_c, None, scale2, False, False,
+                                      want_gs=False)[1].to(w2.dtype)
+        # conv1: data gradient + the skip branch's contribution (+ the producer's activation backward), weight gradient
+        if need[0]:
+            if in_gate is None:
+                gx = _nchw(K.conv_fwd(gz1, wk1t, h, wd, 1, 1, 1, addend=gskip))
+            else:
+                gx = _nchw(K.conv_fwd(gz1, wk1t, h, wd, 1, 1, 1, slope=in_gate[0], gain=in_gate[1], addend=gskip, gate=xn))
+        if need[1]:
+            gw1 = K.modweight_bwd(K.conv_wgrad(xn, gz1, 3, 3, 1, 1, 1, False), w1, ones_c, None, scale1, False, False,
+                                  want_gs=False)[1].to(w1.dtype)
+        return gx, gw1, gb1, gw2, gb2, gws, None, None, None
+
+
+def res_block(x, w1, b1, w2, b2, ws, taps, toeplitz, scale1, scale2, scale_s, slope=0.2, gain=SQRT2, fuse_down=False,
+              pad_blur2=2, pad_blur_s=1, in_gate=None):
+    """See _ResBlockFn."""
+    return _ResBlockFn.apply(x, w1, b1, w2, b2, ws, taps, toeplitz,
+                             (float(scale1), float(scale2), float(scale_s), float(slope), float(gain), bool(fuse_down),
+                              int(pad_blur2), int(pad_blur_s), in_gate))
 
 
 def _view_hw(x, w, up, down, pad0, pack_in):

@@ -134,7 +134,7 @@ def _d2s(y):
 
 
 def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None, noise=None, noise_w=None,
-             slope=1.0, gain=1.0, pack_in=False, pack_out=False):
+             slope=1.0, gain=1.0, pack_in=False, pack_out=False, addend=None, gate=None):
     if pack_in:
         x = _s2d(x)
     b = x.shape[0]
@@ -149,6 +149,10 @@ def conv_fwd(x, w, out_h, out_w, up=1, down=1, pad0=0, bias=None, rowscale=None,
     y = y.permute(0, 2, 3, 1).contiguous()
     if pack_out:
         y = _d2s(y)
+    if addend is not None:
+        y = y + addend.to(y.dtype)
+    if gate is not None:              # backward mode: the producer's activation gradient from its saved output
+        return bias_act_bwd(y, gate.to(y.dtype), rowscale, slope, gain)
     if bias is not None or rowscale is not None or noise is not None or slope != 1.0 or gain != 1.0:
         y = bias_act_fwd(y, bias, rowscale, noise, noise_w, slope, gain)
     return y

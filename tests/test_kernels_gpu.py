@@ -468,3 +468,47 @@ def test_modweight(cfg, dt):
     assert float((gw.cpu().double() - rgw).abs().max() / rgw.abs().max()) < 2e-5, 'gweight'
     gs2, gw2 = K.modweight_bwd(g.cuda(), w.cuda(), s.cuda(), d, scale, demod, flip, want_gs=False, want_gw=True)
     assert gs2 is None and float((gw2 - gw).abs().max()) <= 1e-6 * float(gw.abs().max())
+
+
+# ---- output-shaped side inputs of the convolution epilogue: addend and (backward mode) gate -----------------------
+SIDE_CASES = [
+    # b, h, w, ic, oc, k, up, down, pad0, per_sample, pack_in, pack_out, engines allowed under auto
+    (2, 32, 32, 32, 32, 3, 1, 1, 1, True, False, False, ('fwd_halo',)),
+    (2, 32, 32, 64, 64, 3, 1, 1, 1, False, False, False, ('fwd_halo',)),
+    (2, 48, 40, 32, 64, 1, 1, 1, 0, False, False, False, ('fwd_halo',)),
+    (2, 32, 24, 128, 64, 3, 1, 1, 1, True, True, False, ('fwd_halo',)),      # fused-up data gradient (pack_in)
+    (3, 48, 40, 64, 128, 3, 1, 1, 1, False, False, True, ('fwd_halo',)),     # fused-down data gradient (pack_out)
+    (4, 16, 16, 128, 128, 3, 1, 1, 1, False, False, False, ('fwd_umma',)),
+    (2, 8, 8, 256, 128, 3, 2, 1, 2, False, False, False, ('fwd_umma',)),     # transposed conv (data gradient of a stride-2 conv)
+    (2, 33, 33, 64, 128, 3, 1, 2, 0, False, False, False, ('fwd_umma',)),
+    (2, 16, 16, 3, 64, 1, 1, 1, 0, True, False, False, ('fwd_pointwise',)),  # ToRGB data gradient
+    (2, 16, 16, 64, 3, 1, 1, 1, 0, True, False, False, ('fwd_pointwise',)),
+    (3, 7, 9, 8, 12, 3, 1, 1, 1, True, False, False, ('fwd_simt',)),
+]
+
+
+@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('case', SIDE_CASES)
+def test_conv_epilogue_addend_and_gate(case, dt):
+    b, h, w, ic, oc, k, up, down, pad0, ps, pin, pout, allowed = case
+    if up == 2:
+        oh, ow = (h - 1) * 2 + k - 2 * (k - 1 - pad0), (w - 1) * 2 + k - 2 * (k - 1 - pad0)
+    else:
+        oh, ow = conv_out_hw(h, w, k, up, down, pad0)
+    x, xr = prep(rnd(131, b, 2 * h, 2 * w, ic // 4) if pin else rnd(131, b, h, w, ic), dt)
+    wt, wr = prep(rnd(132, b if ps else 1, k, k, oc, ic) / (ic * k * k) ** 0.5, dt)
+    yshape = (b, 2 * oh, 2 * ow, oc // 4) if pout else (b, oh, ow, oc)
+    ocp = yshape[-1]
+    add, addr = prep(rnd(133, *yshape), dt)
+    gate, gater = prep(rnd(134, *yshape), dt)
+    rs, bias = (rnd(135, b, ocp).abs() + 0.5).float(), rnd(136, ocp).float()
+    kw = dict(pack_in=pin, pack_out=pout)
+    want = allowed if dt == torch.bfloat16 else (('fwd_pointwise',) if 'fwd_pointwise' in allowed else ('fwd_simt',))
+    with engines(*want):
+        y_add = K.conv_fwd(x, wt, oh, ow, up, down, pad0, bias.cuda(), None, None, None, 0.2, 2 ** 0.5, addend=add, **kw)
+        y_gate = K.conv_fwd(x, wt, oh, ow, up, down, pad0, None, rs.cuda(), None, None, 0.2, 2 ** 0.5, addend=add, gate=gate, **kw)
+        y_gate2 = K.conv_fwd(x, wt, oh, ow, up, down, pad0, None, None, None, None, 0.2, 2 ** 0.5, gate=gate, **kw)
+    close(y_add, R.conv_fwd(xr, wr, oh, ow, up, down, pad0, bias.double(), None, None, None, 0.2, 2 ** 0.5, addend=addr, **kw), dt, 'addend')
+    close(y_gate, R.conv_fwd(xr, wr, oh, ow, up, down, pad0, None, rs.double(), None, None, 0.2, 2 ** 0.5, addend=addr, gate=gater, **kw),
+          dt, 'addend + gate')
+    close(y_gate2, R.conv_fwd(xr, wr, oh, ow, up, down, pad0, None, None, None, None, 0.2, 2 ** 0.5, gate=gater, **kw), dt, 'gate')

@@ -64,10 +64,10 @@ def test_fused_networks_match_unfused(cpu_kernels, form):
         assert calls['n'] > 20                                   # every conv of G and D went through mod_conv
     finally:
         kernels.modweight_fwd = real
-    assert max_rel(img1, img0) < 1e-12 and max_rel(pred1, pred0) < 1e-12 and max_rel(gz1, gz0) < 1e-10
+    assert max_rel(img1, img0) < 1e-12 and max_rel(pred1, pred0) < 1e-12 and max_rel(gz1, gz0) < 1e-8
     assert set(g0) == set(g1)
     for k in g0:
-        assert max_rel(g1[k], g0[k]) < 1e-9, k
+        assert max_rel(g1[k], g0[k]) < 1e-7, k
 
 
 def test_no_grad_forward_uses_the_fused_path_and_double_backward_is_refused(cpu_kernels):
@@ -110,3 +110,33 @@ def test_modweight_standin_matches_reference_formula(cpu_kernels, cfg):
     gw_ref, gs_ref = torch.autograd.grad(weight.permute(0, 3, 4, 1, 2), (w, s), g)
     gs, gw = cpu_kernels.modweight_bwd(g, w.detach(), s.detach(), d, scale, cfg['demod'], cfg['flip'])
     assert max_rel(gs, gs_ref) < 1e-12 and max_rel(gw, gw_ref) < 1e-12
+
+
+def test_fused_resblock_with_single_pass_downsampling(cpu_kernels):
+    """ResBlock(32 -> 64): conv2 is the single-pass FIR (*) stride-2 form (space-to-depth view), so in the fused block
+    conv1's activation backward rides in conv2's data-gradient epilogue and from_rgb's in conv1's: discriminator output
+    and every parameter / input gradient equal the per-layer op algebra."""
+    torch.manual_seed(3)
+    d = M.Discriminator(128, channel_multiplier=0.25, act_dtype=F64).double()
+    _randomize(d)
+    assert d.convs[1].conv2.fuse_down and not d.convs[2].conv2.fuse_down
+    x0 = torch.randn(2, 3, 128, 128, dtype=F64)
+    out = []
+    for fused in (False, True):
+        d.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        with (ops.first_order() if fused else torch.enable_grad()):
+            pred, _ = d(x)
+            torch.nn.functional.softplus(-pred).mean().backward()
+        out.append((pred.detach(), x.grad.clone(), {k: v.grad.clone() for k, v in d.named_parameters()}))
+    (p0, gx0, g0), (p1, gx1, g1) = out
+    assert max_rel(p1, p0) < 1e-12 and max_rel(gx1, gx0) < 1e-8
+    for k in g0:
+        assert max_rel(g1[k], g0[k]) < 1e-8, k
+    # frozen discriminator (the generator step): only the input gradient, no parameter gradients
+    for p in d.parameters():
+        p.requires_grad_(False)
+    x = x0.clone().requires_grad_(True)
+    with ops.first_order():
+        torch.nn.functional.softplus(-d(x)[0]).mean().backward()
+    assert max_rel(x.grad, gx0) < 1e-8

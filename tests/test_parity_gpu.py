@@ -419,46 +419,62 @@ def test_graphed_step_equals_eager_step():
         assert err < 2e-3
 
 
-@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
-def test_fused_first_order_path_matches_op_algebra(dt):
-    """`ops.first_order()` (mod_conv: weight path, convolution, epilogue and their gradients as single kernels) against
-    the closed op algebra that the goldens pin, on the GPU: a 64^2 G + D with weight- and activation-modulated layers,
-    image, prediction and every parameter gradient."""
-    torch.manual_seed(5)
+def _g_d_grads(g, d, z, noise, fused):
+    g.zero_grad()
+    d.zero_grad()
+    with (ops.first_order() if fused else torch.enable_grad()):
+        img, _ = g([z], noise=noise)
+        pred, _ = d(img)
+        torch.nn.functional.softplus(-pred).mean().backward()
+    grads = {k: v.grad.float().clone() for k, v in list(g.named_parameters()) + [('d.' + k, v) for k, v in d.named_parameters()]
+             if v.grad is not None}
+    return img.detach().float(), pred.detach().float(), grads
+
+
+def test_fused_first_order_path_matches_op_algebra():
+    """`ops.first_order()` (mod_conv / res_block: weight path, convolution, epilogue, residual and gradient sums as single
+    kernels) against the closed op algebra that the goldens pin, on the GPU: a 64^2 G + D with weight- and
+    activation-modulated layers.  fp32: image, prediction and every parameter gradient agree.  bf16: both paths are
+    compared with the fp32 result -- the fused path must be as close to it as the unfused bf16 path is (their mutual
+    difference is dominated by rounding: e.g. noise strengths are sums with heavy cancellation)."""
     size, sdim = 64, 64
-    g = M.Generator(size, sdim, 3, channel_multiplier=2, conv_transpose=True, act_dtype=dt).to(DEV)
-    d = M.Discriminator(size, channel_multiplier=2, act_dtype=dt).to(DEV)
-    for m in list(g.modules()) + list(d.modules()):
-        if isinstance(m, M.NoiseInjection):
-            m.weight.data.fill_(0.3)
-        if isinstance(m, (M.FusedLeakyReLU,)):
-            m.bias.data.normal_(std=0.3)
-        if isinstance(m, M.ToRGB):
-            m.bias.data.normal_(std=0.3)
-    for i, m in enumerate(mm for mm in g.modules() if isinstance(mm, M.ModulatedConv2d)):
-        m.form = 'weight' if i % 2 else 'auto'
-    z = torch.randn(4, sdim, device=DEV)
-    noise = [torch.randn(4, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=DEV) for i in range(g.num_layers)]
-    out = []
-    for fused in (False, True):
-        g.zero_grad()
-        d.zero_grad()
-        with (ops.first_order() if fused else torch.enable_grad()):
-            img, _ = g([z], noise=noise)
-            pred, _ = d(img)
-            torch.nn.functional.softplus(-pred).mean().backward()
-        out.append((img.detach().float(), pred.detach().float(),
-                    {k: v.grad.clone() for k, v in list(g.named_parameters()) + [('d.' + k, v) for k, v in d.named_parameters()]
-                     if v.grad is not None}))
-    (i0, p0, g0), (i1, p1, g1) = out
-    # bf16: both paths round differently (demodulation folded into bf16 weights vs applied to the fp32 accumulator); the
-    # scalar noise strengths are sums with heavy cancellation (measured 0.19 on one of them)
-    tol_y, tol_g = (1e-4, 2e-3) if dt == torch.float32 else (3e-2, 3e-1)
-    assert rel_err(i1, i0) < tol_y and rel_err(p1, p0) < tol_y
-    assert set(g0) == set(g1)
+    res = {}
+    for dt in (torch.float32, torch.bfloat16):
+        torch.manual_seed(5)
+        g = M.Generator(size, sdim, 3, channel_multiplier=2, conv_transpose=True, act_dtype=dt).to(DEV)
+        d = M.Discriminator(size, channel_multiplier=2, act_dtype=dt).to(DEV)
+        for m in list(g.modules()) + list(d.modules()):
+            if isinstance(m, M.NoiseInjection):
+                m.weight.data.fill_(0.3)
+            if isinstance(m, (M.FusedLeakyReLU,)):
+                m.bias.data.normal_(std=0.3)
+            if isinstance(m, M.ToRGB):
+                m.bias.data.normal_(std=0.3)
+        for i, m in enumerate(mm for mm in g.modules() if isinstance(mm, M.ModulatedConv2d)):
+            m.form = 'weight' if i % 2 else 'auto'
+        z = torch.randn(4, sdim, device=DEV)
+        noise = [torch.randn(4, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=DEV) for i in range(g.num_layers)]
+        for fused in (False, True):
+            res[(dt, fused)] = _g_d_grads(g, d, z, noise, fused)
+    i0, p0, g0 = res[(torch.float32, False)]
+    i1, p1, g1 = res[(torch.float32, True)]
+    assert rel_err(i1, i0) < 1e-4 and rel_err(p1, p0) < 1e-4 and set(g0) == set(g1)
     worst = max((rel_err(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0)
-    print(f'fused vs op algebra ({dt}): image {rel_err(i1, i0):.2e}, worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})')
-    assert worst[0] < tol_g, worst
+    print(f'fused vs op algebra (fp32): image {rel_err(i1, i0):.2e}, worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})')
+    assert worst[0] < 2e-3, worst
+    (iu, pu, gu), (if_, pf, gf) = res[(torch.bfloat16, False)], res[(torch.bfloat16, True)]
+    assert rel_err(if_, i0) < 3e-2 and rel_err(pf, p0) < 5e-2
+    bad = []
+    for k in g0:
+        if float(g0[k].abs().max()) == 0:
+            continue
+        eu, ef = rel_err(gu[k], g0[k]), rel_err(gf[k], g0[k])
+        if ef > max(2.5 * eu, 5e-2):
+            bad.append((k, eu, ef))
+    tot_u = sum(rel_err(gu[k], g0[k]) for k in g0 if float(g0[k].abs().max()) > 0)
+    tot_f = sum(rel_err(gf[k], g0[k]) for k in g0 if float(g0[k].abs().max()) > 0)
+    print(f'bf16 vs fp32 gradients, summed rel-L2 over {len(g0)} tensors: unfused {tot_u:.3f}, fused {tot_f:.3f}; outliers {bad}')
+    assert len(bad) <= 2 and tot_f < 1.5 * tot_u, bad
 
 
 def test_mapping_network_under_autograd():
@@ -581,3 +597,33 @@ def test_inference_front_end_on_gpu(graphs):
     b, _, _ = c.gen_batch(latent=z.clone().to(DEV), normalize=False, static_noise=False)
     assert torch.isfinite(a).all() and float((a - b).abs().max()) > 0
     assert bool(c._graphs) == graphs
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('size,cm', [(64, 2), (128, 0.25)])
+def test_fused_discriminator_matches_op_algebra(size, cm, dt):
+    """the discriminator alone: fused ResBlocks (ops.res_block: residual sum and gradient sums in convolution epilogues,
+    activation backward of conv1 / from_rgb carried by their consumers' data gradients) vs the per-layer op algebra;
+    prediction, input gradient and every parameter gradient, printed per tensor"""
+    torch.manual_seed(9)
+    d = M.Discriminator(size, channel_multiplier=cm, act_dtype=dt).to(DEV)
+    for m in d.modules():
+        if isinstance(m, M.FusedLeakyReLU):
+            m.bias.data.normal_(std=0.3)
+    x0 = torch.randn(4, 3, size, size, device=DEV)
+    out = []
+    for fused in (False, True):
+        d.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        with (ops.first_order() if fused else torch.enable_grad()):
+            pred, _ = d(x)
+            torch.nn.functional.softplus(-pred).mean().backward()
+        out.append((pred.detach().float(), x.grad.clone(), {k: v.grad.clone() for k, v in d.named_parameters()}))
+    (p0, gx0, g0), (p1, gx1, g1) = out
+    errs = {k: rel_err(g1[k], g0[k]) for k in g0 if float(g0[k].abs().max()) > 0}
+    errs['input'] = rel_err(gx1, gx0)
+    errs['pred'] = rel_err(p1, p0)
+    bad = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
+    print(f'fused D {size} cm={cm} {dt}: worst rel-L2 errors {[(k, round(v, 5)) for k, v in bad]}')
+    tol = 2e-3 if dt == torch.float32 else 1e-1
+    assert bad[0][1] < tol, bad
