@@ -1,6 +1,7 @@
 // Shared helpers for libb200gan (sm_100a).  Internal -- the public surface is include/b200gan.h.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -30,6 +31,11 @@ template <> struct io<float> {
 template <> struct io<__nv_bfloat16> {
     static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+template <> struct io<__half> {
+    static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+    static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
 };
 
 // VEC consecutive elements moved as one (up to 128-bit) access
@@ -80,6 +86,9 @@ static inline FastDiv make_fastdiv(uint32_t d) {
             return __VA_ARGS__();                                   \
         } else if ((dtype) == B200GAN_BF16) {                       \
             using T = __nv_bfloat16;                                \
+            return __VA_ARGS__();                                   \
+        } else if ((dtype) == B200GAN_F16) {                        \
+            using T = __half;                                       \
             return __VA_ARGS__();                                   \
         }                                                           \
         b200gan::set_error("unsupported dtype %d", (int)(dtype));   \

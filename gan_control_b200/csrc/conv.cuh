@@ -15,6 +15,7 @@ struct ConvGeom {
     // blur, or a transposed stride-2 convolution followed by it, is a 3x3 stride-1 convolution between such views
     // with composite weights (ops.py), so the blurred / zero-inserted intermediate never exists.
     int pack_in = 0, pack_out = 0;
+    int f16 = 0;             // 16-bit storage is IEEE half instead of bfloat16 (tcgen05 engines; set by the dispatcher)
 };
 
 // the epilogue of every forward engine (include/b200gan.h b200gan_conv_epilogue)

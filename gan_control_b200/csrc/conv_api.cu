@@ -31,9 +31,11 @@ extern "C" int b200gan_set_conv_engine(int engine) {
 }
 
 
-static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, const b200gan::ConvGeom& g,
+static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, const b200gan::ConvGeom& g_in,
                              const b200gan::ConvEp& ep, cudaStream_t st) {
     using namespace b200gan;
+    ConvGeom g = g_in;
+    g.f16 = dtype == B200GAN_F16;
     const int b = g.b;
     const bool packed = g.pack_in || g.pack_out;
     // the tcgen05 epilogues read the output-shaped side inputs (addend / gate) as 16-byte vectors
@@ -49,9 +51,11 @@ static int conv_fwd_dispatch(const void* x, const void* w, void* y, int dtype, c
     return ran(B200GAN_ENGINE_FWD_SIMT, conv_fwd_simt(x, w, y, dtype, g, ep, st));
 }
 
-static int conv_wgrad_dispatch(const void* x, const void* gy, float* gw, int dtype, const b200gan::ConvGeom& g,
+static int conv_wgrad_dispatch(const void* x, const void* gy, float* gw, int dtype, const b200gan::ConvGeom& g_in,
                                cudaStream_t st) {
     using namespace b200gan;
+    ConvGeom g = g_in;
+    g.f16 = dtype == B200GAN_F16;
     const int b = g.b;
     const bool packed = g.pack_in || g.pack_out;
     if (!packed && g_conv_engine.load() != 1 && b > 0 && b <= 65535 && conv_wgrad_pointwise_eligible(dtype, g, x, gy))

@@ -3,11 +3,15 @@
 // gradients.  These are pure streaming passes over a 1024^2 activation (AI ~ 3 FLOP/B, SURVEY.md
 // App. B): no tensor cores, no tiling -- one coalesced 16-byte-vector read of the wide tensor, the
 // narrow tensor and the (per-sample) weights ride in registers / shared memory.
+#include <stdlib.h>
+
 #include "conv.cuh"
 
 namespace b200gan {
 
 constexpr int kPwMaxSmall = 4;
+// B200GAN_PW_GENERIC=1 (timing / test experiments): always use the generic shared-memory-weight kernels
+static const bool g_pw_generic = [] { const char* e = getenv("B200GAN_PW_GENERIC"); return e && e[0] == '1'; }();
 
 struct PwEpilogue {
     const float* bias;
@@ -110,6 +114,144 @@ __global__ void __launch_bounds__(256) pw_small_ic_kernel(const T* __restrict__ 
     }
 }
 
+// ---- fast paths: the weight slice a thread needs is loop-invariant -> registers ---------------------------------------
+// The generic kernels above re-read their weights from shared memory for every vector (24 scalar LDS per 16 bytes of
+// activation) and, in the IC <= 4 one, decode the (pixel, vector) pair with two 64-bit divisions per element: both were
+// issue-bound at 1.2 - 1.7 TB/s (from_rgb forward at 1024^2: 0.91 ms for a 1.2 GB pass, profiles/r02_pointwise.md).
+// Here the channel vector of a thread is fixed for the whole kernel (power-of-two vector counts), its weights, bias and
+// demodulation row live in registers, side inputs are read as 16-byte vectors, and several pixels are in flight per thread.
+
+// OC <= 4 (ToRGB forward, from_rgb data gradient): L = nv / SL lanes share one pixel, lane `sub` owns the vectors
+// sub, sub + L, ... (SL of them); partial sums meet in a shuffle reduction.
+template <typename T, int VEC, int SL>
+__global__ void __launch_bounds__(256, 2) pw_small_oc_reg_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                              T* __restrict__ y, int npix, int ic, int oc, int per_sample,
+                                                              int L, PwEpilogue ep) {
+    constexpr int U = SL >= 4 ? 1 : (SL == 2 ? 2 : 4);           // pixel groups in flight per warp
+    const int b = blockIdx.y;
+    const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
+    const int lane = threadIdx.x & 31, sub = lane & (L - 1), ppw = 32 / L, pw_ = lane / L;
+    float wr[SL][kPwMaxSmall][VEC];
+#pragma unroll
+    for (int s = 0; s < SL; ++s)
+#pragma unroll
+        for (int o = 0; o < kPwMaxSmall; ++o)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) wr[s][o][j] = o < oc ? io<T>::ld(wb + (int64_t)o * ic + (sub + s * L) * VEC + j) : 0.f;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const float nw = (ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
+    const T* xb = x + (int64_t)b * npix * ic;
+    for (int p0 = warp * ppw; p0 < npix; p0 += warps * ppw * U) {
+        Pack<T, VEC> xv[U][SL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * warps * ppw + pw_;
+#pragma unroll
+            for (int s = 0; s < SL; ++s)
+                if (p < npix) xv[u][s] = *reinterpret_cast<const Pack<T, VEC>*>(xb + (int64_t)p * ic + (sub + s * L) * VEC);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * warps * ppw + pw_;
+            float acc[kPwMaxSmall] = {0.f, 0.f, 0.f, 0.f};
+            if (p < npix) {
+#pragma unroll
+                for (int s = 0; s < SL; ++s)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float xf = io<T>::ld(&xv[u][s].v[j]);
+#pragma unroll
+                        for (int o = 0; o < kPwMaxSmall; ++o) acc[o] = fmaf(xf, wr[s][o][j], acc[o]);
+                    }
+            }
+#pragma unroll
+            for (int o = 0; o < kPwMaxSmall; ++o)
+                for (int off = L >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+            if (sub == 0 && p < npix) {
+                const int64_t pix = (int64_t)b * npix + p;
+                const float nz = ep.noise ? nw * io<T>::ld((const T*)ep.noise + pix) : 0.f;
+#pragma unroll
+                for (int o = 0; o < kPwMaxSmall; ++o)
+                    if (o < oc) io<T>::st(y + pix * oc + o, pw_epilogue<T>(ep, acc[o], b, oc, o, pix, nz));
+            }
+        }
+    }
+}
+
+// IC <= 4 (from_rgb forward, ToRGB data gradient): a thread owns output vector v = tid % nv and walks over pixels.
+template <typename T, int VEC, int ICN>
+__global__ void __launch_bounds__(256, 2) pw_small_ic_reg_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                              T* __restrict__ y, int npix, int ic, int oc, int per_sample,
+                                                              int log_nv, PwEpilogue ep) {
+    constexpr int U = 3;
+    const int b = blockIdx.y;
+    const int nv = 1 << log_nv;
+    const int v = threadIdx.x & (nv - 1), pl = threadIdx.x >> log_nv, npl = blockDim.x >> log_nv;
+    const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
+    float wr[VEC][ICN], br[VEC], rr[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int o = v * VEC + j;
+#pragma unroll
+        for (int c = 0; c < ICN; ++c) wr[j][c] = c < ic ? io<T>::ld(wb + (int64_t)o * ic + c) : 0.f;
+        br[j] = (ep.on && ep.bias && !ep.gate) ? ep.bias[o] : 0.f;
+        rr[j] = (ep.on && ep.rowscale) ? ep.rowscale[(int64_t)b * oc + o] : 1.f;
+    }
+    const float nw = (ep.on && ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
+    const float g_pos = ep.gain, g_neg = ep.gain * ep.slope;
+    const T* xb = x + (int64_t)b * npix * ic;
+    const int stride = gridDim.x * npl;
+    for (int p0 = blockIdx.x * npl + pl; p0 < npix; p0 += stride * U) {
+        float xs[U][ICN], nz[U];
+        Pack<T, VEC> sa[U], sg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * stride;
+            nz[u] = 0.f;
+#pragma unroll
+            for (int c = 0; c < ICN; ++c) xs[u][c] = (c < ic && p < npix) ? io<T>::ld(xb + (int64_t)p * ic + c) : 0.f;
+            if (ep.on && p < npix) {
+                const int64_t pix = (int64_t)b * npix + p;
+                if (ep.noise) nz[u] = nw * io<T>::ld((const T*)ep.noise + pix);
+                if (ep.addend) sa[u] = *reinterpret_cast<const Pack<T, VEC>*>((const T*)ep.addend + pix * oc + v * VEC);
+                if (ep.gate) sg[u] = *reinterpret_cast<const Pack<T, VEC>*>((const T*)ep.gate + pix * oc + v * VEC);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * stride;
+            if (p >= npix) continue;
+            Pack<T, VEC> out;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < ICN; ++c) a = fmaf(xs[u][c], wr[j][c], a);
+                if (ep.on) {                                    // same order of operations as pw_epilogue
+                    if (ep.addend) a += io<T>::ld(&sa[u].v[j]);
+                    a *= rr[j];
+                    if (ep.gate) {
+                        a *= io<T>::ld(&sg[u].v[j]) > 0.f ? g_pos : g_neg;
+                    } else {
+                        a += nz[u] + br[j];
+                        a = a > 0.f ? a * g_pos : a * g_neg;
+                    }
+                }
+                io<T>::st(&out.v[j], a);
+            }
+            *reinterpret_cast<Pack<T, VEC>*>(y + ((int64_t)b * npix + p) * oc + v * VEC) = out;
+        }
+    }
+}
+
+static inline int pw_log2_exact(int v) {                       // log2 of a power of two, else -1
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
 // ---- weight gradient with one narrow side:  gw[wb][o][c] += sum_p gy[p][o] * x[p][c] ----------------
 // `wide` has wc channels (vectorised), `narrow` has nc <= 4.  narrow_is_oc selects the output indexing.
 template <typename T, int VEC>
@@ -165,7 +307,7 @@ static bool pw_shape(const ConvGeom& g) {
 
 bool conv_fwd_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
     if (!pw_shape(g)) return false;
-    const int vec = dtype == B200GAN_BF16 ? 8 : 4;
+    const int vec = dtype == B200GAN_F32 ? 4 : 8;
     if ((int64_t)g.oc * g.ic * 4 > 40 * 1024) return false;      // weights are staged in (default-limit) shared memory
     if (g.oc <= kPwMaxSmall && g.ic % vec == 0 && (uintptr_t)x % 16 == 0) return true;
     if (g.ic <= kPwMaxSmall && g.oc % vec == 0 && (uintptr_t)y % 16 == 0) return true;
@@ -180,15 +322,42 @@ int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const C
         const size_t smem = (size_t)g.oc * g.ic * sizeof(float);
         int bx = (int)cdiv((int64_t)sm_count() * 8, g.b);
         if (g.oc <= kPwMaxSmall) {
-            int need = (int)cdiv(npix, 64);
-            if (bx > need) bx = need;
-            pw_small_oc_kernel<T, V><<<dim3(bx < 1 ? 1 : bx, g.b), 256, smem, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc,
-                                                                                  g.w_per_sample, ep);
+            const int nv = g.ic / V, lnv = pw_log2_exact(nv);
+            if (lnv >= 0 && nv <= 128 && !g_pw_generic) {
+                // register-weight kernel: SL vectors per lane, L = nv / SL lanes per pixel
+                const int sl = nv <= 32 ? 1 : nv / 32, L = nv / sl, ppw = 32 / L;
+                int need = (int)cdiv(npix, 8 * ppw * (sl >= 4 ? 1 : 4 / sl));
+                if (bx > need) bx = need;
+                const dim3 grid(bx < 1 ? 1 : bx, g.b);
+                if (sl == 1)
+                    pw_small_oc_reg_kernel<T, V, 1><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc, g.w_per_sample, L, ep);
+                else if (sl == 2)
+                    pw_small_oc_reg_kernel<T, V, 2><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc, g.w_per_sample, L, ep);
+                else
+                    pw_small_oc_reg_kernel<T, V, 4><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc, g.w_per_sample, L, ep);
+            } else {
+                int need = (int)cdiv(npix, 64);
+                if (bx > need) bx = need;
+                pw_small_oc_kernel<T, V><<<dim3(bx < 1 ? 1 : bx, g.b), 256, smem, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc,
+                                                                                      g.w_per_sample, ep);
+            }
         } else {
-            int need = (int)cdiv((int64_t)npix * (g.oc / V), 256);
-            if (bx > need) bx = need;
-            pw_small_ic_kernel<T, V><<<dim3(bx < 1 ? 1 : bx, g.b), 256, smem, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc,
-                                                                                  g.w_per_sample, ep);
+            const int nv = g.oc / V, lnv = pw_log2_exact(nv);
+            if (lnv >= 0 && nv <= 256 && !g_pw_generic) {
+                const int npl = 256 >> lnv;
+                int need = (int)cdiv(npix, npl * 3);
+                if (bx > need) bx = need;
+                const dim3 grid(bx < 1 ? 1 : bx, g.b);
+                if (g.ic <= 3)
+                    pw_small_ic_reg_kernel<T, V, 3><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc, g.w_per_sample, lnv, ep);
+                else
+                    pw_small_ic_reg_kernel<T, V, 4><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc, g.w_per_sample, lnv, ep);
+            } else {
+                int need = (int)cdiv((int64_t)npix * (g.oc / V), 256);
+                if (bx > need) bx = need;
+                pw_small_ic_kernel<T, V><<<dim3(bx < 1 ? 1 : bx, g.b), 256, smem, st>>>((const T*)x, (const T*)w, (T*)y, npix, g.ic, g.oc,
+                                                                                      g.w_per_sample, ep);
+            }
         }
         count_launch();
         return check_launch("conv_fwd_pointwise");
@@ -197,7 +366,7 @@ int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const C
 
 bool conv_wgrad_pointwise_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy) {
     if (!pw_shape(g)) return false;
-    const int vec = dtype == B200GAN_BF16 ? 8 : 4;
+    const int vec = dtype == B200GAN_F32 ? 4 : 8;
     if (g.oc <= kPwMaxSmall && g.ic % vec == 0 && g.ic / vec <= 256 && (uintptr_t)x % 16 == 0) return true;
     if (g.ic <= kPwMaxSmall && g.oc % vec == 0 && g.oc / vec <= 256 && (uintptr_t)gy % 16 == 0) return true;
     return false;

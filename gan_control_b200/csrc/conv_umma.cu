@@ -57,6 +57,7 @@ struct FwdParams {
     const float* noise_w;
     float slope, gain;
     int has_ep;
+    int f16;                         // 16-bit storage is IEEE half
     const __nv_bfloat16* addend;     // output-shaped side inputs (include/b200gan.h b200gan_conv_epilogue)
     const __nv_bfloat16* gate;
     __nv_bfloat16* y;
@@ -148,7 +149,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        const uint32_t idesc = instr_desc_bf16(kTileM, p.BN, 0, 0);
+        const uint32_t idesc = instr_desc_bf16(kTileM, p.BN, 0, 0, p.f16);
         const uint32_t hi = desc_hi(8u * (uint32_t)p.row_bytes, (uint32_t)p.layout);
         const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), 16), b_lo0 = desc_lo(smem_u32(b_buf), 16);
         const uint32_t a_inc = (uint32_t)p.a_stage_bytes >> 4, b_inc = (uint32_t)p.b_stage_bytes >> 4;
@@ -229,7 +230,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             tc_fence_after();
             const int64_t pix = ((int64_t)n * p.OH + oy) * p.OW + ox;
             __nv_bfloat16* dst = p.y + pix * p.OC + ocb * p.BN;
-            const float nz = (valid && p.noise) ? nw * __uint_as_float(nraw << 16) : 0.f;
+            const float nz = (valid && p.noise) ? nw * lo16(nraw, p.f16) : 0.f;
             fetch_noise(tile + gridDim.x);
             const float* rs = p.rowscale ? p.rowscale + (int64_t)(valid ? n : 0) * p.OC + ocb * p.BN : nullptr;
             const float* bs = p.bias ? p.bias + ocb * p.BN : nullptr;
@@ -261,11 +262,11 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                             for (int e = 0; e < 16; ++e) rr[e] = rs ? rs[c0 + e] : 1.f;
                         }
-                        side_apply16(v, p.addend ? &s_add : nullptr, &s_gate, rr, g, gs);
+                        side_apply16(v, p.addend ? &s_add : nullptr, &s_gate, rr, g, gs, p.f16);
                     } else if (p.has_ep) {
                         if (p.addend) {
                             float one[16];
-                            side_apply16(v, &s_add, nullptr, one, 1.f, 1.f);
+                            side_apply16(v, &s_add, nullptr, one, 1.f, 1.f, p.f16);
                         }
                         float rr[16], bb[16];
                         if (vec_side) {
@@ -300,8 +301,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     uint32_t pk[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                        pk[e] = pack16x2(v[2 * e], v[2 * e + 1], p.f16);
                     }
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
                     d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -370,7 +370,7 @@ static int next_pow2(int v) {
 
 // Does the tcgen05 engine take this convolution?  (Everything else goes to conv_simt.cu.)
 bool conv_fwd_umma_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
-    if (dtype != B200GAN_BF16) return false;
+    if (dtype != B200GAN_BF16 && dtype != B200GAN_F16) return false;
     if (g.kh * g.kw > kMaxTaps) return false;
     if (!((g.up == 1 && (g.down == 1 || g.down == 2)) || (g.up == 2 && g.down == 1))) return false;
     if (g.ic < 32 || g.ic % 8 != 0) return false;
@@ -476,6 +476,7 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
     p.slope = slope; p.gain = gain;
     p.has_ep = ep_active(ep) ? 1 : 0;
+    p.f16 = g.f16;
     p.addend = (const __nv_bfloat16*)ep.addend;
     p.gate = (const __nv_bfloat16*)ep.gate;
     p.y = (__nv_bfloat16*)y;

@@ -50,6 +50,7 @@ struct HaloParams {
     const float* noise_w;
     float slope, gain;
     int has_ep;
+    int f16;                             // 16-bit storage is IEEE half
     const __nv_bfloat16* addend;         // output-shaped side inputs (include/b200gan.h b200gan_conv_epilogue)
     const __nv_bfloat16* gate;
     int dbg;                             // B200GAN_HALO_DEBUG (timing experiments only): 1 no MMA, 2 no TMA loads, 4 no stores, 8 no tcgen05.ld
@@ -81,8 +82,7 @@ __device__ __forceinline__ void epilogue_math_store16(const HaloParams& p, float
     uint32_t pk[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        pk[e] = pack16x2(v[2 * e], v[2 * e + 1], p.f16);
     }
     uint4* d4 = reinterpret_cast<uint4*>(dst);
     d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -210,7 +210,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // uniform-datapath instructions per tile at ~7 clk each = the whole 1820-clk tile period, tensor pipe 17 %
         // active, the TMA producer and the epilogue warps waiting on it (profiles/r01_conv_issue_bound.md, r01_ncu_kernels.md).  Now the
         // taps are unrolled with immediate descriptor offsets and the tile decode is a multiply-high.
-        const uint32_t idesc = instr_desc_bf16(128, p.BN, 0, 0);
+        const uint32_t idesc = instr_desc_bf16(128, p.BN, 0, 0, p.f16);
         constexpr uint32_t PW = KDIM == 1 ? 8 : 16;
         constexpr uint32_t ROW_UNITS = ROWB >> 4;                        // descriptor units (16 B) per pixel
         constexpr int KSTEPS = ROWB / 32;                                // K = 16 elements = 32 B per MMA
@@ -312,7 +312,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     load16<true>(p.bias ? p.bias + c0 : nullptr, b16, 0.f);
                 }
                 if (SIDE && (p.addend || p.gate))
-                    side_apply16(v, p.addend ? &s_add : nullptr, p.gate ? &s_gate : nullptr, r16, p.gain, p.gain * p.slope);
+                    side_apply16(v, p.addend ? &s_add : nullptr, p.gate ? &s_gate : nullptr, r16, p.gain, p.gain * p.slope, p.f16);
                 epilogue_math_store16<true, SIDE>(p, v, dst + c0, r16, b16, nz);
             }
         };
@@ -393,7 +393,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const float* rs_g = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
                 mbar_wait(tfull + acc, acc_par);
                 tc_fence_after();
-                const float nz = (valid && p.noise) ? nw * __uint_as_float(nraw0 << 16) : 0.f;
+                const float nz = (valid && p.noise) ? nw * lo16(nraw0, p.f16) : 0.f;
                 fetch_noise(tile + 2 * gridDim.x);
                 prefetch_side(tile + 4 * (int)gridDim.x);
                 for (int c0 = 0; c0 < p.BN; c0 += 16) chunk(taddr, c0, dst, c0, rs_g, nz, valid);
@@ -407,8 +407,8 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 tc_fence_after();
                 float nz[4] = {0.f, 0.f, 0.f, 0.f};
                 if (valid && p.noise) {
-                    nz[0] = nw * __uint_as_float(nraw0 << 16); nz[1] = nw * __uint_as_float(nraw0 & 0xffff0000u);
-                    nz[2] = nw * __uint_as_float(nraw1 << 16); nz[3] = nw * __uint_as_float(nraw1 & 0xffff0000u);
+                    nz[0] = nw * lo16(nraw0, p.f16); nz[1] = nw * hi16(nraw0, p.f16);
+                    nz[2] = nw * lo16(nraw1, p.f16); nz[3] = nw * hi16(nraw1, p.f16);
                 }
                 fetch_noise(tile + 2 * gridDim.x);
                 prefetch_side(tile + 4 * (int)gridDim.x);
@@ -453,7 +453,7 @@ static bool halo_plan(const ConvGeom& g, HaloParams& p) {
 }
 
 bool conv_fwd_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* w, const void* y) {
-    if (dtype != B200GAN_BF16) return false;
+    if (dtype != B200GAN_BF16 && dtype != B200GAN_F16) return false;
     if (g.up != 1 || g.down != 1 || g.kh != g.kw || (g.kh != 1 && g.kh != 3)) return false;
     if (g.out_h < kHTH || g.out_w < kHTW) return false;
     if (g.out_h != g.in_h + 2 * g.pad0 - g.kh + 1 || g.out_w != g.in_w + 2 * g.pad0 - g.kw + 1) return false;
@@ -504,6 +504,7 @@ int conv_fwd_halo(const void* x, const void* w, void* y, const ConvGeom& g, cons
     p.bias = bias; p.rowscale = rowscale; p.noise = (const __nv_bfloat16*)noise; p.noise_w = noise_w;
     p.slope = slope; p.gain = gain;
     p.has_ep = ep_active(ep) ? 1 : 0;
+    p.f16 = g.f16;
     p.addend = (const __nv_bfloat16*)ep.addend;
     p.gate = (const __nv_bfloat16*)ep.gate;
     p.y = (__nv_bfloat16*)y;

@@ -151,6 +151,22 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float v[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- 16-bit storage: bfloat16 or (f16 != 0) IEEE half ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16) {
+    if (f16) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float lo16(uint32_t w, int f16) {
+    return f16 ? __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))) : __uint_as_float(w << 16);
+}
+__device__ __forceinline__ float hi16(uint32_t w, int f16) {
+    return f16 ? __half2float(__ushort_as_half((unsigned short)(w >> 16))) : __uint_as_float(w & 0xffff0000u);
+}
+
 // ---- epilogue side inputs: 16 consecutive bf16 of an output-shaped tensor (addend / gate, include/b200gan.h) ----------
 struct Side16 {
     uint4 a, b;
@@ -161,26 +177,26 @@ __device__ __forceinline__ Side16 side_load16(const __nv_bfloat16* p) {
     s.b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
     return s;
 }
-__device__ __forceinline__ void side_unpack16(const Side16& s, float (&o)[16]) {
+__device__ __forceinline__ void side_unpack16(const Side16& s, float (&o)[16], int f16) {
     const uint32_t w[8] = {s.a.x, s.a.y, s.a.z, s.a.w, s.b.x, s.b.y, s.b.z, s.b.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        o[2 * e] = __uint_as_float(w[e] << 16);
-        o[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        o[2 * e] = lo16(w[e], f16);
+        o[2 * e + 1] = hi16(w[e], f16);
     }
 }
 // v = (v + addend) [gate mode: * r * (gate > 0 ? g : gs)]; the forward activation is applied by the caller otherwise
 __device__ __forceinline__ void side_apply16(float (&v)[16], const Side16* addend, const Side16* gate, const float (&r)[16],
-                                             float g, float gs) {
+                                             float g, float gs, int f16) {
     if (addend) {
         float a[16];
-        side_unpack16(*addend, a);
+        side_unpack16(*addend, a, f16);
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] += a[e];
     }
     if (gate) {
         float y[16];
-        side_unpack16(*gate, y);
+        side_unpack16(*gate, y, f16);
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] *= r[e] * (y[e] > 0.f ? g : gs);
     }
@@ -200,11 +216,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B.
-__host__ __device__ inline uint32_t instr_desc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ inline uint32_t instr_desc_bf16(int m, int n, int a_mn_major, int b_mn_major, int f16 = 0) {
     uint32_t d = 0;
     d |= 1u << 4;                       // c_format = F32
-    d |= 1u << 7;                       // a_format = BF16
-    d |= 1u << 10;                      // b_format = BF16
+    if (!f16) {                         // kind::f16 operand formats: 0 = F16, 1 = BF16
+        d |= 1u << 7;                   // a_format = BF16
+        d |= 1u << 10;                  // b_format = BF16
+    }
     d |= (uint32_t)(a_mn_major & 1) << 15;
     d |= (uint32_t)(b_mn_major & 1) << 16;
     d |= (uint32_t)(n >> 3) << 17;

@@ -55,6 +55,7 @@ struct WgParams {
     int total_units;
     int sa_stages, sb_stages, a_slot_bytes, b_slot_bytes;
     int tmem_cols;
+    int f16;                 // operands are IEEE half instead of bfloat16
     float* gw;
 };
 
@@ -163,7 +164,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
     } else if (warp == 1) {
         // ================= MMA issuer (whole warp, elected lane issues) =================
-        const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1);        // both operands MN-major
+        const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1, p.f16);        // both operands MN-major
         const int ksteps = p.rows / 16;
         const uint32_t a_hi = desc_hi(8u * (uint32_t)p.rowb_m, (uint32_t)p.layout_m);
         const uint32_t b_hi = desc_hi(8u * (uint32_t)p.rowb_n, (uint32_t)p.layout_n);
@@ -262,7 +263,7 @@ static int wg_pow2_ge(int v, int lo) {
 }
 
 bool conv_wgrad_umma_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy) {
-    if (dtype != B200GAN_BF16) return false;
+    if (dtype != B200GAN_BF16 && dtype != B200GAN_F16) return false;
     if (g.kh * g.kw > kWgMaxTaps) return false;
     if (!((g.up == 1 && (g.down == 1 || g.down == 2)) || (g.up == 2 && g.down == 1))) return false;
     if (!(g.ic == 32 || g.ic == 64 || g.ic % 128 == 0)) return false;
@@ -278,6 +279,7 @@ int conv_wgrad_umma(const void* x, const void* gy, float* gw, const ConvGeom& g,
     p.B = g.b; p.IC = g.ic; p.OC = g.oc; p.taps_total = g.kh * g.kw; p.per_sample = g.w_per_sample;
     p.sa = g.up; p.sb = g.down;
     p.gw = gw;
+    p.f16 = g.f16;
     // operand geometry
     p.atom_m = g.ic >= 64 ? 64 : 32;
     p.rowb_m = p.atom_m * 2;

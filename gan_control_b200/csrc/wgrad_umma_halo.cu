@@ -34,6 +34,7 @@ struct WhParams {
     int x_packed, gy_packed, x_phase, gy_phase;
     int IC_total, OC_total, ic_off, oc_off;
     float* gw;
+    int f16;                 // operands are IEEE half instead of bfloat16
 };
 
 __global__ void __launch_bounds__(kWhThreads, 1)
@@ -105,7 +106,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = instr_desc_bf16(128, p.OC, 1, 1);
+        const uint32_t idesc = instr_desc_bf16(128, p.OC, 1, 1, p.f16);
         const uint32_t a_hi = desc_hi((uint32_t)(p.PW * p.rowb_m), (uint32_t)p.layout_m);     // next tile row of pixels
         const uint32_t b_hi = desc_hi(8u * (uint32_t)p.rowb_n, (uint32_t)p.layout_n);
         const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), (uint32_t)p.rowb_m);                  // LBO = one pixel = next kx
@@ -192,7 +193,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 }
 
 bool conv_wgrad_halo_eligible(int dtype, const ConvGeom& g, const void* x, const void* gy) {
-    if (dtype != B200GAN_BF16) return false;
+    if (dtype != B200GAN_BF16 && dtype != B200GAN_F16) return false;
     if (g.up != 1 || g.down != 1 || g.kh != g.kw || (g.kh != 1 && g.kh != 3)) return false;
     // a packed operand is processed as its two row-phase halves (see WhParams)
     const int ic = g.pack_in ? g.ic / 2 : g.ic, oc = g.pack_out ? g.oc / 2 : g.oc;
@@ -211,7 +212,7 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
     const int ic = g.pack_in ? g.ic / 2 : g.ic, oc = g.pack_out ? g.oc / 2 : g.oc;      // per launch (row-phase half)
     p.B = g.b; p.H = g.in_h; p.W = g.in_w; p.IC = ic; p.OC = oc; p.k = g.kh; p.pad0 = g.pad0;
     p.IC_total = g.ic; p.OC_total = g.oc; p.x_packed = g.pack_in; p.gy_packed = g.pack_out;
-    p.per_sample = g.w_per_sample; p.gw = gw;
+    p.per_sample = g.w_per_sample; p.gw = gw; p.f16 = g.f16;
     p.tiles_h = (g.out_h + kWhTH - 1) / kWhTH;
     p.tiles_w = (g.out_w + kWhTW - 1) / kWhTW;
     p.tiles_per_img = p.tiles_h * p.tiles_w;

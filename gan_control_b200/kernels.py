@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libb200gan.so')
 _lib = None
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 _c = ctypes
 _vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 
@@ -116,7 +116,9 @@ def _dt(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
-    raise TypeError(f'libb200gan supports float32 / bfloat16 activations, got {t.dtype}')
+    if t.dtype == torch.float16:
+        return F16
+    raise TypeError(f'libb200gan supports float32 / bfloat16 / float16 activations, got {t.dtype}')
 
 
 def _cuda(*ts):

@@ -14,7 +14,7 @@
  *  - plain C types only; tensors are raw device pointers + explicit sizes.
  *  - activations are NHWC ("channels last"): x[n][h][w][c], c contiguous.
  *    An NCHW-contiguous tensor (N,C,H,W) is the NHWC tensor (N*C,H,W,1).
- *  - `dtype`: B200GAN_F32 or B200GAN_BF16 storage; all arithmetic accumulates
+ *  - `dtype`: B200GAN_F32, B200GAN_BF16 or B200GAN_F16 storage; all arithmetic accumulates
  *    in fp32.  Reductions / weight gradients are always written as fp32.
  *  - every call is asynchronous on `stream` (a cudaStream_t), never allocates
  *    device memory, never synchronises, and is re-entrant.
@@ -33,6 +33,8 @@ extern "C" {
 
 #define B200GAN_F32 0
 #define B200GAN_BF16 1
+#define B200GAN_F16 2    /* IEEE half storage: the tensor-core PARITY mode (same tcgen05 kind::f16 instruction as bf16, operand
+                          * round-off 2^-11 instead of 2^-9; fp32 accumulation) */
 
 #define B200GAN_EINVAL (-1)   /* bad argument (shape / dtype / alignment)   */
 #define B200GAN_ENOSUP (-2)   /* configuration not supported by this build   */

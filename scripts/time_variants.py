@@ -1,5 +1,5 @@
 """Device time of each captured step variant (d, d_reg, g, g_reg) and the kernel table of one of them.
-    python scripts/time_variants.py [variant-to-profile]"""
+    python scripts/time_variants.py [variant-to-profile ...]"""
 import os
 import sys
 
@@ -34,10 +34,10 @@ for name in ('d', 'd_reg', 'g', 'g_reg'):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print(f'{name:6s} {sorted(ts)[1]:8.2f} ms   ({step.graph_launches[name]} libb200gan launches)', flush=True)
-which = sys.argv[1] if len(sys.argv) > 1 else None
-if which:
+for which in sys.argv[1:]:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step.graphs[which].replay()
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=60))
+    print(f'==== kernel table of one replay of the {which!r} graph ====')
+    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=90))

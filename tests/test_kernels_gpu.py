@@ -9,6 +9,7 @@ from oracle import kernels_ref as R
 
 pytestmark = pytest.mark.gpu
 DTYPES = [torch.float32, torch.bfloat16]
+DTYPES16 = [torch.float32, torch.bfloat16, torch.float16]
 
 
 def rnd(seed, *shape):
@@ -169,6 +170,10 @@ def test_blur_separable_taps(dt):
 CONV_CASES = [
     (2, 32, 32, 32, 3, 1, 1, 1, 0, True), (2, 16, 16, 3, 64, 1, 1, 1, 0, False), (3, 8, 8, 512, 3, 1, 1, 1, 0, True),
     (2, 16, 16, 3, 512, 1, 1, 1, 0, True), (2, 9, 9, 40, 2, 1, 1, 1, 0, False),
+    # register-weight pointwise kernels: every lanes-per-pixel / vectors-per-lane variant, ragged pixel counts
+    (2, 9, 9, 128, 3, 1, 1, 1, 0, True), (1, 11, 7, 256, 3, 1, 1, 1, 0, True), (2, 13, 13, 1024, 3, 1, 1, 1, 0, False),
+    (3, 5, 5, 64, 4, 1, 1, 1, 0, True), (2, 5, 5, 4, 128, 1, 1, 1, 0, True), (1, 33, 31, 3, 32, 1, 1, 1, 0, False),
+    (2, 7, 9, 2, 256, 1, 1, 1, 0, True), (2, 1, 1, 512, 3, 1, 1, 1, 0, True),
     # b, h, w, ic, oc, k, up, down, pad0, per_sample
     (2, 8, 8, 16, 32, 3, 1, 1, 1, False), (3, 7, 9, 8, 12, 3, 1, 1, 1, True), (2, 6, 6, 8, 6, 3, 2, 1, 2, True),
     (2, 9, 9, 16, 8, 3, 1, 2, 0, False), (2, 8, 8, 3, 32, 1, 1, 1, 0, False), (2, 4, 4, 513, 64, 3, 1, 1, 1, False),
@@ -182,7 +187,7 @@ def conv_out_hw(h, w, k, up, down, pad0):
     return (zh + 2 * pad0 - k) // down + 1, (zw + 2 * pad0 - k) // down + 1
 
 
-@pytest.mark.parametrize('dt', DTYPES)
+@pytest.mark.parametrize('dt', DTYPES16)
 @pytest.mark.parametrize('case', CONV_CASES)
 def test_conv_fwd_and_wgrad(case, dt):
     b, h, w, ic, oc, k, up, down, pad0, ps = case
@@ -253,11 +258,11 @@ UMMA_CASES = [
 ]
 
 
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize('case', UMMA_CASES)
-def test_conv_fwd_umma(case):
+def test_conv_fwd_umma(case, dt):
     """the tcgen05 engine against the fp64 contract stand-in, and against the CUDA-core engine"""
     b, h, w, ic, oc, k, up, down, pad0, ps = case
-    dt = torch.bfloat16
     if up == 2:
         oh, ow = (h - 1) * 2 + k - 2 * (k - 1 - pad0), (w - 1) * 2 + k - 2 * (k - 1 - pad0)
     else:
@@ -296,10 +301,10 @@ WGRAD_UMMA_CASES = UMMA_CASES[:8] + UMMA_CASES[9:] + [
 ]
 
 
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize('case', WGRAD_UMMA_CASES)
-def test_conv_wgrad_umma(case):
+def test_conv_wgrad_umma(case, dt):
     b, h, w, ic, oc, k, up, down, pad0, ps = case
-    dt = torch.bfloat16
     if up == 2:
         oh, ow = (h - 1) * 2 + k - 2 * (k - 1 - pad0), (w - 1) * 2 + k - 2 * (k - 1 - pad0)
     else:
@@ -334,11 +339,11 @@ HALO_CASES = [
 ]
 
 
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize('case', HALO_CASES)
-def test_conv_fwd_halo(case):
+def test_conv_fwd_halo(case, dt):
     """halo-reuse tcgen05 variant vs the general tcgen05 kernel (engine 2) and the fp64 stand-in"""
     b, h, w, ic, oc, k, ps = case
-    dt = torch.bfloat16
     pad0 = k // 2
     x, xr = prep(rnd(81, b, h, w, ic), dt)
     wt, wr = prep(rnd(82, b if ps else 1, k, k, oc, ic) / (ic * k * k) ** 0.5, dt)
@@ -359,11 +364,11 @@ def test_conv_fwd_halo(case):
     close(y_ep, R.conv_fwd(xr, wr, h, w, 1, 1, pad0, bias.double(), rs.double(), noiser, nw.double(), 0.2, 2 ** 0.5), dt, 'halo fwd+ep')
 
 
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize('case', [c for c in HALO_CASES if c[4] in (32, 64)] + [(16, 64, 64, 32, 32, 3, False)])
-def test_conv_wgrad_halo(case):
+def test_conv_wgrad_halo(case, dt):
     """halo-reuse weight-gradient kernel vs the general tcgen05 wgrad (engine 2) and the fp64 stand-in"""
     b, h, w, ic, oc, k, ps = case
-    dt = torch.bfloat16
     pad0 = k // 2
     x, xr = prep(rnd(91, b, h, w, ic), dt)
     gy, gyr = prep(rnd(92, b, h, w, oc), dt)
@@ -396,12 +401,12 @@ PACKED_CASES = [
 ]
 
 
+@pytest.mark.parametrize('dt', [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize('case', PACKED_CASES)
-def test_conv_packed(case):
+def test_conv_packed(case, dt):
     """packed forward (+ fused epilogue) and weight gradient on every engine that takes the shape, against the
     fp64 stand-in (which materialises the space-to-depth views)"""
     b, h, w, ic, oc, ps, pin, pout = case
-    dt = torch.bfloat16
     x, xr = prep(rnd(101, b, 2 * h, 2 * w, ic // 4) if pin else rnd(101, b, h, w, ic), dt)
     wt, wr = prep(rnd(102, b if ps else 1, 3, 3, oc, ic) / (ic * 9) ** 0.5, dt)
     ocp = oc // 4 if pout else oc
