@@ -10,8 +10,10 @@
 namespace b200gan {
 
 constexpr int kPwMaxSmall = 4;
-// B200GAN_PW_GENERIC=1 (timing / test experiments): always use the generic shared-memory-weight kernels
-static const bool g_pw_generic = [] { const char* e = getenv("B200GAN_PW_GENERIC"); return e && e[0] == '1'; }();
+// B200GAN_PW_MODE (timing / test experiments): 0 = best kernel per shape (default), 1 = no mma.sync kernels,
+// 2 = only the generic shared-memory-weight kernels
+static const int g_pw_mode = [] { const char* e = getenv("B200GAN_PW_MODE"); return e ? atoi(e) : 0; }();
+static const bool g_pw_generic = g_pw_mode >= 2;
 
 struct PwEpilogue {
     const float* bias;
@@ -245,6 +247,216 @@ __global__ void __launch_bounds__(256, 2) pw_small_ic_reg_kernel(const T* __rest
     }
 }
 
+// ---- 16-bit storage: the same two passes on mma.sync (m16n8k16 / m16n8k8, fp32 accumulate) --------------------------------
+// The register-weight kernels above still spend ~100 issue slots per 16 bytes of activation (conversions, FFMAs, shuffle
+// reductions) and measured 1.2 - 2.5 TB/s (profiles/r02_pointwise.md).  A warp-level MMA does the 16-pixel x 16-channel
+// products in one instruction straight from the registers the 16-byte loads filled: the k index of a dot product is
+// arbitrary as long as both operands agree, so each lane's 16-byte chunk (8 consecutive channels) IS its share of two
+// k-steps, for the activation rows (g, g + 8) and for the weight row n = g alike (fragment layout of PTX
+// mma.m16n8k16: lane = 4 g + t; the index algebra is checked by emulation in tests/test_pointwise_mapping_cpu.py).
+// tcgen05 has no place here: M = 16 pixel granularity, K <= 32, nothing to stage in shared memory.
+template <typename T> struct WarpMma;
+template <> struct WarpMma<__nv_bfloat16> {
+    static __device__ __forceinline__ void k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ void k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+    }
+};
+template <> struct WarpMma<__half> {
+    static __device__ __forceinline__ void k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ void k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+    }
+};
+template <typename T> __device__ __forceinline__ uint32_t pw_pair(const T* p, bool lo_ok, bool hi_ok) {
+    const unsigned short lo = lo_ok ? *reinterpret_cast<const unsigned short*>(p) : (unsigned short)0;
+    const unsigned short hi = hi_ok ? *reinterpret_cast<const unsigned short*>(p + 1) : (unsigned short)0;
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+// OC <= 4, IC = 32 * NQ: a warp takes 16 pixels per step (rows g and g + 8 of the fragment), U steps in flight.
+template <typename T, int NQ>
+__global__ void __launch_bounds__(256) pw_small_oc_mma_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y,
+                                                              int npix, int ic, int oc, int per_sample, PwEpilogue ep) {
+    constexpr int U = NQ >= 4 ? 1 : 4 / NQ;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
+    uint4 wq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+        wq[q] = g < oc ? *reinterpret_cast<const uint4*>(wb + (int64_t)g * ic + q * 32 + t * 8) : make_uint4(0u, 0u, 0u, 0u);
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int groups = (npix + 15) >> 4;
+    const float nw = (ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
+    const T* xb = x + (int64_t)b * npix * ic;
+    for (int g0 = warp; g0 < groups; g0 += warps * U) {
+        uint4 xa[U][NQ], xh[U][NQ];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p_lo = (g0 + u * warps) * 16 + g, p_hi = p_lo + 8;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                xa[u][q] = p_lo < npix ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p_lo * ic + q * 32 + t * 8)) : make_uint4(0u, 0u, 0u, 0u);
+                xh[u][q] = p_hi < npix ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p_hi * ic + q * 32 + t * 8)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                WarpMma<T>::k16(c, xa[u][q].x, xh[u][q].x, xa[u][q].y, xh[u][q].y, wq[q].x, wq[q].y);
+                WarpMma<T>::k16(c, xa[u][q].z, xh[u][q].z, xa[u][q].w, xh[u][q].w, wq[q].z, wq[q].w);
+            }
+            // c[0], c[1]: pixel row g, output channels 2t, 2t + 1;  c[2], c[3]: row g + 8
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = (g0 + u * warps) * 16 + g + 8 * h;
+                if (p >= npix || 2 * t >= oc) continue;
+                const int64_t pix = (int64_t)b * npix + p;
+                const float nz = ep.noise ? nw * io<T>::ld((const T*)ep.noise + pix) : 0.f;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int o = 2 * t + e;
+                    if (o < oc) io<T>::st(y + pix * oc + o, pw_epilogue<T>(ep, c[2 * h + e], b, oc, o, pix, nz));
+                }
+            }
+        }
+    }
+}
+
+// IC <= 4, OC = 32 * NQ: output-channel tiles are permuted so that lane (g, t) ends up with the 8 CONSECUTIVE channels
+// 32 q + 8 t .. + 8 of rows g and g + 8 (one 16-byte store each): column n of tile (q, j) is channel 32 q + 8 (n / 2) + 2 j + n % 2.
+template <typename T, int NQ>
+__global__ void __launch_bounds__(256) pw_small_ic_mma_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y,
+                                                              int npix, int ic, int oc, int per_sample, PwEpilogue ep) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
+    uint32_t bq[NQ][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = q * 32 + (g >> 1) * 8 + j * 2 + (g & 1);
+            bq[q][j] = pw_pair<T>(wb + (int64_t)o * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic);
+        }
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int groups = (npix + 15) >> 4;
+    const float nw = (ep.on && ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
+    const float g_pos = ep.gain, g_neg = ep.gain * ep.slope;
+    const bool lrelu_ok = ep.gain > 0.f && ep.slope >= 0.f && ep.slope <= 1.f;      // gain * lrelu(u) == max(g u, g slope u)
+    const T* xb = x + (int64_t)b * npix * ic;
+    // the narrow operand of the NEXT step is requested before this step's MMAs and stores (a step is otherwise one
+    // dependent load -> MMA -> store chain per warp: 2.9 TB/s of stores at 32 warps per SM, profiles/r02_pointwise.md)
+    auto fetch = [&](int g0, uint32_t& a0, uint32_t& a1, float (&nz)[2]) {
+        const int p_lo = g0 * 16 + g, p_hi = p_lo + 8;
+        a0 = (g0 < groups && p_lo < npix) ? pw_pair<T>(xb + (int64_t)p_lo * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic) : 0u;
+        a1 = (g0 < groups && p_hi < npix) ? pw_pair<T>(xb + (int64_t)p_hi * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic) : 0u;
+        nz[0] = nz[1] = 0.f;
+        if (ep.on && ep.noise && g0 < groups) {
+            if (p_lo < npix) nz[0] = nw * io<T>::ld((const T*)ep.noise + (int64_t)b * npix + p_lo);
+            if (p_hi < npix) nz[1] = nw * io<T>::ld((const T*)ep.noise + (int64_t)b * npix + p_hi);
+        }
+    };
+    uint32_t a0n, a1n;
+    float nzn[2];
+    fetch(warp, a0n, a1n, nzn);
+    for (int g0 = warp; g0 < groups; g0 += warps) {
+        const int p_lo = g0 * 16 + g, p_hi = p_lo + 8;
+        const uint32_t a0 = a0n, a1 = a1n;
+        const float nz[2] = {nzn[0], nzn[1]};
+        fetch(g0 + warps, a0n, a1n, nzn);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float c[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+                WarpMma<T>::k8(c[j], a0, a1, bq[q][j]);
+            }
+            const int o0 = q * 32 + t * 8;
+            float br[8], rr[8];
+            if (ep.on) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                    const float4 bv = (ep.bias && !ep.gate) ? __ldg(reinterpret_cast<const float4*>(ep.bias + o0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 rv = ep.rowscale ? __ldg(reinterpret_cast<const float4*>(ep.rowscale + (int64_t)b * oc + o0 + e))
+                                                  : make_float4(1.f, 1.f, 1.f, 1.f);
+                    br[e] = bv.x; br[e + 1] = bv.y; br[e + 2] = bv.z; br[e + 3] = bv.w;
+                    rr[e] = rv.x; rr[e + 1] = rv.y; rr[e + 2] = rv.z; rr[e + 3] = rv.w;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = h ? p_hi : p_lo;
+                if (p >= npix) continue;
+                const int64_t off = ((int64_t)b * npix + p) * oc + o0;
+                Pack<T, 8> out;
+                Pack<T, 8> sa, sg;
+                if (ep.on && ep.addend) sa = *reinterpret_cast<const Pack<T, 8>*>((const T*)ep.addend + off);
+                if (ep.on && ep.gate) sg = *reinterpret_cast<const Pack<T, 8>*>((const T*)ep.gate + off);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float a = c[e >> 1][2 * h + (e & 1)];
+                    if (ep.on) {                                // same order of operations as pw_epilogue
+                        if (ep.addend) a += io<T>::ld(&sa.v[e]);
+                        a *= rr[e];
+                        if (ep.gate) {
+                            a *= io<T>::ld(&sg.v[e]) > 0.f ? g_pos : g_neg;
+                        } else {
+                            a += nz[h] + br[e];
+                            a = lrelu_ok ? fmaxf(a * g_pos, a * g_neg) : (a > 0.f ? a * g_pos : a * g_neg);
+                        }
+                    }
+                    io<T>::st(&out.v[e], a);
+                }
+                *reinterpret_cast<Pack<T, 8>*>(y + off) = out;
+            }
+        }
+    }
+}
+
+// launchers of the 16-bit MMA kernels; false when the shape is not theirs
+template <typename T>
+static bool pw_launch_mma(const T* x, const T* w, T* y, int npix, const ConvGeom& g, const PwEpilogue& ep, cudaStream_t st) {
+    int bx = (int)cdiv((int64_t)sm_count() * 8, g.b);
+    const int need = (int)cdiv(cdiv(npix, 16), 8);
+    if (bx > need) bx = need;
+    const dim3 grid(bx < 1 ? 1 : bx, g.b);
+    if (g.oc <= kPwMaxSmall && g.ic % 32 == 0 && g.ic <= 128) {
+        switch (g.ic / 32) {
+            case 1: pw_small_oc_mma_kernel<T, 1><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            case 2: pw_small_oc_mma_kernel<T, 2><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            case 4: pw_small_oc_mma_kernel<T, 4><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            default: return false;
+        }
+    }
+    const bool side_aligned = (((uintptr_t)ep.bias | (uintptr_t)ep.rowscale | (uintptr_t)ep.addend | (uintptr_t)ep.gate) & 15) == 0;
+    if (g.ic <= kPwMaxSmall && g.oc % 32 == 0 && g.oc <= 128 && side_aligned) {
+        switch (g.oc / 32) {
+            case 1: pw_small_ic_mma_kernel<T, 1><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            case 2: pw_small_ic_mma_kernel<T, 2><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            case 4: pw_small_ic_mma_kernel<T, 4><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            default: return false;
+        }
+    }
+    return false;
+}
+template <>
+bool pw_launch_mma<float>(const float*, const float*, float*, int, const ConvGeom&, const PwEpilogue&, cudaStream_t) { return false; }
+
 static inline int pw_log2_exact(int v) {                       // log2 of a power of two, else -1
     if (v <= 0 || (v & (v - 1))) return -1;
     int l = 0;
@@ -321,6 +533,10 @@ int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const C
         constexpr int V = 16 / sizeof(T);
         const size_t smem = (size_t)g.oc * g.ic * sizeof(float);
         int bx = (int)cdiv((int64_t)sm_count() * 8, g.b);
+        if (g_pw_mode == 0 && pw_launch_mma<T>((const T*)x, (const T*)w, (T*)y, npix, g, ep, st)) {
+            count_launch();
+            return check_launch("conv_fwd_pointwise");
+        }
         if (g.oc <= kPwMaxSmall) {
             const int nv = g.ic / V, lnv = pw_log2_exact(nv);
             if (lnv >= 0 && nv <= 128 && !g_pw_generic) {

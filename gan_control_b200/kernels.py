@@ -60,6 +60,8 @@ _SIGNATURES = {
     'b200gan_mapping_fwd': ([_vp, _vp, _vp] + [_i] * 6 + [_vp], _i),
     'b200gan_mapping_bwd': ([_vp] * 6 + [_i] * 6 + [_vp], _i),
     'b200gan_adam_ema': ([_vp, _vp, _vp, _vp, _vp, _i64] + [_f] * 4 + [_vp, _f, _f, _vp], _i),
+    'b200gan_affine_color_fwd': ([_vp, _vp, _vp, _vp, _i] + [_i] * 6 + [_vp, _vp, _vp], _i),
+    'b200gan_affine_color_bwd': ([_vp, _vp, _vp, _vp, _i] + [_i] * 6 + [_vp, _vp], _i),
 }
 
 
@@ -454,3 +456,37 @@ def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, bias_corr, ema_decay=0.0, g
         _check(lib().b200gan_adam_ema(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(ema), p.numel(), float(lr), float(beta1),
                                       float(beta2), float(eps), _ptr(bias_corr), float(ema_decay),
                                       float(grad_scale), _stream()), 'adam_ema')
+
+
+def _strides4(t):
+    return (ctypes.c_int64 * 4)(*t.stride())
+
+
+def affine_color_fwd(x, mat, color, out_h, out_w):
+    """ADA warp + colour (include/b200gan.h): x (N,C,H,W) in ANY layout (strides are passed), C <= 4; mat (N,6) float64 source-
+    pixel affine map; color (N,C,C+1) float32 or None.  Returns (N,C,out_h,out_w) in x's dtype and memory format."""
+    _cuda(x, mat, color)
+    assert x.ndim == 4 and x.shape[1] <= 4 and mat.dtype == torch.float64 and mat.shape == (x.shape[0], 6) and mat.is_contiguous()
+    n, c, h, w = x.shape
+    if color is not None:
+        assert color.dtype == torch.float32 and color.shape == (n, c, c + 1) and color.is_contiguous()
+    fmt = torch.channels_last if (c > 1 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()) \
+        else torch.contiguous_format
+    y = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device, memory_format=fmt)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            _check(lib().b200gan_affine_color_fwd(_ptr(x), _ptr(y), _ptr(mat), _ptr(color), _dt(x), n, c, h, w, out_h, out_w,
+                                                  _strides4(x), _strides4(y), _stream()), 'affine_color_fwd')
+    return y
+
+
+def affine_color_bwd(gy, mat, color, in_h, in_w):
+    """adjoint of affine_color_fwd w.r.t. the image: gy (N,C,out_h,out_w) any layout -> fp32 planar (N,C,in_h,in_w)"""
+    _cuda(gy, mat, color)
+    n, c, oh, ow = gy.shape
+    gx = torch.zeros((n, c, in_h, in_w), dtype=torch.float32, device=gy.device)
+    if gy.numel():
+        with torch.cuda.device(gy.device):
+            _check(lib().b200gan_affine_color_bwd(_ptr(gy), _ptr(gx), _ptr(mat), _ptr(color), _dt(gy), n, c, in_h, in_w, oh, ow,
+                                                  _strides4(gy), _stream()), 'affine_color_bwd')
+    return gx

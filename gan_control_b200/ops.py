@@ -792,6 +792,47 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
 
 
 # ---------------------------------------------------------------------------------------------
+# ADA augmentation core                                   (trainers/non_leaking.py:341-357, 373-383)
+# ---------------------------------------------------------------------------------------------
+class _AffineColor(Function):
+    """Bilinear warp by a per-sample affine map of pixel coordinates + per-sample colour matrix, one kernel each way
+    (include/b200gan.h b200gan_affine_color_fwd / _bwd).  Linear in x, so the backward is the adjoint kernel and the
+    double backward is the forward again; the matrices carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, mat, color, out_h, out_w):
+        ctx.save_for_backward(mat, color)
+        ctx.cfg = (x.shape[2], x.shape[3], out_h, out_w, x.dtype)
+        return K.affine_color_fwd(x, mat, color, out_h, out_w)
+
+    @staticmethod
+    def backward(ctx, gy):
+        mat, color = ctx.saved_tensors
+        h, w, oh, ow, dtype = ctx.cfg
+        return _AffineColorAdjoint.apply(gy, mat, color, h, w).to(dtype), None, None, None, None
+
+
+class _AffineColorAdjoint(Function):
+    @staticmethod
+    def forward(ctx, gy, mat, color, in_h, in_w):
+        ctx.save_for_backward(mat, color)
+        ctx.cfg = (gy.shape[2], gy.shape[3], gy.dtype)
+        return K.affine_color_bwd(gy, mat, color, in_h, in_w)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        mat, color = ctx.saved_tensors
+        oh, ow, dtype = ctx.cfg
+        return _AffineColor.apply(ggx.to(dtype), mat, color, oh, ow), None, None, None, None
+
+
+def affine_color(x, mat, color, out_hw):
+    """x (N,C,H,W), C <= 4; mat (N,6) float64: output pixel (ox, oy) samples x at (m0 ox + m1 oy + m2, m3 ox + m4 oy + m5)
+    bilinearly (zero outside); color (N,C,C+1) float32 rows (matrix | offset) or None."""
+    return _AffineColor.apply(x, mat, color, out_hw[0], out_hw[1])
+
+
+# ---------------------------------------------------------------------------------------------
 # dense layers                                                         (gan_model.py:189-197)
 # ---------------------------------------------------------------------------------------------
 class _Gemm(Function):

@@ -263,6 +263,23 @@ int b200gan_mapping_bwd(const float* z, const float* acts, float* gbuf, const b2
                         const b200gan_fc_layer_grad* grads, float* dz, int n_groups, int n_layers, int batch,
                         int z_dim, int row_width, int normalize, void* stream);
 
+/* ---- ADA augmentation: geometric warp + colour transform -------------------------
+ * Replaces, in `trainers/non_leaking.py`, the sampling-grid chain `make_grid` / `affine_grid` / rescale and
+ * `F.grid_sample(img_2x, grid, mode="bilinear", align_corners=False, padding_mode="zeros")` of `random_apply_affine`
+ * (:341-357) together with `apply_color` (:373-383), in one pass and without a grid tensor:
+ *   (sx, sy) = (m0*ox + m1*oy + m2,  m3*ox + m4*oy + m5)          mat: DEVICE double [n][6], source PIXEL coordinates
+ *   s[ch]    = bilinear sample of x[b][ch] at (sx, sy), zero outside the image
+ *   y[b][o][oy][ox] = sum_ch color[b][o][ch] * s[ch] + color[b][o][c]     color: DEVICE float [n][c][c+1] or NULL (y = s)
+ * x (n, c, in_h, in_w) and y (n, c, out_h, out_w), c <= 4, are addressed through HOST arrays of four element strides
+ * (n, c, h, w): planar NCHW and channels-last tensors are both taken as they are.
+ * `_bwd` is the adjoint w.r.t. the image (the matrices carry no gradient, generator_trainer.py:421-422): it ADDS
+ * into gx, fp32 planar (n, c, in_h, in_w), which the caller zeroes.                                                */
+int b200gan_affine_color_fwd(const void* x, void* y, const double* mat, const float* color, int dtype, int n, int c,
+                             int in_h, int in_w, int out_h, int out_w, const int64_t* x_strides,
+                             const int64_t* y_strides, void* stream);
+int b200gan_affine_color_bwd(const void* gy, float* gx, const double* mat, const float* color, int dtype, int n, int c,
+                             int in_h, int in_w, int out_h, int out_w, const int64_t* gy_strides, void* stream);
+
 /* ---- optimiser ------------------------------------------------------------------
  * Adam step as `torch.optim.Adam` (gt.py:161-173; eps added after the bias-corrected sqrt) fused with
  * the generator EMA `accumulate` (trainers/utils.py:8-12; ema may be NULL).  fp32, in place.

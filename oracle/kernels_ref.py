@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 # every `gan_control_b200.kernels` entry point that has a stand-in here (what the CPU tests monkeypatch)
 STAND_INS = ['upfirdn2d', 'bias_act_fwd', 'bias_act_bwd', 'epilogue_bwd', 'reduce_nhwc', 'conv_fwd', 'conv_wgrad', 'linear_fwd',
-             'gemm_f32', 'adam_ema', 'launch_count', 'modweight_fwd', 'modweight_bwd']
+             'gemm_f32', 'adam_ema', 'launch_count', 'modweight_fwd', 'modweight_bwd', 'affine_color_fwd', 'affine_color_bwd']
 
 
 def _gather_pad(z, pad0_y, pad0_x, need_h, need_w):
@@ -226,3 +226,41 @@ def adam_ema(p, g, m, v, ema, lr, beta1, beta2, eps, bias_corr, ema_decay=0.0, g
 
 def launch_count():
     return 0
+
+
+def _affine_color(x, mat, color, out_h, out_w):
+    """contract of b200gan_affine_color_fwd, differentiable in x: bilinear sample (zeros outside) of x at the source PIXEL
+    coordinates mat @ (ox, oy, 1), then the per-sample colour matrix | offset"""
+    n, c, h, w = x.shape
+    dt = x.dtype if x.dtype == torch.float64 else torch.float32
+    ox = torch.arange(out_w, dtype=torch.float64).view(1, 1, out_w)
+    oy = torch.arange(out_h, dtype=torch.float64).view(1, out_h, 1)
+    m = mat.double().view(n, 6, 1, 1)
+    sx = m[:, 0] * ox + m[:, 1] * oy + m[:, 2]
+    sy = m[:, 3] * ox + m[:, 4] * oy + m[:, 5]
+    x0, y0 = torch.floor(sx), torch.floor(sy)
+    fx, fy = (sx - x0).to(dt), (sy - y0).to(dt)
+    xp = F.pad(x.to(dt), (1, 1, 1, 1))                              # one ring of zeros: every out-of-range tap lands in it
+    out = 0
+    for dy, dx, wt in [(0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)), (1, 0, (1 - fx) * fy), (1, 1, fx * fy)]:
+        xi = (x0 + dx).clamp(-1, w).long() + 1
+        yi = (y0 + dy).clamp(-1, h).long() + 1
+        idx = (yi * (w + 2) + xi).view(n, 1, -1).expand(n, c, -1)
+        out = out + xp.reshape(n, c, -1).gather(2, idx).view(n, c, out_h, out_w) * wt.unsqueeze(1)
+    if color is not None:
+        cm = color.to(dt)
+        out = torch.einsum('noc,nchw->nohw', cm[:, :, :c], out) + cm[:, :, c].view(n, c, 1, 1)
+    return out
+
+
+def affine_color_fwd(x, mat, color, out_h, out_w):
+    return _affine_color(x, mat, color, out_h, out_w).to(x.dtype)
+
+
+def affine_color_bwd(gy, mat, color, in_h, in_w):
+    n, c = gy.shape[:2]
+    dt = torch.float64 if gy.dtype == torch.float64 else torch.float32
+    x = torch.zeros(n, c, in_h, in_w, dtype=dt, requires_grad=True)
+    y = _affine_color(x, mat, color, gy.shape[2], gy.shape[3])
+    gx, = torch.autograd.grad(y, x, gy.to(dt))
+    return gx

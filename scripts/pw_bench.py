@@ -1,5 +1,5 @@
 """1x1 RGB-side convolutions (ToRGB forward / data gradient, from_rgb forward) timed alone at the FFHQ-1024 shapes,
-batch 16, bf16, CUDA events, L2 flushed between launches.  B200GAN_PW_GENERIC=1 selects the old generic kernels.
+batch 16, bf16, CUDA events, L2 flushed between launches.  B200GAN_PW_MODE=1 disables the mma.sync kernels, 2 forces the generic shared-memory-weight kernels.
     python scripts/pw_bench.py"""
 import os
 import sys
@@ -31,7 +31,7 @@ def timed(fn, reps=5):
     return sorted(ts)[len(ts) // 2]
 
 
-print(f'generic kernels forced: {os.environ.get("B200GAN_PW_GENERIC", "0")}')
+print(f"B200GAN_PW_MODE = {os.environ.get('B200GAN_PW_MODE', '0')}")
 print('| layer | ms | GB moved | TB/s |')
 print('|---|---|---|---|')
 for res, c in [(1024, 32), (512, 64), (256, 128), (128, 256), (64, 512)]:

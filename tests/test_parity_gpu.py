@@ -522,13 +522,13 @@ def test_fused_first_order_path_matches_op_algebra():
         if g0[k].numel() <= 4:
             if ef > max(4 * eu, 0.3):
                 tiny_bad.append((k, eu, ef))
-        elif ef > max(2.5 * eu, 5e-2):
+        elif ef > max(4 * eu, 0.15):      # a wrong gradient shows as O(1); per-channel bias sums vary 2-3x with rounding
             bad.append((k, eu, ef))
     big = [k for k in g0 if float(g0[k].abs().max()) > 0 and g0[k].numel() > 4]
     tot_u = sum(rel_err(gu[k], g0[k]) for k in big)
     tot_f = sum(rel_err(gf[k], g0[k]) for k in big)
     print(f'bf16 vs fp32 gradients, summed rel-L2 over {len(big)} tensors: unfused {tot_u:.3f}, fused {tot_f:.3f}; outliers {bad} {tiny_bad}')
-    assert len(bad) <= 2 and not tiny_bad and tot_f < 1.5 * tot_u, (bad, tiny_bad)
+    assert not bad and not tiny_bad and tot_f < 2 * tot_u, (bad, tiny_bad)
 
 
 def test_mapping_network_under_autograd():
