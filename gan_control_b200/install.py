@@ -11,7 +11,9 @@ construction time (`gm.py:87,127,192,400,885`) and the CUDA-op package location
 
 `install()` (1) registers `gan_control.models.op` exporting `upfirdn2d, FusedLeakyReLU,
 fused_leaky_relu, conv2d_gradfix`, (2) replaces the operator names inside
-`gan_control.models.gan_model`.  `state_dict` keys and shapes are unchanged, so checkpoints written by
+`gan_control.models.gan_model`, (3) if `gan_control.trainers.non_leaking` is (or later gets) imported,
+`install_augment()` swaps its `augment / random_apply_affine / random_apply_color` for the fused ones
+(`gan_control_b200.augment`: same signatures, same random draws).  `state_dict` keys and shapes are unchanged, so checkpoints written by
 either side load in the other.
 """
 import sys
@@ -54,4 +56,23 @@ def install(gan_model=None):
     for name in PATCHED_CLASSES:
         setattr(gan_model, name, getattr(modules, name))
     gan_model.B200GAN_INSTALLED = True
+    nl = sys.modules.get('gan_control.trainers.non_leaking')
+    if nl is not None and hasattr(nl, 'random_apply_affine'):       # the real module (not a test stub) is loaded
+        install_augment(nl)
     return gan_model
+
+
+def install_augment(non_leaking=None):
+    """Replace the image work of `gan_control.trainers.non_leaking` (ADA, :314-392) by the three-kernel path of
+    `gan_control_b200.augment`; the samplers keep drawing on the host.  `generator_trainer` binds `augment` by name at
+    import (`from ...non_leaking import augment`, gt.py:28), so call this before importing the trainer, or pass the
+    trainer module to have its binding replaced as well."""
+    from . import augment as A
+    if non_leaking is None:
+        import gan_control.trainers.non_leaking as non_leaking
+    for name in ('augment', 'random_apply_affine', 'random_apply_color'):
+        setattr(non_leaking, name, getattr(A, name))
+    trainer = sys.modules.get('gan_control.trainers.generator_trainer')
+    if trainer is not None and hasattr(trainer, 'augment'):
+        trainer.augment = A.augment
+    return non_leaking

@@ -51,7 +51,7 @@ def train(config, save_dir=None, iters=None, data=None, device='cuda', act_dtype
     if data is None:
         data = synthetic_images(step.batch, mc['size'], mc['img_channels'], device, seed=rank)
     if use_graphs is None:
-        use_graphs = torch.device(device).type == 'cuda'
+        use_graphs = torch.device(device).type == 'cuda' and step.ada is None
     if use_graphs:
         step.capture((step.batch, mc['img_channels'], mc['size'], mc['size']))
     run = step.train_step_graphed if use_graphs else step.train_step

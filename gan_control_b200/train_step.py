@@ -297,17 +297,16 @@ class GradBuckets:
 def unbuilt_objective_terms(config):
     """What a gan-control config asks for that this step does NOT do.  The reference applies, when `model_config.vanilla`
     is false, every enabled `training_config.*_loss` (embedding / orientation / expression / age / hair / ..., gt.py:205-
-    300, 431-434) on batches arranged by `MiniBatchUtils.re_arrange_z`; independently it applies ADA augmentation
-    (`augment.enabled`, gt.py:647-653), `d_every` (gt.py:351), and a transfer-learning initialisation (gt.py:134-143).
-    This path builds the adversarial + R1 + path-length objective only (SURVEY.md section 8 scope), so a config that
-    relies on any of the above would silently train something else."""
+    300, 431-434) on batches arranged by `MiniBatchUtils.re_arrange_z`; independently it applies `d_every` (gt.py:351)
+    and a transfer-learning initialisation (gt.py:134-143).  This path builds the adversarial + R1 + path-length
+    objective, with ADA augmentation (`augment.enabled`, gt.py:421-422, 647-653: `gan_control_b200.augment`) when the
+    config asks for it (SURVEY.md section 8 scope), so a config that relies on any of the above would silently train
+    something else."""
     mc, tc = config['model_config'], config['training_config']
     out = []
     if not mc.get('vanilla', False):
         out += [f'{k} (attribute loss)' for k, v in tc.items() if k.endswith('_loss') and isinstance(v, dict)
                 and v.get('enabled')]
-    if (tc.get('augment') or {}).get('enabled'):
-        out.append('augment (ADA)')
     if tc.get('d_every', 1) != 1:
         out.append(f"d_every={tc['d_every']}")
     if (tc.get('transfer_learning_model') or {}).get('enabled'):
@@ -320,13 +319,18 @@ class GanTrainStep:
 
     def __init__(self, generator, discriminator, g_ema=None, batch=16, lr_g=0.002, lr_d=0.002, r1=1.0,
                  d_reg_every=16, g_reg_every=4, path_regularize=2.0, path_batch_shrink=2, mixing=0.0,
-                 g_moving_average=10000, latent_size=512, world_size=1, bucket_mb=8, global_batch=None):
+                 g_moving_average=10000, latent_size=512, world_size=1, bucket_mb=8, global_batch=None, ada=None):
         self.g, self.d, self.g_ema = generator, discriminator, g_ema
         self.batch, self.world = batch, world_size
         self.global_batch = global_batch or batch * world_size
         self.r1, self.d_reg_every, self.g_reg_every = r1, d_reg_every, g_reg_every
         self.path_regularize, self.path_batch_shrink, self.mixing = path_regularize, path_batch_shrink, mixing
         self.latent_size = latent_size
+        # ADA (gt.py:333-337): None, a fixed probability, or an `augment.AdaptiveP` controller
+        if ada is not None and not hasattr(ada, 'update'):
+            from .augment import AdaptiveP
+            ada = AdaptiveP(p=float(ada))
+        self.ada = ada
         self.device = next(generator.parameters()).device
         self.mean_path_length = torch.zeros((), device=self.device, dtype=next(generator.parameters()).dtype)
         self.accum = 0.5 ** (self.global_batch / g_moving_average)                       # gt.py:332
@@ -398,10 +402,15 @@ class GanTrainStep:
                   g_reg_every=tc['g_reg_every'], path_regularize=tc['path_regularize'],
                   path_batch_shrink=tc['path_batch_shrink'], mixing=tc['mixing'], g_moving_average=tc['g_moving_average'],
                   latent_size=mc['latent_size'], world_size=world_size, global_batch=tc['batch'])
+        aug = tc.get('augment') or {}
+        if aug.get('enabled'):
+            from .augment import AdaptiveP
+            kw['ada'] = AdaptiveP(p=aug.get('p', 0), ada_target=aug.get('ada_target', 0.6), ada_length=aug.get('ada_length', 500000))
         kw.update(overrides)
         step = cls(g, d, g_ema, **kw)
         step.config = config
-        step.effective_objective = {'terms': ['adversarial (non-saturating / logistic)', 'r1', 'path_length'],
+        step.effective_objective = {'terms': ['adversarial (non-saturating / logistic)', 'r1', 'path_length'] +
+                                             (['ada_augment'] if step.ada is not None else []),
                                     'ignored_config_terms': dropped}
         ck = config.get('ckpt_config') or {}
         if ck.get('enabled'):
@@ -456,6 +465,10 @@ class GanTrainStep:
         with torch.no_grad():
             styles, kw = self._styles(self.batch, noise)
             fake_img, _ = self.g(styles, **kw)
+            if self.ada is not None:                 # gt.py:651-653: both batches, independent draws
+                from .augment import augment
+                real_img, _ = augment(real_img, self.ada.p)
+                fake_img, _ = augment(fake_img, self.ada.p)
         with first_order():                          # plain step: no double backward -> fused single-kernel layers
             fake_pred, _ = self.d(fake_img)
             real_pred, _ = self.d(real_img)
@@ -465,6 +478,8 @@ class GanTrainStep:
             d_loss.backward()
             self.d_buckets.finish()
         self.d_optim.step(grad_scale=1.0 / self.world, buckets=self.d_buckets)
+        if self.ada is not None:
+            self.ada.update(real_pred)               # r_t statistic and the adaptive probability (gt.py:669-687; host sync)
         self.stats['d_loss'] = d_loss.detach()
         return d_loss.detach()
 
@@ -490,6 +505,9 @@ class GanTrainStep:
         with first_order():
             styles, kw = self._styles(self.batch, noise)
             fake_img, _ = self.g(styles, **kw)
+            if self.ada is not None:                 # gt.py:421-422: the generator is trained through the augmentation
+                from .augment import augment
+                fake_img, _ = augment(fake_img, self.ada.p)
             fake_pred, _ = self.d(fake_img)
             g_loss = g_nonsaturating_loss(fake_pred)
             self.g_buckets.begin()
@@ -584,6 +602,9 @@ class GanTrainStep:
     def capture(self, real_shape, warmup=2):
         """Capture discriminator_step / generator_step (+ their regularised variants) into CUDA graphs
         reading from a static image buffer.  Style mixing is drawn on the device (`_styles`), so it is captured too."""
+        if self.ada is not None:
+            raise RuntimeError('ADA augmentation draws its transforms (and the padding they need) on the host every step: '
+                               'run `train_step` eagerly, CUDA-graph capture is for the un-augmented step')
         self.static_real = torch.zeros(real_shape, device=self.device)
         snapshot = self._snapshot()          # the warm-up runs are real optimiser steps on a dummy batch: undone below
         side = torch.cuda.Stream()

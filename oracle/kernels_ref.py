@@ -260,7 +260,8 @@ def affine_color_fwd(x, mat, color, out_h, out_w):
 def affine_color_bwd(gy, mat, color, in_h, in_w):
     n, c = gy.shape[:2]
     dt = torch.float64 if gy.dtype == torch.float64 else torch.float32
-    x = torch.zeros(n, c, in_h, in_w, dtype=dt, requires_grad=True)
-    y = _affine_color(x, mat, color, gy.shape[2], gy.shape[3])
-    gx, = torch.autograd.grad(y, x, gy.to(dt))
+    with torch.enable_grad():                                     # (called from inside an autograd Function's forward)
+        x = torch.zeros(n, c, in_h, in_w, dtype=dt, requires_grad=True)
+        y = _affine_color(x, mat, color, gy.shape[2], gy.shape[3])
+        gx, = torch.autograd.grad(y, x, gy.detach().to(dt))
     return gx

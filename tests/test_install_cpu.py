@@ -115,6 +115,12 @@ def test_from_config_matches_reference_construction(name):
     with pytest.warns(UserWarning, match='IGNORED config terms'):
         step = GanTrainStep.from_config(cfg, device='cpu', world_size=4, act_dtype=torch.float32, vanilla_only=True)
     assert step.effective_objective['ignored_config_terms']
+    # ADA is built (gan_control_b200.augment): enabled configs get the controller with the config's p / target / length
+    aug = tc.get('augment') or {}
+    assert (step.ada is not None) == bool(aug.get('enabled'))
+    assert not any('augment' in t for t in step.effective_objective['ignored_config_terms'])
+    if step.ada is not None:
+        assert step.ada.target == aug['ada_target'] and ('ada_augment' in step.effective_objective['terms'])
     bu = MiniBatchUtils(tc['mini_batch'], tc['sub_groups_dict'], total_batch=tc['batch'])
     ref_g = gm.Generator(mc['size'], mc['latent_size'], mc['n_mlp'], channel_multiplier=mc['channel_multiplier'],
                          out_channels=mc['img_channels'], split_fc=mc['split_fc'], marge_fc=mc['marge_fc'],
@@ -161,3 +167,23 @@ def test_conv2d_gradfix_surface(cpu_kernels):
     for bad in (dict(dilation=2), dict(groups=2)):
         with pytest.raises(NotImplementedError):
             gradfix.conv2d(x, w, **bad)
+
+
+def test_install_augment_replaces_the_reference_functions(cpu_kernels):
+    """`install_augment` on the real `trainers/non_leaking.py`: its `augment` then IS the fused one and, drawing from the
+    same seed, returns what the reference's own pipeline returns"""
+    import gan_control_b200
+    from gan_control_b200 import augment as A
+    from oracle.make_golden_ada import load_non_leaking
+    gm, _ = import_reference()
+    ref = load_non_leaking(gm)                     # pristine copy for the expected values
+    nl = load_non_leaking(gm)
+    gan_control_b200.install_augment(nl)
+    assert nl.augment is A.augment and nl.random_apply_affine is A.random_apply_affine
+    img = rnd(600, 2, 3, 32, 32)
+    torch.manual_seed(21)
+    want, (g_ref, c_ref) = ref.augment(img, 0.9)
+    torch.manual_seed(21)
+    got, (g_new, c_new) = nl.augment(img, 0.9)
+    assert torch.equal(g_ref, g_new) and torch.equal(c_ref[:, :3], c_new[:, :3])
+    assert max_rel(got, want) < 1e-4
