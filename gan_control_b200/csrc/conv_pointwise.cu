@@ -358,26 +358,17 @@ __global__ void __launch_bounds__(256) pw_small_ic_mma_kernel(const T* __restric
     const float g_pos = ep.gain, g_neg = ep.gain * ep.slope;
     const bool lrelu_ok = ep.gain > 0.f && ep.slope >= 0.f && ep.slope <= 1.f;      // gain * lrelu(u) == max(g u, g slope u)
     const T* xb = x + (int64_t)b * npix * ic;
-    // the narrow operand of the NEXT step is requested before this step's MMAs and stores (a step is otherwise one
-    // dependent load -> MMA -> store chain per warp: 2.9 TB/s of stores at 32 warps per SM, profiles/r02_pointwise.md)
-    auto fetch = [&](int g0, uint32_t& a0, uint32_t& a1, float (&nz)[2]) {
+    // (requesting the narrow operand of the NEXT step one iteration ahead was measured SLOWER: 0.48 vs 0.40 ms for
+    // 3 -> 32 @1024^2, profiles/r02_pointwise.md; the pass is bound by its 16-byte stores, 32 resident warps cover the loads)
+    for (int g0 = warp; g0 < groups; g0 += warps) {
         const int p_lo = g0 * 16 + g, p_hi = p_lo + 8;
-        a0 = (g0 < groups && p_lo < npix) ? pw_pair<T>(xb + (int64_t)p_lo * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic) : 0u;
-        a1 = (g0 < groups && p_hi < npix) ? pw_pair<T>(xb + (int64_t)p_hi * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic) : 0u;
-        nz[0] = nz[1] = 0.f;
-        if (ep.on && ep.noise && g0 < groups) {
+        const uint32_t a0 = p_lo < npix ? pw_pair<T>(xb + (int64_t)p_lo * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic) : 0u;
+        const uint32_t a1 = p_hi < npix ? pw_pair<T>(xb + (int64_t)p_hi * ic + 2 * t, 2 * t < ic, 2 * t + 1 < ic) : 0u;
+        float nz[2] = {0.f, 0.f};
+        if (ep.on && ep.noise) {
             if (p_lo < npix) nz[0] = nw * io<T>::ld((const T*)ep.noise + (int64_t)b * npix + p_lo);
             if (p_hi < npix) nz[1] = nw * io<T>::ld((const T*)ep.noise + (int64_t)b * npix + p_hi);
         }
-    };
-    uint32_t a0n, a1n;
-    float nzn[2];
-    fetch(warp, a0n, a1n, nzn);
-    for (int g0 = warp; g0 < groups; g0 += warps) {
-        const int p_lo = g0 * 16 + g, p_hi = p_lo + 8;
-        const uint32_t a0 = a0n, a1 = a1n;
-        const float nz[2] = {nzn[0], nzn[1]};
-        fetch(g0 + warps, a0n, a1n, nzn);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             float c[4][4];

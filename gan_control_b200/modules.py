@@ -173,7 +173,8 @@ class ModulatedConv2d(nn.Module):                                             # 
 
     def operands(self, input, style):
         """(x, wk, d, shared): the convolution operands of one of the two equivalent forms (module docstring), the
-        demodulation coefficients d (None when demodulate=False) and whether wk is the shared, parameter-only weight
+        demodulation coefficients d still to be applied to the OUTPUT (None when demodulate=False or when they are
+        already folded into per-sample weights) and whether wk is the shared, parameter-only weight
         of the activation-modulated form (ops.conv_gather `param_weight`; the weight-modulated wk carries the style
         even when the batch is 1)."""
         batch, in_channel, height, width = input.shape
@@ -185,6 +186,13 @@ class ModulatedConv2d(nn.Module):                                             # 
             d = torch.rsqrt(ops._Gemm.apply(s * s, wsq, False, True, 1.0) + 1e-8)
         if self._weight_form(height, width):
             wk = w.unsqueeze(0) * s.view(batch, 1, in_channel, 1, 1)          # (B, OC, IC, k, k)
+            if d is not None:
+                # demodulation folded into the per-sample weights, as the reference does (gm.py:289): the B*OC*IC*k^2
+                # product is tiny next to the activation, and the convolution then needs no per-(sample, channel) scale
+                # in its epilogue -- under create_graph (path length) that removes the recomputation of the convolution
+                # output for d's gradient and two full-size passes (scale, dot) per layer and per differentiation order
+                wk = wk * d.view(batch, self.out_channel, 1, 1, 1)
+                d = None
             return input, wk, d, False
         wk = w.unsqueeze(0)
         x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
