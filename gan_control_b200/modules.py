@@ -705,7 +705,10 @@ class Discriminator(nn.Module):                                               # 
         self.final_linear = nn.Sequential(EqualLinear(channels[4] * 4 * 4, channels[4], activation='fused_lrelu'),
                                           EqualLinear(channels[4], 1))
 
-    def forward(self, input):
+    def forward(self, input, stddev_chunks=1):
+        """stddev_chunks > 1: `input` is that many independent batches concatenated (the discriminator step's fake and
+        real batch, gt.py:655-656).  Every layer is per-sample except the minibatch-stddev statistic, which is then taken
+        within each chunk, so the result equals separate calls -- with half the launches and better-filled small layers."""
         x = input.to(dtype=self.act_dtype, memory_format=torch.channels_last)
         blocks = list(self.convs)
         if (ops.fused_prep() and torch.is_grad_enabled() and len(blocks) > 1 and isinstance(blocks[1], ResBlock)
@@ -721,15 +724,23 @@ class Discriminator(nn.Module):                                               # 
                 out = blk(out)
         else:
             out = self.convs(x)
-        return self._forward_split(out, self.final_conv, self.final_linear), None
+        return self._forward_split(out, self.final_conv, self.final_linear, stddev_chunks), None
 
-    def _forward_split(self, out, final_conv, final_linear):                  # gm.py:1003-1016
+    def _minibatch_stddev(self, out):                                         # gm.py:1004-1012
         batch, channel, height, width = out.shape
         group = min(batch, self.stddev_group)
         stddev = ops.up32(out).reshape(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
         stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
         stddev = stddev.mean([2, 3, 4], keepdim=True).squeeze(2)
-        stddev = stddev.repeat(group, 1, height, width).to(out.dtype)
+        return stddev.repeat(group, 1, height, width).to(out.dtype)
+
+    def _forward_split(self, out, final_conv, final_linear, stddev_chunks=1):     # gm.py:1003-1016
+        batch = out.shape[0]
+        if stddev_chunks > 1:
+            assert batch % stddev_chunks == 0
+            stddev = torch.cat([self._minibatch_stddev(o) for o in out.chunk(stddev_chunks)])
+        else:
+            stddev = self._minibatch_stddev(out)
         out = self._final_conv_split(out, stddev, final_conv)
         out = out.reshape(batch, -1)
         return final_linear(out)

@@ -681,3 +681,31 @@ def test_fused_discriminator_matches_op_algebra(size, cm, dt):
     print(f'fused D {size} cm={cm} {dt}: worst rel-L2 errors {[(k, round(v, 5)) for k, v in bad]}')
     tol = 2e-3 if dt == torch.float32 else 1e-1
     assert bad[0][1] < tol, bad
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+def test_discriminator_on_concatenated_batches_equals_separate_calls(dt):
+    """`Discriminator.forward(stddev_chunks=2)` (the discriminator step's single pass over [fake; real]): predictions and
+    parameter gradients equal those of the two separate calls of the reference step (gt.py:655-656)."""
+    torch.manual_seed(3)
+    d = M.Discriminator(64, channel_multiplier=0.5, act_dtype=dt).to(DEV)
+    for m in d.modules():
+        if isinstance(m, M.FusedLeakyReLU):
+            m.bias.data.normal_(std=0.3)
+    a, b = torch.randn(8, 3, 64, 64, device=DEV), torch.randn(8, 3, 64, 64, device=DEV)
+    res = []
+    for merged in (False, True):
+        d.zero_grad()
+        with ops.first_order():
+            if merged:
+                pa, pb = d(torch.cat([a, b]), stddev_chunks=2)[0].chunk(2)
+            else:
+                pa, pb = d(a)[0], d(b)[0]
+            O.d_logistic_loss(pb, pa).backward()
+        res.append((pa.detach().float(), pb.detach().float(), {k: v.grad.float().clone() for k, v in d.named_parameters()}))
+    (pa0, pb0, g0), (pa1, pb1, g1) = res
+    tol_p, tol_g = (1e-5, 1e-4) if dt == torch.float32 else (2e-2, 5e-2)
+    assert max_rel(pa1, pa0) < tol_p and max_rel(pb1, pb0) < tol_p
+    worst = max((rel_err(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0 and g0[k].numel() > 4)
+    print(f'{dt}: merged vs separate discriminator passes, worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})')
+    assert worst[0] < tol_g, worst
