@@ -201,8 +201,8 @@ def _time_kernel(torch, fn, flush, reps=10, warm=3):
 
 def conv_roofline(torch, K, dtype, size, batch, peaks):
     """Every 3x3 layer class of the resolution, timed alone with CUDA events on the launching stream (inputs >> L2, L2
-    flushed between launches) as the StyledConv it is on the path: per-sample modulated weights and the fused
-    demodulation / noise / bias / leaky-ReLU epilogue operands.  Forward and weight gradient.  Headline = the layer the
+    flushed between launches) as the StyledConv it is on the path: per-sample modulated + demodulated weights and the
+    fused noise / bias / leaky-ReLU epilogue operands.  Forward and weight gradient.  Headline = the layer the
     metric is quoted on, 32 -> 32 at full resolution: HBM-bound (input read once + output written once) with its
     tensor-pipe fraction beside it.  Returns (headline, all layers)."""
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
@@ -213,13 +213,14 @@ def conv_roofline(torch, K, dtype, size, batch, peaks):
         x = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
         w = (torch.randn(batch, 3, 3, ch, ch, device='cuda') / (3 * ch ** 0.5)).to(dtype)     # per-sample (modulated) weights
         gy = torch.randn(batch, res, res, ch, device='cuda').to(dtype)
-        d = torch.rand(batch, ch, device='cuda') + 0.5
         bias = torch.randn(ch, device='cuda')
         noise = torch.randn(batch, res, res, device='cuda').to(dtype)
         nw = torch.full((1,), 0.1, device='cuda')
         flops = 2.0 * batch * res * res * ch * ch * 9
         nbytes = 2.0 * batch * res * res * ch * x.element_size()
-        for kind, fn in (('fwd', lambda: K.conv_fwd(x, w, res, res, 1, 1, 1, bias, d, noise, nw, 0.2, 2 ** 0.5)),
+        # (the demodulation coefficients are folded into the per-sample weights by `modweight_fwd` / `ModulatedConv2d.operands`
+        # for every layer of this list, gm.py:289 -- the epilogue carries noise, bias and the activation)
+        for kind, fn in (('fwd', lambda: K.conv_fwd(x, w, res, res, 1, 1, 1, bias, None, noise, nw, 0.2, 2 ** 0.5)),
                          ('wgrad', lambda: K.conv_wgrad(x, gy, 3, 3, 1, 1, 1, True))):
             ms = _time_kernel(torch, fn, flush)
             what = f'conv3x3 {ch}->{ch} @{res}x{res} batch {batch}'
@@ -228,7 +229,7 @@ def conv_roofline(torch, K, dtype, size, batch, peaks):
             row = {'bound': bound, 'achieved': gbs if bound == 'hbm' else tfs, 'peak': hbm if bound == 'hbm' else tf,
                    'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': max(gbs / hbm, tfs / tf),
                    'traffic': NCU_TRAFFIC_BYTES.get(what) if (batch == 16 and kind == 'fwd') else None,
-                   'kernel': what + (' + fused epilogue (demod, noise, bias, lrelu), per-sample weights' if kind == 'fwd'
+                   'kernel': what + (' + fused epilogue (noise, bias, lrelu), per-sample demodulated weights' if kind == 'fwd'
                                      else ' weight gradient (per-sample)'),
                    'pass': kind, 'kernel_ms': ms, 'algorithmic_flops': flops, 'algorithmic_bytes': nbytes,
                    'hbm_gbs': gbs, 'frac_hbm': gbs / hbm, 'tensor_tflops': tfs, 'frac_tensor': tfs / tf,

@@ -474,18 +474,29 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[s][j] = 0.f;
     if (pl < npl) {
-        for (int p = p_begin + pl; p < p_end; p += npl) {
-            const int64_t pix = (int64_t)b * npix + p;
-            const Pack<T, VEC> wv = *reinterpret_cast<const Pack<T, VEC>*>(wide + pix * wc + v * VEC);
-            float ns[kPwMaxSmall];
+        // four pixels in flight per thread: with one, the pass was bound by load latency (2.2 - 3.7 TB/s,
+        // profiles/r02_pointwise.md)
+        constexpr int U = 4;
+        for (int p0 = p_begin + pl; p0 < p_end; p0 += npl * U) {
+            Pack<T, VEC> wv[U];
+            float ns[U][kPwMaxSmall];
 #pragma unroll
-            for (int s = 0; s < kPwMaxSmall; ++s) ns[s] = s < nc ? io<T>::ld(narrow + pix * nc + s) : 0.f;
+            for (int u = 0; u < U; ++u) {
+                const int p = p0 + u * npl;
+                const bool ok = p < p_end;
+                const int64_t pix = (int64_t)b * npix + (ok ? p : p0);
+                wv[u] = *reinterpret_cast<const Pack<T, VEC>*>(wide + pix * wc + v * VEC);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float wf = io<T>::ld(&wv.v[j]);
-#pragma unroll
-                for (int s = 0; s < kPwMaxSmall; ++s) acc[s][j] = fmaf(wf, ns[s], acc[s][j]);
+                for (int s = 0; s < kPwMaxSmall; ++s) ns[u][s] = (s < nc && ok) ? io<T>::ld(narrow + pix * nc + s) : 0.f;
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float wf = io<T>::ld(&wv[u].v[j]);
+#pragma unroll
+                    for (int s = 0; s < kPwMaxSmall; ++s) acc[s][j] = fmaf(wf, ns[u][s], acc[s][j]);
+                }
         }
 #pragma unroll
         for (int s = 0; s < kPwMaxSmall; ++s)

@@ -59,12 +59,27 @@ __global__ void __launch_bounds__(256) mapping_kernel(const float* __restrict__ 
                 float acc[MB];
 #pragma unroll
                 for (int i = 0; i < MB; ++i) acc[i] = 0.f;
-                for (int k = lane; k < L.in_dim; k += 32) {
-                    const float wv = wrow[k];
+                const float* xin = in + (int64_t)b0 * row_stride + L.in_off;
+                if ((L.in_dim & 127) == 0 && (row_width & 3) == 0 && (L.in_off & 3) == 0 && ((uintptr_t)wrow & 15) == 0 &&
+                    ((uintptr_t)in & 15) == 0) {
+                    // 16-byte loads, four k per lane and step: a 512-wide layer is 4 dependent load rounds instead of 16
+                    // (the kernel is a chain of L2 round trips: 46 us per layer before, profiles/r02_launches_step.md)
+                    for (int k = lane * 4; k < L.in_dim; k += 128) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
 #pragma unroll
-                    for (int i = 0; i < MB; ++i)
-                        if (b0 + i < batch)
-                            acc[i] = fmaf(wv, in[(int64_t)(b0 + i) * row_stride + L.in_off + k], acc[i]);
+                        for (int i = 0; i < MB; ++i)
+                            if (b0 + i < batch) {
+                                const float4 xv = *reinterpret_cast<const float4*>(xin + (int64_t)i * row_stride + k);
+                                acc[i] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[i]))));
+                            }
+                    }
+                } else {
+                    for (int k = lane; k < L.in_dim; k += 32) {
+                        const float wv = wrow[k];
+#pragma unroll
+                        for (int i = 0; i < MB; ++i)
+                            if (b0 + i < batch) acc[i] = fmaf(wv, xin[(int64_t)i * row_stride + k], acc[i]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < MB; ++i) {

@@ -45,6 +45,8 @@ for res, c in [(1024, 32), (512, 64), (256, 128), (128, 256), (64, 512)]:
     w_t = torch.randn(B, 1, 1, c, 3, device=dev).bfloat16()
     ms = timed(lambda: K.conv_fwd(g3, w_t, res, res, 1, 1, 0))
     print(f'| ToRGB dgrad 3->{c} @{res}^2 | {ms:.3f} | {gb:.2f} | {gb / ms:.2f} |')
+    ms = timed(lambda: K.conv_wgrad(x, g3, 1, 1, 1, 1, 0, True))
+    print(f'| ToRGB wgrad {c}->3 @{res}^2 (per-sample) | {ms:.3f} | {gb:.2f} | {gb / ms:.2f} |')
     del x, g3
 img = torch.randn(B, 1024, 1024, 3, device=dev).bfloat16()
 w_in = torch.randn(1, 1, 1, 32, 3, device=dev).bfloat16()
@@ -53,6 +55,8 @@ ms = timed(lambda: K.conv_fwd(img, w_in, 1024, 1024, 1, 1, 0, b32, None, None, N
 gb = B * 1024 * 1024 * 35 * 2 / 1e9
 print(f'| from_rgb fwd 3->32 @1024^2 + bias + lrelu | {ms:.3f} | {gb:.2f} | {gb / ms:.2f} |')
 y0 = torch.randn(B, 1024, 1024, 32, device=dev).bfloat16()
+ms = timed(lambda: K.conv_wgrad(img, y0, 1, 1, 1, 1, 0, False))
+print(f'| from_rgb wgrad 3->32 @1024^2 (shared) | {ms:.3f} | {gb:.2f} | {gb / ms:.2f} |')
 ms = timed(lambda: K.conv_fwd(img, w_in, 1024, 1024, 1, 1, 0, None, None, None, None, 0.2, 2 ** 0.5, gate=y0))
 gb = B * 1024 * 1024 * 67 * 2 / 1e9
 print(f'| 3->32 @1024^2 + gate | {ms:.3f} | {gb:.2f} | {gb / ms:.2f} |')
