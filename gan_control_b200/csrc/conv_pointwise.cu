@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) pw_small_ic_mma_kernel(const T* __restric
 // launchers of the 16-bit MMA kernels; false when the shape is not theirs
 template <typename T>
 static bool pw_launch_mma(const T* x, const T* w, T* y, int npix, const ConvGeom& g, const PwEpilogue& ep, cudaStream_t st) {
-    int bx = (int)cdiv((int64_t)sm_count() * 8, g.b);
+    int bx = sm_count() * 8 / g.b;                                  // whole waves only (see conv_wgrad_pointwise)
     const int need = (int)cdiv(cdiv(npix, 16), 8);
     if (bx > need) bx = need;
     const dim3 grid(bx < 1 ? 1 : bx, g.b);
@@ -474,29 +474,20 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const T* __restrict__ wid
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[s][j] = 0.f;
     if (pl < npl) {
-        // four pixels in flight per thread: with one, the pass was bound by load latency (2.2 - 3.7 TB/s,
-        // profiles/r02_pointwise.md)
-        constexpr int U = 4;
-        for (int p0 = p_begin + pl; p0 < p_end; p0 += npl * U) {
-            Pack<T, VEC> wv[U];
-            float ns[U][kPwMaxSmall];
+        // (four pixels in flight per thread were measured SLOWER, 0.53 vs 0.31 ms at 3 <-> 32 @1024^2: 102 registers, half
+        // the resident warps -- profiles/r02_pointwise.md)
+        for (int p = p_begin + pl; p < p_end; p += npl) {
+            const int64_t pix = (int64_t)b * npix + p;
+            const Pack<T, VEC> wv = *reinterpret_cast<const Pack<T, VEC>*>(wide + pix * wc + v * VEC);
+            float ns[kPwMaxSmall];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int p = p0 + u * npl;
-                const bool ok = p < p_end;
-                const int64_t pix = (int64_t)b * npix + (ok ? p : p0);
-                wv[u] = *reinterpret_cast<const Pack<T, VEC>*>(wide + pix * wc + v * VEC);
+            for (int s = 0; s < kPwMaxSmall; ++s) ns[s] = s < nc ? io<T>::ld(narrow + pix * nc + s) : 0.f;
 #pragma unroll
-                for (int s = 0; s < kPwMaxSmall; ++s) ns[u][s] = (s < nc && ok) ? io<T>::ld(narrow + pix * nc + s) : 0.f;
+            for (int j = 0; j < VEC; ++j) {
+                const float wf = io<T>::ld(&wv.v[j]);
+#pragma unroll
+                for (int s = 0; s < kPwMaxSmall; ++s) acc[s][j] = fmaf(wf, ns[s], acc[s][j]);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float wf = io<T>::ld(&wv[u].v[j]);
-#pragma unroll
-                    for (int s = 0; s < kPwMaxSmall; ++s) acc[s][j] = fmaf(wf, ns[u][s], acc[s][j]);
-                }
         }
 #pragma unroll
         for (int s = 0; s < kPwMaxSmall; ++s)
@@ -534,7 +525,7 @@ int conv_fwd_pointwise(const void* x, const void* w, void* y, int dtype, const C
     return B200_DISPATCH(dtype, [&] {
         constexpr int V = 16 / sizeof(T);
         const size_t smem = (size_t)g.oc * g.ic * sizeof(float);
-        int bx = (int)cdiv((int64_t)sm_count() * 8, g.b);
+        int bx = sm_count() * 8 / g.b;
         if (g_pw_mode == 0 && pw_launch_mma<T>((const T*)x, (const T*)w, (T*)y, npix, g, ep, st)) {
             count_launch();
             return check_launch("conv_fwd_pointwise");
@@ -598,7 +589,9 @@ int conv_wgrad_pointwise(const void* x, const void* gy, float* gw, int dtype, co
         const T* wide = narrow_oc ? (const T*)x : (const T*)gy;
         const T* narrow = narrow_oc ? (const T*)gy : (const T*)x;
         const int wc = narrow_oc ? g.ic : g.oc, nc = narrow_oc ? g.oc : g.ic;
-        int blocks = (int)cdiv((int64_t)sm_count() * 4, g.b);
+        // at most ONE wave of resident blocks (4 per SM): rounding the per-sample count up left a 16-block second wave at
+        // batch 32 and doubled the kernel (1.06 ms vs 2 x 0.31 ms at batch 16, gpurun_out/r2p_variants.log)
+        int blocks = sm_count() * 4 / g.b;
         int ppb = (int)cdiv(npix, blocks < 1 ? 1 : blocks);
         if (ppb < 256) ppb = 256;
         blocks = (int)cdiv(npix, ppb);

@@ -486,6 +486,19 @@ def _ones_row(ic, like):
     return _ONES[key]
 
 
+def _channel_sums(t):
+    """sum over (n, h, w) of a contiguous NHWC tensor, fp32.  Narrow tensors (C < 16, the RGB side) are folded so that
+    g consecutive pixels form g*C channels: the reduction kernel then runs with full lanes instead of C of 32."""
+    n, h, w, c = t.shape
+    hw = h * w
+    if c >= 16:
+        return K.reduce_nhwc(t, None, per_channel=True)[0]
+    g = 32
+    while hw % g:
+        g //= 2
+    return K.reduce_nhwc(t.reshape(n, hw // g, 1, g * c), None, per_channel=True)[0].view(g, c).sum(0)
+
+
 class _ModConv(Function):
     """y = gain*lrelu(conv(x, w_eff)*d_ext[b,o] + nw*noise + bias[o]),  w_eff[b] = scale*weight*s[b]*demod[b]
     -- a whole ModulatedConv2d / StyledConv / ToRGB / ConvLayer with its weight path (gm.py:284-289, 152-160):
@@ -530,6 +543,12 @@ class _ModConv(Function):
             gconv = gyn
             if bias is not None and need[6]:
                 gb = K.reduce_nhwc(gconv, None, per_channel=True)[0].reshape(bias.shape).to(bias.dtype)
+        elif has_ep and d_ext is None and noise is None and slope == 1.0 and gain == 1.0:
+            # bias-only epilogue (ToRGB, gm.py:424-428): the gradient passes through unchanged, only the bias sum is left.
+            # (The generic epilogue backward copied the 3-channel tensor with 3 of 32 lanes active: 1.3 ms per G step.)
+            gconv = gyn
+            if bias is not None and need[6]:
+                gb = _channel_sums(gconv).reshape(bias.shape).to(bias.dtype)
         elif has_ep:
             gconv, gd_, gb_, gnw_ = K.epilogue_bwd(gyn, y, d_ext, noise, noise_w if noise is not None else None,
                                                    None if bias is None else bias.reshape(-1), slope, gain,
