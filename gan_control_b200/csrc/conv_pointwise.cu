@@ -282,11 +282,13 @@ template <typename T> __device__ __forceinline__ uint32_t pw_pair(const T* p, bo
     return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
-// OC <= 4, IC = 32 * NQ: a warp takes 16 pixels per step (rows g and g + 8 of the fragment), U steps in flight.
+// OC <= 4, IC = 32 * NQ: a warp takes 16 pixels per step (rows g and g + 8 of the fragment); U steps in flight for the
+// narrow layers, QC 32-channel chunks in flight for the wide ones (eight 16-byte loads per lane either way).
 template <typename T, int NQ>
 __global__ void __launch_bounds__(256) pw_small_oc_mma_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ y,
                                                               int npix, int ic, int oc, int per_sample, PwEpilogue ep) {
     constexpr int U = NQ >= 4 ? 1 : 4 / NQ;
+    constexpr int QC = NQ >= 4 ? 4 : NQ;
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const T* wb = w + (int64_t)(per_sample ? b : 0) * oc * ic;
@@ -300,24 +302,33 @@ __global__ void __launch_bounds__(256) pw_small_oc_mma_kernel(const T* __restric
     const float nw = (ep.noise && ep.noise_w) ? *ep.noise_w : 0.f;
     const T* xb = x + (int64_t)b * npix * ic;
     for (int g0 = warp; g0 < groups; g0 += warps * U) {
-        uint4 xa[U][NQ], xh[U][NQ];
+        float c[U][4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p_lo = (g0 + u * warps) * 16 + g, p_hi = p_lo + 8;
+        for (int u = 0; u < U; ++u) c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0.f;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                xa[u][q] = p_lo < npix ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p_lo * ic + q * 32 + t * 8)) : make_uint4(0u, 0u, 0u, 0u);
-                xh[u][q] = p_hi < npix ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p_hi * ic + q * 32 + t * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        for (int q0 = 0; q0 < NQ; q0 += QC) {
+            uint4 xa[U][QC], xh[U][QC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int p_lo = (g0 + u * warps) * 16 + g, p_hi = p_lo + 8;
+#pragma unroll
+                for (int q = 0; q < QC; ++q) {
+                    xa[u][q] = p_lo < npix ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p_lo * ic + (q0 + q) * 32 + t * 8))
+                                           : make_uint4(0u, 0u, 0u, 0u);
+                    xh[u][q] = p_hi < npix ? __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p_hi * ic + (q0 + q) * 32 + t * 8))
+                                           : make_uint4(0u, 0u, 0u, 0u);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < QC; ++q) {
+                    WarpMma<T>::k16(c[u], xa[u][q].x, xh[u][q].x, xa[u][q].y, xh[u][q].y, wq[q0 + q].x, wq[q0 + q].y);
+                    WarpMma<T>::k16(c[u], xa[u][q].z, xh[u][q].z, xa[u][q].w, xh[u][q].w, wq[q0 + q].z, wq[q0 + q].w);
+                }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                WarpMma<T>::k16(c, xa[u][q].x, xh[u][q].x, xa[u][q].y, xh[u][q].y, wq[q].x, wq[q].y);
-                WarpMma<T>::k16(c, xa[u][q].z, xh[u][q].z, xa[u][q].w, xh[u][q].w, wq[q].z, wq[q].w);
-            }
             // c[0], c[1]: pixel row g, output channels 2t, 2t + 1;  c[2], c[3]: row g + 8
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(256) pw_small_oc_mma_kernel(const T* __restric
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int o = 2 * t + e;
-                    if (o < oc) io<T>::st(y + pix * oc + o, pw_epilogue<T>(ep, c[2 * h + e], b, oc, o, pix, nz));
+                    if (o < oc) io<T>::st(y + pix * oc + o, pw_epilogue<T>(ep, c[u][2 * h + e], b, oc, o, pix, nz));
                 }
             }
         }
@@ -426,12 +437,14 @@ static bool pw_launch_mma(const T* x, const T* w, T* y, int npix, const ConvGeom
     const int need = (int)cdiv(cdiv(npix, 16), 8);
     if (bx > need) bx = need;
     const dim3 grid(bx < 1 ? 1 : bx, g.b);
-    if (g.oc <= kPwMaxSmall && g.ic % 32 == 0 && g.ic <= 128) {
+    if (g.oc <= kPwMaxSmall && g.ic % 32 == 0 && g.ic <= 512) {
         switch (g.ic / 32) {
             case 1: pw_small_oc_mma_kernel<T, 1><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
             case 2: pw_small_oc_mma_kernel<T, 2><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
             case 4: pw_small_oc_mma_kernel<T, 4><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
-            default: return false;
+            case 8: pw_small_oc_mma_kernel<T, 8><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            case 16: pw_small_oc_mma_kernel<T, 16><<<grid, 256, 0, st>>>(x, w, y, npix, g.ic, g.oc, g.w_per_sample, ep); return true;
+            default: break;
         }
     }
     const bool side_aligned = (((uintptr_t)ep.bias | (uintptr_t)ep.rowscale | (uintptr_t)ep.addend | (uintptr_t)ep.gate) & 15) == 0;

@@ -21,6 +21,10 @@ namespace b200gan {
 
 using namespace umma;
 
+#ifndef B200GAN_F32X2
+#define B200GAN_F32X2 1      // packed fp32 pairs in the epilogue math (umma.cuh)
+#endif
+
 constexpr int kHaloThreads = 384;            // warp 0: TMA, 1-3: MMA issuers (2 also allocates TMEM), 4-7 and 8-11: two epilogue groups
 constexpr int kHaloIssuers = 3;              // MMA-issuing warps (1, 2, 3), tiles round-robin
 constexpr int kHaloAcc = 6;                  // max TMEM accumulators in flight (HaloParams::nacc in use; tiles alternate between the epilogue groups)
@@ -66,11 +70,27 @@ __device__ __forceinline__ void epilogue_math_store16(const HaloParams& p, float
         // gain * lrelu(u) = max(g*u, g*slope*u) for gain > 0, 0 <= slope <= 1 (every use on the path): FFMA, FMUL, FMNMX
         const float g = p.gain, gs = p.gain * p.slope;
         if (g > 0.f && p.slope >= 0.f && p.slope <= 1.f) {
+#if B200GAN_F32X2
+            // two channels per instruction: (nz + b), (v [* r] + .), * g, * gs as packed pairs; only the max stays scalar
+            const F2 nz2 = f2_pack(nz, nz), g2 = f2_pack(g, g), gs2 = f2_pack(gs, gs);
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+                const F2 c2 = f2_add(f2_pack(b[e], b[e + 1]), nz2);
+                const F2 v2 = f2_pack(v[e], v[e + 1]);
+                const F2 u2 = ROW ? f2_fma(v2, f2_pack(r[e], r[e + 1]), c2) : f2_add(v2, c2);
+                float t0, t1, s0, s1;
+                f2_unpack(f2_mul(u2, g2), t0, t1);
+                f2_unpack(f2_mul(u2, gs2), s0, s1);
+                v[e] = fmaxf(t0, s0);
+                v[e + 1] = fmaxf(t1, s1);
+            }
+#else
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const float u = ROW ? fmaf(v[e], r[e], nz + b[e]) : v[e] + (nz + b[e]);
                 v[e] = fmaxf(u * g, u * gs);
             }
+#endif
         } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {

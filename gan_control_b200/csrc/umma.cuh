@@ -167,6 +167,32 @@ __device__ __forceinline__ float hi16(uint32_t w, int f16) {
     return f16 ? __half2float(__ushort_as_half((unsigned short)(w >> 16))) : __uint_as_float(w & 0xffff0000u);
 }
 
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes of fp32 math) ---------------------------
+// The epilogue warps share their scheduler with the MMA-issuing / TMA warps, whose issue latency is the kernel's critical
+// path on the short-K layers (profiles/r02_epilogue_cost.md: every epilogue instruction costs ~1 clk of kernel time).
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+
 // ---- epilogue side inputs: 16 consecutive bf16 of an output-shaped tensor (addend / gate, include/b200gan.h) ----------
 struct Side16 {
     uint4 a, b;
