@@ -70,27 +70,28 @@ __device__ __forceinline__ void epilogue_math_store16(const HaloParams& p, float
         // gain * lrelu(u) = max(g*u, g*slope*u) for gain > 0, 0 <= slope <= 1 (every use on the path): FFMA, FMUL, FMNMX
         const float g = p.gain, gs = p.gain * p.slope;
         if (g > 0.f && p.slope >= 0.f && p.slope <= 1.f) {
-#if B200GAN_F32X2
-            // two channels per instruction: (nz + b), (v [* r] + .), * g, * gs as packed pairs; only the max stays scalar
-            const F2 nz2 = f2_pack(nz, nz), g2 = f2_pack(g, g), gs2 = f2_pack(gs, gs);
+            if (B200GAN_F32X2 && p.rowscale == nullptr) {
+                // two channels per instruction: (nz + b), (v + .), * g, * gs as packed pairs; only the max stays scalar.
+                // Measured (scripts/epilogue_cost.py, bench.py): 32 -> 32 @1024^2 with noise + bias 0.700 -> 0.687 ms,
+                // 64 -> 64 @512^2 0.355 -> 0.350 ms.  With a demodulation row (FFMA2 form) it was SLOWER (0.72 -> 0.94 ms),
+                // so that (now unused: the demodulation is folded into the weights) case keeps the scalar code.
+                const F2 nz2 = f2_pack(nz, nz), g2 = f2_pack(g, g), gs2 = f2_pack(gs, gs);
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-                const F2 c2 = f2_add(f2_pack(b[e], b[e + 1]), nz2);
-                const F2 v2 = f2_pack(v[e], v[e + 1]);
-                const F2 u2 = ROW ? f2_fma(v2, f2_pack(r[e], r[e + 1]), c2) : f2_add(v2, c2);
-                float t0, t1, s0, s1;
-                f2_unpack(f2_mul(u2, g2), t0, t1);
-                f2_unpack(f2_mul(u2, gs2), s0, s1);
-                v[e] = fmaxf(t0, s0);
-                v[e + 1] = fmaxf(t1, s1);
-            }
-#else
+                for (int e = 0; e < 16; e += 2) {
+                    const F2 u2 = f2_add(f2_pack(v[e], v[e + 1]), f2_add(f2_pack(b[e], b[e + 1]), nz2));
+                    float t0, t1, s0, s1;
+                    f2_unpack(f2_mul(u2, g2), t0, t1);
+                    f2_unpack(f2_mul(u2, gs2), s0, s1);
+                    v[e] = fmaxf(t0, s0);
+                    v[e + 1] = fmaxf(t1, s1);
+                }
+            } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float u = ROW ? fmaf(v[e], r[e], nz + b[e]) : v[e] + (nz + b[e]);
-                v[e] = fmaxf(u * g, u * gs);
+                for (int e = 0; e < 16; ++e) {
+                    const float u = ROW ? fmaf(v[e], r[e], nz + b[e]) : v[e] + (nz + b[e]);
+                    v[e] = fmaxf(u * g, u * gs);
+                }
             }
-#endif
         } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
