@@ -299,10 +299,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                         }
                     }
                     uint32_t pk[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        pk[e] = pack16x2(v[2 * e], v[2 * e + 1], p.f16);
-                    }
+                    pack16(v, pk, p.f16);
                     uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
                     d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);

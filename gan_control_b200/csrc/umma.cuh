@@ -160,6 +160,23 @@ __device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// 16 floats -> 8 packed words; the storage-format test is ONE warp-uniform branch around the eight conversions (inside
+// pack16x2 the compiler evaluates both conversions per pair and selects: 16 F2FP + 8 SEL per 16 channels instead of 8 F2FP)
+__device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&pk)[8], int f16) {
+    if (f16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+}
 __device__ __forceinline__ float lo16(uint32_t w, int f16) {
     return f16 ? __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))) : __uint_as_float(w << 16);
 }

@@ -326,6 +326,9 @@ class GanTrainStep:
         self.r1, self.d_reg_every, self.g_reg_every = r1, d_reg_every, g_reg_every
         self.path_regularize, self.path_batch_shrink, self.mixing = path_regularize, path_batch_shrink, mixing
         self.latent_size = latent_size
+        # (a discriminator class without the `stddev_chunks` argument -- e.g. the reference's own -- gets the two separate calls)
+        import inspect
+        self._d_takes_chunks = 'stddev_chunks' in inspect.signature(discriminator.forward).parameters
         # ADA (gt.py:333-337): None, a fixed probability, or an `augment.AdaptiveP` controller
         if ada is not None and not hasattr(ada, 'update'):
             from .augment import AdaptiveP
@@ -470,7 +473,7 @@ class GanTrainStep:
                 real_img, _ = augment(real_img, self.ada.p)
                 fake_img, _ = augment(fake_img, self.ada.p)
         with first_order():                          # plain step: no double backward -> fused single-kernel layers
-            if fake_img.shape == real_img.shape:
+            if fake_img.shape == real_img.shape and self._d_takes_chunks:
                 # D(fake), D(real) (gt.py:655-656) as ONE pass over the concatenated batch: identical values (the
                 # minibatch-stddev statistic stays per batch), half the launches, one weight-gradient reduction
                 both = torch.cat([fake_img, real_img.to(dtype=fake_img.dtype, memory_format=torch.channels_last)])
