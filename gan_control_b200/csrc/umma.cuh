@@ -222,10 +222,18 @@ __device__ __forceinline__ Side16 side_load16(const __nv_bfloat16* p) {
 }
 __device__ __forceinline__ void side_unpack16(const Side16& s, float (&o)[16], int f16) {
     const uint32_t w[8] = {s.a.x, s.a.y, s.a.z, s.a.w, s.b.x, s.b.y, s.b.z, s.b.w};
+    if (f16) {                      // one warp-uniform branch, not a select per element (see pack16)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        o[2 * e] = lo16(w[e], f16);
-        o[2 * e + 1] = hi16(w[e], f16);
+        for (int e = 0; e < 8; ++e) {
+            o[2 * e] = lo16(w[e], 1);
+            o[2 * e + 1] = hi16(w[e], 1);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            o[2 * e] = lo16(w[e], 0);
+            o[2 * e + 1] = hi16(w[e], 0);
+        }
     }
 }
 // v = (v + addend) [gate mode: * r * (gate > 0 ? g : gs)]; the forward activation is applied by the caller otherwise
