@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(const T* __restrict__
 
 // 16-byte vectorised variant: thread = (channel vector, pixel lane); per-thread partial sums, one
 // shared-memory reduction per block, one global atomic per (block, channel).
-template <typename T, int VEC>
+// WANT_GD: the demodulation gradient sum gz*z is asked for (a per-(sample, channel) scale on the OUTPUT; the weight-modulated
+// layers fold it into their weights and the discriminator has none, so the common instance skips the pre-activation recovery)
+template <typename T, int VEC, bool WANT_GD>
 __global__ void __launch_bounds__(256, 4) epilogue_bwd_vec_kernel(const T* __restrict__ gy, const T* __restrict__ y,
                                                                   T* __restrict__ gconv, const float* __restrict__ rowscale,
                                                                   const T* __restrict__ noise, const float* __restrict__ noise_w,
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256, 4) epilogue_bwd_vec_kernel(const T* __res
     const int64_t sample = blockIdx.y;
     const int64_t p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
     const float nw = (noise && noise_w) ? *noise_w : 0.f;
-    const float inv_gain = 1.f / gain, inv_gs = 1.f / (gain * slope);
+    const float inv_gain = 1.f / gain, inv_gs = 1.f / (gain * slope), gain_neg = gain * slope;
     // Per-thread state is kept small (<= 64 registers, 4 blocks per SM) and two pixels' loads are issued before
     // any use: the first version (76 registers, one vector pair in flight) was latency-bound -- ncu: 8.3
     // long-scoreboard stalls per issue, 34 % warps active, 51 % of HBM (profiles/r01_ncu_kernels.md).
@@ -213,11 +215,13 @@ __global__ void __launch_bounds__(256, 4) epilogue_bwd_vec_kernel(const T* __res
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const float yy = io<T>::ld(&yv.v[j]);
-                const float gz = io<T>::ld(&gv.v[j]) * gain * (yy > 0.f ? 1.f : slope);
+                const float gz = io<T>::ld(&gv.v[j]) * (yy > 0.f ? gain : gain_neg);
                 io<T>::st(&out.v[j], gz * dv[j]);
-                const float u = yy > 0.f ? yy * inv_gain : yy * inv_gs;
                 sb[j] += gz;
-                sd[j] = fmaf(gz, u - nzw, sd[j]);
+                if (WANT_GD) {
+                    const float u = yy > 0.f ? yy * inv_gain : yy * inv_gs;
+                    sd[j] = fmaf(gz, u - nzw, sd[j]);
+                }
                 gsum += gz;
             }
             sn = fmaf(gsum, nz, sn);
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256, 4) epilogue_bwd_vec_kernel(const T* __res
         for (int j = 0; j < VEC; ++j) {
             const float bvj = bias ? bias[v * VEC + j] : 0.f;
             atomicAdd(&red_b[v * VEC + j], sb[j]);
-            atomicAdd(&red_d[v * VEC + j], (sd[j] - bvj * sb[j]) / dv[j]);
+            if (WANT_GD) atomicAdd(&red_d[v * VEC + j], (sd[j] - bvj * sb[j]) / dv[j]);
         }
         atomicAdd(red_n, sn);
     }
@@ -277,9 +281,14 @@ extern "C" int b200gan_epilogue_bwd(const void* gy, const void* y, void* gconv, 
             if (ppb < 128) ppb = 128;
             slabs = cdiv(hw, ppb);
             const size_t smem = (2 * (size_t)c + 1) * sizeof(float);
-            epilogue_bwd_vec_kernel<T, V><<<dim3((unsigned)slabs, (unsigned)n), 256, smem, (cudaStream_t)stream>>>(
-                (const T*)gy, (const T*)y, (T*)gconv, rowscale, (const T*)noise, noise_w, bias, gd, gb, gnw, hw, (int)c, ppb,
-                slope, gain);
+            if (gd != nullptr)
+                epilogue_bwd_vec_kernel<T, V, true><<<dim3((unsigned)slabs, (unsigned)n), 256, smem, (cudaStream_t)stream>>>(
+                    (const T*)gy, (const T*)y, (T*)gconv, rowscale, (const T*)noise, noise_w, bias, gd, gb, gnw, hw, (int)c, ppb,
+                    slope, gain);
+            else
+                epilogue_bwd_vec_kernel<T, V, false><<<dim3((unsigned)slabs, (unsigned)n), 256, smem, (cudaStream_t)stream>>>(
+                    (const T*)gy, (const T*)y, (T*)gconv, rowscale, (const T*)noise, noise_w, bias, gd, gb, gnw, hw, (int)c, ppb,
+                    slope, gain);
             count_launch();
             return check_launch("epilogue_bwd");
         }

@@ -269,6 +269,25 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                             side_apply16(v, &s_add, nullptr, one, 1.f, 1.f, p.f16);
                         }
                         float rr[16], bb[16];
+                        if (vec_side && rs == nullptr && fast_act) {
+                            // no demodulation row (it is folded into the weights on the weight-modulated layers): bias +
+                            // noise + leaky-ReLU on packed fp32 pairs (see conv_umma_halo.cu epilogue_math_store16)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 b4 = bs ? __ldg(reinterpret_cast<const float4*>(bs + c0) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                bb[4 * e] = b4.x; bb[4 * e + 1] = b4.y; bb[4 * e + 2] = b4.z; bb[4 * e + 3] = b4.w;
+                            }
+                            const F2 nz2 = f2_pack(nz, nz), g2 = f2_pack(g, g), gs2 = f2_pack(gs, gs);
+#pragma unroll
+                            for (int e = 0; e < 16; e += 2) {
+                                const F2 u2 = f2_add(f2_pack(v[e], v[e + 1]), f2_add(f2_pack(bb[e], bb[e + 1]), nz2));
+                                float t0, t1, s0, s1;
+                                f2_unpack(f2_mul(u2, g2), t0, t1);
+                                f2_unpack(f2_mul(u2, gs2), s0, s1);
+                                v[e] = fmaxf(t0, s0);
+                                v[e + 1] = fmaxf(t1, s1);
+                            }
+                        } else {
                         if (vec_side) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -296,6 +315,7 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                                 const float u = fmaf(v[e], rr[e], nz + bb[e]);
                                 v[e] = g * (u > 0.f ? u : u * p.slope);
                             }
+                        }
                         }
                     }
                     uint32_t pk[8];

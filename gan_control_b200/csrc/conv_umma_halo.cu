@@ -310,23 +310,15 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // port (N <= 32: 40 clk of operand fetch per instruction) and LDS wavefronts are taken from them: the read-only
         // global path (L1 hits) is faster there (0.57 vs 0.65 ms).  A register-resident bias row spilled (168 registers).
         const bool side_smem = ch_phys > 32;
-        // output-shaped side inputs (the gradient another consumer contributes, the producer's saved output) of one
-        // 16-channel chunk of this thread's pixel
-        auto side_issue = [&](__nv_bfloat16* dst, int c0, bool valid, Side16& sa, Side16& sg) {
-            if (!SIDE) return;
-            const int64_t soff = (dst - p.y) + c0;
-            if (valid && p.addend) sa = side_load16(p.addend + soff);
-            if (valid && p.gate) sg = side_load16(p.gate + soff);
-        };
-        // `pre`: the side inputs were requested by the caller (one chunk ahead, the first one before the accumulator wait);
-        // otherwise they are loaded here, in front of the TMEM read
-        auto chunk = [&](uint32_t taddr, int col, __nv_bfloat16* dst, int c0, const float* rs_g, float nz, bool valid,
-                         const Side16* pre_add, const Side16* pre_gate) {
+        auto chunk = [&](uint32_t taddr, int col, __nv_bfloat16* dst, int c0, const float* rs_g, float nz, bool valid) {
             float v[16], r16[16], b16[16];
+            // output-shaped side inputs (the gradient another consumer contributes, the producer's saved output): their
+            // loads are issued before the TMEM read so that the two latencies overlap
             Side16 s_add, s_gate;
             if (SIDE) {
-                if (pre_add != nullptr) { s_add = *pre_add; s_gate = *pre_gate; }
-                else side_issue(dst, c0, valid, s_add, s_gate);
+                const int64_t soff = (dst - p.y) + c0;
+                if (valid && p.addend) s_add = side_load16(p.addend + soff);
+                if (valid && p.gate) s_gate = side_load16(p.gate + soff);
             }
             if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)col, v);
             if (valid && !(p.dbg & 4)) {
@@ -417,22 +409,12 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 __nv_bfloat16* dst = p.y + pix * p.OC;
                 if (side_smem) stage_rowscale((int)n);
                 const float* rs_g = p.rowscale ? p.rowscale + (int64_t)n * p.OC : nullptr;
-                // Side inputs ride one chunk ahead of the math: the first chunk's loads are in flight while this group waits
-                // for the accumulator, the next chunk's while the current one is converted and stored (read at their point
-                // of use they cost an L2 round trip per chunk on the kernel's critical path: conv1's data gradient with
-                // addend + gate ran 1.0 ms against 0.56 ms plain, profiles/r02_side_inputs.md).
-                Side16 sa_cur, sg_cur, sa_nxt, sg_nxt;
-                side_issue(dst, 0, valid, sa_cur, sg_cur);
                 mbar_wait(tfull + acc, acc_par);
                 tc_fence_after();
                 const float nz = (valid && p.noise) ? nw * lo16(nraw0, p.f16) : 0.f;
                 fetch_noise(tile + 2 * gridDim.x);
                 prefetch_side(tile + 4 * (int)gridDim.x);
-                for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                    if (SIDE && c0 + 16 < p.BN) side_issue(dst, c0 + 16, valid, sa_nxt, sg_nxt);
-                    chunk(taddr, c0, dst, c0, rs_g, nz, valid, SIDE ? &sa_cur : nullptr, SIDE ? &sg_cur : nullptr);
-                    if (SIDE) { sa_cur = sa_nxt; sg_cur = sg_nxt; }
-                }
+                for (int c0 = 0; c0 < p.BN; c0 += 16) chunk(taddr, c0, dst, c0, rs_g, nz, valid);
             } else {
                 // depth-to-space: accumulator columns [(py*2+px)*CQ + c] of view pixel (oy, ox) are channel c of the
                 // physical pixel (2*oy+py, 2*ox+px); bias / rowscale / noise follow the physical tensor
@@ -451,7 +433,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 #pragma unroll
                 for (int ph = 0; ph < 4; ++ph) {
                     __nv_bfloat16* dst = p.y + (pix0 + (ph >> 1) * (2 * p.OW) + (ph & 1)) * p.CQ;
-                    for (int c0 = 0; c0 < p.CQ; c0 += 16) chunk(taddr, ph * p.CQ + c0, dst, c0, rs_g, nz[ph], valid, nullptr, nullptr);
+                    for (int c0 = 0; c0 < p.CQ; c0 += 16) chunk(taddr, ph * p.CQ + c0, dst, c0, rs_g, nz[ph], valid);
                 }
             }
             tc_fence_before();
