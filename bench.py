@@ -177,11 +177,13 @@ def run_reference(args):
 # per-layer roofline of the convolution kernels, timed alone WITH their fused epilogue operands
 # ---------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at batch 16, from the `ncu --set full` captures summarised in
-# profiles/r01_ncu_kernels.md (None where the layer has not been captured)
+# profiles/r01_ncu_kernels.md / profiles/r02_headline.md (None where the layer has not been captured)
 NCU_TRAFFIC_BYTES = {'conv3x3 256->256 @128x128 batch 16': 135.4e6 + 85.79e6,
                      'conv3x3 128->128 @256x256 batch 16': 268.762e6 + 220.351e6,
                      'conv3x3 64->64 @512x512 batch 16': 537.110e6 + 487.299e6,
-                     'conv3x3 32->32 @1024x1024 batch 16': 1.073810e9 + 1.025126e9}
+                     # round 2, the kernel as the bench times it (noise + bias + leaky-ReLU, demodulated weights): profiles/r02_headline.md
+                     'conv3x3 32->32 @1024x1024 batch 16': 1.107661e9 + 1.032646e9}
+NCU_TRAFFIC_BYTES_WGRAD = {'conv3x3 32->32 @1024x1024 batch 16': 2.284250e9 + 0.005649e9}
 
 
 def _time_kernel(torch, fn, flush, reps=10, warm=3):
@@ -228,7 +230,7 @@ def conv_roofline(torch, K, dtype, size, batch, peaks):
             bound = 'hbm' if gbs / hbm >= tfs / tf else 'tensor'
             row = {'bound': bound, 'achieved': gbs if bound == 'hbm' else tfs, 'peak': hbm if bound == 'hbm' else tf,
                    'unit': 'GB/s' if bound == 'hbm' else 'TFLOP/s', 'frac': max(gbs / hbm, tfs / tf),
-                   'traffic': NCU_TRAFFIC_BYTES.get(what) if (batch == 16 and kind == 'fwd') else None,
+                   'traffic': (NCU_TRAFFIC_BYTES if kind == 'fwd' else NCU_TRAFFIC_BYTES_WGRAD).get(what) if batch == 16 else None,
                    'kernel': what + (' + fused epilogue (noise, bias, lrelu), per-sample demodulated weights' if kind == 'fwd'
                                      else ' weight gradient (per-sample)'),
                    'pass': kind, 'kernel_ms': ms, 'algorithmic_flops': flops, 'algorithmic_bytes': nbytes,
