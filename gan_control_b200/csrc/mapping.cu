@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) mapping_kernel(const float* __restrict__ 
         for (int k = lane; k < L.in_dim; k += 32) ss += src[k] * src[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float r = normalize ? rsqrtf(ss / (float)L.in_dim + 1e-8f) : 1.f;
+        const float r = (normalize & 1) ? rsqrtf(ss / (float)L.in_dim + 1e-8f) : 1.f;
         float* dst = acts + (int64_t)b * row_stride + L.in_off;
         for (int k = lane; k < L.in_dim; k += 32) dst[k] = src[k] * r;
     }
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) mapping_kernel(const float* __restrict__ 
                     for (int i = 0; i < MB; ++i)
                         if (i == lane) v = acc[i];
                     v = v * L.scale + bj;
-                    v = 1.4142135623730951f * (v > 0.f ? v : 0.2f * v);     // fused_lrelu (gm.py:192)
+                    if (!(normalize & 2)) v = 1.4142135623730951f * (v > 0.f ? v : 0.2f * v);     // fused_lrelu (gm.py:192)
                     out[(int64_t)(b0 + lane) * row_stride + L.out_off + j] = v;
                 }
             }
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) mapping_bwd_kernel(const float* __restric
         // phase A: activation gradient in place; clear the input-gradient row
         for (int64_t e = tid; e < layer_stride; e += nthreads) {
             const float yv = y[e];
-            gcur[e] *= 1.4142135623730951f * (yv > 0.f ? 1.f : 0.2f);
+            if (!(normalize & 2)) gcur[e] *= 1.4142135623730951f * (yv > 0.f ? 1.f : 0.2f);
             gprev[e] = 0.f;
         }
         grid.sync();
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) mapping_bwd_kernel(const float* __restric
             const float* gr = gcur + (int64_t)b * row_width + L.in_off;
             const float* xh = acts + (int64_t)b * row_width + L.in_off;
             float* dst = dz + (int64_t)b * z_dim + L.in_off;
-            if (!normalize) {
+            if (!(normalize & 1)) {
                 for (int k = lane; k < L.in_dim; k += 32) dst[k] = gr[k];
                 continue;
             }

@@ -413,9 +413,10 @@ def gemm_f32(a, b, trans_a, trans_b, alpha=1.0):
     return c
 
 
-def mapping_fwd(z, layer_table, n_groups, n_layers, row_width, normalize):
+def mapping_fwd(z, layer_table, n_groups, n_layers, row_width, normalize, linear=False):
     """Persistent mapping-network kernel.  z (B, z_dim) fp32; layer_table: uint8 CUDA tensor holding
-    n_layers*n_groups `FcLayer` structs.  Returns acts (n_layers+1, B, row_width) fp32."""
+    n_layers*n_groups `FcLayer` structs.  Returns acts (n_layers+1, B, row_width) fp32.
+    linear: the layers have no activation (include/b200gan.h: flag bit 1) -- a batch of plain EqualLinear layers."""
     _cuda(z, layer_table)
     z = _f32c(z)
     batch, z_dim = z.shape
@@ -423,11 +424,11 @@ def mapping_fwd(z, layer_table, n_groups, n_layers, row_width, normalize):
     if batch:
         with torch.cuda.device(z.device):
             _check(lib().b200gan_mapping_fwd(_ptr(z), _ptr(acts), _ptr(layer_table), n_groups, n_layers, batch, z_dim,
-                                             row_width, int(normalize), _stream()), 'mapping_fwd')
+                                             row_width, int(bool(normalize)) | (2 if linear else 0), _stream()), 'mapping_fwd')
     return acts
 
 
-def mapping_bwd(z, acts, g_out, layer_table, grad_table, n_groups, n_layers, row_width, normalize, want_dz=False):
+def mapping_bwd(z, acts, g_out, layer_table, grad_table, n_groups, n_layers, row_width, normalize, want_dz=False, linear=False):
     """Backward of mapping_fwd in one cooperative kernel.  g_out (B, out_width) = dL/d(acts[n_layers][:, :out_width]); the
     parameter gradients are WRITTEN where `grad_table` (uint8 CUDA tensor of n_layers*n_groups FcLayerGrad) points.
     Returns dz (B, z_dim) or None."""
@@ -436,12 +437,12 @@ def mapping_bwd(z, acts, g_out, layer_table, grad_table, n_groups, n_layers, row
     batch, z_dim = z.shape
     gbuf = torch.zeros((2, batch, row_width), dtype=torch.float32, device=z.device)
     gbuf[0, :, :g_out.shape[1]] = g_out
-    dz = torch.empty_like(z) if want_dz else None
+    dz = torch.zeros_like(z) if want_dz else None          # columns no layer reads keep a zero gradient
     if batch:
         with torch.cuda.device(z.device):
             _check(lib().b200gan_mapping_bwd(_ptr(z), _ptr(acts), _ptr(gbuf), _ptr(layer_table), _ptr(grad_table), _ptr(dz),
-                                             n_groups, n_layers, batch, z_dim, row_width, int(normalize), _stream()),
-                   'mapping_bwd')
+                                             n_groups, n_layers, batch, z_dim, row_width,
+                                             int(bool(normalize)) | (2 if linear else 0), _stream()), 'mapping_bwd')
     return dz
 
 

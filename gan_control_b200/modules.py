@@ -178,7 +178,7 @@ class ModulatedConv2d(nn.Module):                                             # 
         of the activation-modulated form (ops.conv_gather `param_weight`; the weight-modulated wk carries the style
         even when the batch is 1)."""
         batch, in_channel, height, width = input.shape
-        s = self.modulation(style)                                            # (B, IC) fp32, gm.py:284
+        s = self._style(style)                                                # (B, IC) fp32, gm.py:284
         w = self.weight[0] * self.scale                                       # (OC, IC, k, k)
         d = None
         if self.demodulate:                                                   # gm.py:287-289
@@ -198,6 +198,15 @@ class ModulatedConv2d(nn.Module):                                             # 
         x = input * s.view(batch, in_channel, 1, 1).to(input.dtype)
         return x, wk, d, True
 
+    _s_pre = None       # (B, IC) modulation computed for all layers at once by Generator.synthesis, consumed by the next call
+
+    def _style(self, style):
+        """s = modulation(style) (gm.py:284), or the value the generator computed for all layers in one launch"""
+        if self._s_pre is not None:
+            s, self._s_pre = self._s_pre, None
+            return s
+        return self.modulation(style)
+
     def demod_coeff(self, s):
         """d[b,o] = rsqrt(sum_{i,k} (scale*W*s)^2 + 1e-8) (gm.py:287-289) as a (B,IC)x(IC,OC) product"""
         w = self.weight[0] * self.scale
@@ -210,7 +219,7 @@ class ModulatedConv2d(nn.Module):                                             # 
         Returns (y, d): d is None unless the demodulation is still to be applied by the caller (activation-modulated
         transposed convolution)."""
         batch, in_channel, height, width = input.shape
-        s = self.modulation(style)                                            # (B, IC) fp32, gm.py:284
+        s = self._style(style)                                                # (B, IC) fp32, gm.py:284
         k = self.kernel_size
         geom = dict(flip=True, up=2, pad0=k - 1, out_hw=((height - 1) * 2 + k, (width - 1) * 2 + k)) if transpose \
             else dict(pad0=self.padding)
@@ -379,6 +388,17 @@ class FcConfig:                                    # utils/mini_batch_multi_spli
         return cls(names, groups)
 
 
+def _cached_linear_batch(module, items, in_width, device):
+    """layer table of `ops.build_linear_batch_table`, rebuilt only when a parameter moved (see _cached_fc_table)"""
+    key = tuple(p.data_ptr() for lin, _ in items for p in (lin.weight, lin.bias)) + (in_width,)
+    tbl = module.__dict__.get('_mod_table')
+    if tbl is None or tbl['key'] != key or tbl['table'].device != device:
+        tbl = ops.build_linear_batch_table(items, in_width, device)
+        tbl['key'] = key
+        module.__dict__['_mod_table'] = tbl
+    return tbl
+
+
 def _cached_fc_table(module, groups_fn, device):
     """The kernel's layer table holds raw parameter pointers: rebuild only when a parameter moved (the H2D
     copy of a fresh table must not happen inside CUDA-graph capture; warm-up builds it)."""
@@ -531,7 +551,41 @@ class Generator(nn.Module):                                                   # 
             return image, latent
         return image, None
 
+    def _modulated_layers(self):
+        """[(ModulatedConv2d, latent index)] in the order `synthesis` calls them (gm.py:779-793)"""
+        items = [(self.conv1.conv, 0), (self.to_rgb1.conv, 1)]
+        i = 1
+        for conv1, conv2, to_rgb in zip(self.convs[::2], self.convs[1::2], self.to_rgbs):
+            items += [(conv1.conv, i), (conv2.conv, i + 1), (to_rgb.conv, i + 2)]
+            i += 2
+        return items
+
+    def _precompute_modulations(self, latent):
+        """All style modulations `s = EqualLinear(w_l)` (gm.py:245, 284: one per StyledConv / ToRGB, 26 at 1024^2) in ONE
+        launch of the mapping kernel (batch-of-linear-layers mode) instead of one skinny GEMM per layer -- and one launch for
+        their backward instead of ~5 per layer.  First-order / no-grad passes on CUDA; each layer picks its slice up in
+        `ModulatedConv2d._style`."""
+        if not (ops.fused_prep() and latent.is_cuda and latent.dtype == torch.float32 and latent.ndim == 3
+                and latent.shape[1] == self.n_latent):
+            return
+        layers = self._modulated_layers()
+        items = [(m.modulation, k * self.style_dim) for m, k in layers]
+        tbl = _cached_linear_batch(self, items, self.n_latent * self.style_dim, latent.device)
+        flat = latent.reshape(latent.shape[0], -1).contiguous()
+        s_all = ops.mapping_apply(tbl, flat, normalize=False) if torch.is_grad_enabled() \
+            else ops.mapping_forward(tbl, flat, normalize=False)
+        for (m, _), s in zip(layers, s_all.split(tbl['widths'], dim=1)):          # split: ONE cat in the backward pass
+            m._s_pre = s
+
     def synthesis(self, latent, noise):
+        self._precompute_modulations(latent)
+        try:
+            return self._synthesis(latent, noise)
+        finally:
+            for m, _ in self._modulated_layers():
+                m._s_pre = None
+
+    def _synthesis(self, latent, noise):
         out = self.input(latent).to(dtype=self.act_dtype, memory_format=torch.channels_last)
         out = self.conv1(out, latent[:, 0], noise=self._noise(noise[0], out))
         skip = self.to_rgb1(out, latent[:, 1])

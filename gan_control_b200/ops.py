@@ -948,8 +948,34 @@ def build_fc_table(groups, device):
 
 def mapping_forward(tbl, z, normalize=True):
     """Whole mapping network / MultiFcStack / FcStack forward in ONE cooperative kernel (no autograd)."""
-    acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize)
+    acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize,
+                         linear=tbl.get('linear', False))
     return acts[tbl['n_layers'], :, :tbl['out_width']]
+
+
+def build_linear_batch_table(items, in_width, device):
+    """items: [(EqualLinear without activation, input column offset)]: a batch of independent linear layers evaluated by ONE
+    launch of the mapping kernels (flag `linear`): layer j reads columns [off_j, off_j + in_dim_j) of the (B, in_width)
+    input and writes its out_dim_j outputs after those of layer j - 1.  Same dictionary as `build_fc_table`."""
+    table = (K.FcLayer * len(items))()
+    keep, keep_params, scales, slices, off = [], [], [], [], 0
+    for j, (lin, in_off) in enumerate(items):
+        w, b = lin.weight.detach(), lin.bias.detach()
+        assert w.is_contiguous() and b.is_contiguous() and w.dtype == torch.float32 and not lin.activation
+        keep += [w, b]
+        keep_params += [lin.weight, lin.bias]
+        scales.append((float(lin.scale), float(lin.lr_mul)))
+        slices.append((in_off, in_off + w.shape[1]))
+        e = table[j]
+        e.w, e.bias = w.data_ptr(), b.data_ptr()
+        e.in_dim, e.out_dim, e.in_off, e.out_off = w.shape[1], w.shape[0], in_off, off
+        e.scale, e.bias_mul = float(lin.scale), float(lin.lr_mul)
+        off += w.shape[0]
+    raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(device)
+    return {'table': raw, 'n_groups': len(items), 'n_layers': 1, 'row_width': max(in_width, off), 'out_width': off,
+            'key': tuple(t.data_ptr() for t in keep), 'keep': keep, 'keep_params': keep_params, 'linear': True,
+            'widths': [lin.weight.shape[0] for lin, _ in items],
+            'geom': {'n_layers': 1, 'slices': slices, 'scales': scales, 'linear': True}}
 
 
 def _grad_table(tbl, device):
@@ -987,7 +1013,7 @@ def _mapping_reference(z, params, geom, normalize):
         for gi in range(len(cols)):
             w, b = params[2 * (l * len(cols) + gi)], params[2 * (l * len(cols) + gi) + 1]
             scale, lr_mul = geom['scales'][l * len(cols) + gi]
-            cols[gi] = equal_linear(cols[gi], w, b, scale, lr_mul, True)
+            cols[gi] = equal_linear(cols[gi], w, b, scale, lr_mul, not geom.get('linear', False))
     return torch.cat(cols, dim=1)
 
 
@@ -998,7 +1024,8 @@ class _MappingFn(Function):
 
     @staticmethod
     def forward(ctx, z, tbl, normalize, *params):
-        acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize)
+        acts = K.mapping_fwd(z, tbl['table'], tbl['n_groups'], tbl['n_layers'], tbl['row_width'], normalize,
+                             linear=tbl.get('linear', False))
         ctx.tbl, ctx.normalize = tbl, normalize
         ctx.save_for_backward(z, acts, *params)
         return acts[tbl['n_layers'], :, :tbl['out_width']].clone()
@@ -1019,7 +1046,7 @@ class _MappingFn(Function):
                          [next(grads) if p.requires_grad else None for p in params])
         gt = _grad_table(tbl, z.device)
         dz = K.mapping_bwd(z, acts, g.contiguous().float(), tbl['table'], gt, tbl['n_groups'], tbl['n_layers'], tbl['row_width'],
-                           normalize, want_dz=need_z)
+                           normalize, want_dz=need_z, linear=tbl.get('linear', False))
         flat = tbl['grad_flat'].clone()        # the shared buffer is overwritten by the next backward of this table
         outs = []
         for i, (off, shape) in enumerate(tbl['grad_views']):

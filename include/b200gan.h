@@ -239,7 +239,11 @@ int b200gan_gemm_f32(const float* a, const float* b, float* c, int m, int n, int
  * (layers[l * n_groups + g]).  `acts` is a caller-provided fp32 buffer
  * [n_layers + 1][batch][row_width]: row 0 receives the (normalised) input, row l
  * the output of layer l; the last row is the w latent.  It doubles as the saved
- * activations of the backward pass.                                          */
+ * activations of the backward pass.
+ * `normalize` is a flag word: bit 0 = PixelNorm the input slices, bit 1 = LINEAR layers (no fused leaky-ReLU): with
+ * bit 1 set and n_layers = 1 the call is a batch of independent EqualLinear layers without activation -- the style
+ * modulations `ModulatedConv2d.modulation` of ALL generator layers (gm.py:245, 284) in one launch, each group reading its
+ * own 512-wide slice of the (B, n_latent * 512) W+ tensor.                                                        */
 typedef struct {
     const float* w;      /* [out_dim][in_dim] fp32 */
     const float* bias;   /* [out_dim] fp32 */

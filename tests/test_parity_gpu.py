@@ -711,3 +711,44 @@ def test_discriminator_on_concatenated_batches_equals_separate_calls(dt):
     worst = max((rel_err(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0 and g0[k].numel() > 4)
     print(f'{dt}: merged vs separate discriminator passes, worst parameter-gradient rel-L2 {worst[0]:.2e} ({worst[1]})')
     assert worst[0] < tol_g, worst
+
+
+@pytest.mark.parametrize('mixing', [False, True])
+def test_batched_style_modulations_equal_the_per_layer_path(mixing):
+    """`Generator._precompute_modulations` (all `ModulatedConv2d.modulation` layers, gm.py:245/284, in one launch of the
+    mapping kernel, one more for their backward) against the per-layer EqualLinear path: image, dL/dz and every
+    parameter gradient of a first-order pass; W+ input with two latents mixed exercises the per-layer input slices."""
+    torch.manual_seed(9)
+    g = M.Generator(64, 64, 3, channel_multiplier=2, conv_transpose=True).to(DEV)
+    for m in g.modules():
+        if isinstance(m, M.NoiseInjection):
+            m.weight.data.fill_(0.2)
+    z = [torch.randn(3, 64, device=DEV, requires_grad=True) for _ in range(2 if mixing else 1)]
+    noise = [torch.randn(3, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=DEV) for i in range(g.num_layers)]
+    cot = torch.randn(3, 3, 64, 64, device=DEV)
+    res = []
+    for batched in (False, True):
+        g.zero_grad()
+        for t in z:
+            t.grad = None
+        saved = M.Generator._precompute_modulations
+        if not batched:
+            M.Generator._precompute_modulations = lambda self, latent: None
+        try:
+            with ops.first_order():
+                n0 = __import__('gan_control_b200.kernels', fromlist=['x']).launch_count()
+                img, _ = g(z, noise=noise, inject_index=2)
+                (img * cot).sum().backward()
+                launches = __import__('gan_control_b200.kernels', fromlist=['x']).launch_count() - n0
+        finally:
+            M.Generator._precompute_modulations = saved
+        res.append((img.detach().clone(), [t.grad.clone() for t in z], {k: v.grad.clone() for k, v in g.named_parameters()}, launches))
+    (i0, z0, g0, l0), (i1, z1, g1, l1) = res
+    assert max_rel(i1, i0) < 1e-5
+    for a, b in zip(z1, z0):
+        assert max_rel(a, b) < 1e-4
+    worst = max((max_rel(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0)
+    print(f'batched modulations (mixing={mixing}): worst parameter gradient max-rel {worst[0]:.2e} ({worst[1]}); '
+          f'libb200gan launches {l0} -> {l1}')
+    assert worst[0] < 1e-4, worst
+    assert l1 < l0 - 40          # 14 modulation layers here: forward + backward launches per layer are gone
