@@ -744,11 +744,13 @@ def test_batched_style_modulations_equal_the_per_layer_path(mixing):
             M.Generator._precompute_modulations = saved
         res.append((img.detach().clone(), [t.grad.clone() for t in z], {k: v.grad.clone() for k, v in g.named_parameters()}, launches))
     (i0, z0, g0, l0), (i1, z1, g1, l1) = res
+    # The two passes differ by fp32 summation order only; gradients are piecewise in the leaky-ReLU gates, so one gate whose
+    # pre-activation rounds to the other side of zero moves them by ~1e-4 of their norm (scripts/determinism_probe.py): a
+    # wrong slice / missing term would show as O(1), the bound is rel-L2 5e-3.
     assert max_rel(i1, i0) < 1e-5
-    for a, b in zip(z1, z0):
-        assert max_rel(a, b) < 1e-4
-    worst = max((max_rel(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0)
-    print(f'batched modulations (mixing={mixing}): worst parameter gradient max-rel {worst[0]:.2e} ({worst[1]}); '
-          f'libb200gan launches {l0} -> {l1}')
-    assert worst[0] < 3e-4, worst
+    ez = max(rel_err(a, b) for a, b in zip(z1, z0))
+    worst = max((rel_err(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0)
+    print(f'batched modulations (mixing={mixing}): dL/dz rel-L2 {ez:.2e}, worst parameter gradient rel-L2 {worst[0]:.2e} '
+          f'({worst[1]}); libb200gan launches {l0} -> {l1}')
+    assert ez < 5e-3 and worst[0] < 5e-3, (ez, worst)
     assert l1 <= l0 - 30         # 14 modulation layers here: a skinny GEMM forward and two GEMMs backward per layer are gone
