@@ -25,6 +25,11 @@ using namespace umma;
 #define B200GAN_F32X2 1      // packed fp32 pairs in the epilogue math (umma.cuh)
 #endif
 
+#ifndef B200GAN_HALO_DEBUG
+#define B200GAN_HALO_DEBUG 0     // 1: the run-time switches of HaloParams::dbg are compiled in (they sit in the issue-critical loops)
+#endif
+constexpr bool kHaloDebug = B200GAN_HALO_DEBUG != 0;
+
 constexpr int kHaloThreads = 384;            // warp 0: TMA, 1-3: MMA issuers (2 also allocates TMEM), 4-7 and 8-11: two epilogue groups
 constexpr int kHaloIssuers = 3;              // MMA-issuing warps (1, 2, 3), tiles round-robin
 constexpr int kHaloAcc = 6;                  // max TMEM accumulators in flight (HaloParams::nacc in use; tiles alternate between the epilogue groups)
@@ -57,7 +62,8 @@ struct HaloParams {
     int f16;                             // 16-bit storage is IEEE half
     const __nv_bfloat16* addend;         // output-shaped side inputs (include/b200gan.h b200gan_conv_epilogue)
     const __nv_bfloat16* gate;
-    int dbg;                             // B200GAN_HALO_DEBUG (timing experiments only): 1 no MMA, 2 no TMA loads, 4 no stores, 8 no tcgen05.ld
+    int dbg;                             // timing experiments only (build with -DB200GAN_HALO_DEBUG=1, then env B200GAN_HALO_DEBUG):
+                                         // 1 no MMA, 2 no TMA loads, 4 no stores, 8 no tcgen05.ld
     __nv_bfloat16* y;
 };
 
@@ -193,7 +199,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
             for (int c = 0; c < p.kchunks; ++c) {
                 mbar_wait(aempty + stage, par ^ 1);
-                if (p.dbg & 2) {
+                if (kHaloDebug && (p.dbg & 2)) {
                     if (elect_one()) mbar_arrive(afull + stage);
                 } else if (elect_one()) {
                     mbar_arrive_expect_tx(afull + stage, (uint32_t)p.a_stage_bytes);
@@ -267,7 +273,7 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint32_t w_base = w_lo0 + (uint32_t)c * w_inc;
 #pragma unroll
                     for (int tap = 0; tap < taps; ++tap) {
-                        if (p.dbg & 1) break;
+                        if (kHaloDebug && (p.dbg & 1)) break;
                         const uint32_t a_lo = a_base + (uint32_t)((tap / KDIM) * PW + (tap % KDIM)) * ROW_UNITS;
                         const uint32_t w_lo = w_base + (uint32_t)tap * w_tap;
 #pragma unroll
@@ -320,8 +326,8 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (valid && p.addend) s_add = side_load16(p.addend + soff);
                 if (valid && p.gate) s_gate = side_load16(p.gate + soff);
             }
-            if (!(p.dbg & 8)) tmem_ld_x16(taddr + (uint32_t)col, v);
-            if (valid && !(p.dbg & 4)) {
+            if (!(kHaloDebug && (p.dbg & 8))) tmem_ld_x16(taddr + (uint32_t)col, v);
+            if (valid && !(kHaloDebug && (p.dbg & 4))) {
                 if (side_smem) {
                     load16<false>(p.rowscale ? my_rs + c0 : nullptr, r16, 1.f);
                     load16<false>(bs_sm ? bs_sm + c0 : nullptr, b16, 0.f);

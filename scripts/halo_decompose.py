@@ -1,4 +1,5 @@
-"""Which stage bounds conv_fwd_halo?  Times the kernel with stages switched off through B200GAN_HALO_DEBUG
+"""(Needs a library built with -DB200GAN_HALO_DEBUG=1: the switches are compiled out of the product build.)
+Which stage bounds conv_fwd_halo?  Times the kernel with stages switched off through B200GAN_HALO_DEBUG
 (1 no MMA, 2 no TMA loads, 4 no global stores, 8 no tcgen05.ld): results are garbage, only the time matters."""
 import os
 import sys

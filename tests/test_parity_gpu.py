@@ -716,41 +716,54 @@ def test_discriminator_on_concatenated_batches_equals_separate_calls(dt):
 @pytest.mark.parametrize('mixing', [False, True])
 def test_batched_style_modulations_equal_the_per_layer_path(mixing):
     """`Generator._precompute_modulations` (all `ModulatedConv2d.modulation` layers, gm.py:245/284, in one launch of the
-    mapping kernel, one more for their backward) against the per-layer EqualLinear path: image, dL/dz and every
-    parameter gradient of a first-order pass; W+ input with two latents mixed exercises the per-layer input slices."""
+    mapping kernel, one more for their backward) against the per-layer EqualLinear path ON THE SAME W+ LATENT: the values
+    every layer receives, and -- the op is linear, so there are no activation gates to flip -- dL/d(latent) and every
+    modulation parameter gradient for one random cotangent.  Then the whole generator: same image, fewer launches."""
+    from gan_control_b200 import kernels as K
     torch.manual_seed(9)
     g = M.Generator(64, 64, 3, channel_multiplier=2, conv_transpose=True).to(DEV)
-    for m in g.modules():
-        if isinstance(m, M.NoiseInjection):
-            m.weight.data.fill_(0.2)
-    z = [torch.randn(3, 64, device=DEV, requires_grad=True) for _ in range(2 if mixing else 1)]
-    noise = [torch.randn(3, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=DEV) for i in range(g.num_layers)]
-    cot = torch.randn(3, 3, 64, 64, device=DEV)
+    layers = g._modulated_layers()
+    latent = torch.randn(3, g.n_latent, 64, device=DEV)
+    if not mixing:
+        latent = latent[:, :1].repeat(1, g.n_latent, 1)
+    cots = [torch.randn(3, m.modulation.weight.shape[0], device=DEV) for m, _ in layers]
     res = []
     for batched in (False, True):
         g.zero_grad()
-        for t in z:
-            t.grad = None
+        lat = latent.clone().requires_grad_(True)
+        if batched:
+            with ops.first_order():
+                g._precompute_modulations(lat)
+            ss = [m._s_pre for m, _ in layers]
+            assert all(t is not None for t in ss)
+            for m, _ in layers:
+                m._s_pre = None
+        else:
+            ss = [m.modulation(lat[:, k]) for m, k in layers]
+        sum((t * c).sum() for t, c in zip(ss, cots)).backward()
+        res.append(([t.detach().clone() for t in ss], lat.grad.clone(),
+                    {n: p.grad.clone() for n, p in g.named_parameters() if 'modulation' in n}))
+    (s0, l0, g0), (s1, l1, g1) = res
+    assert max(max_rel(a, b) for a, b in zip(s1, s0)) < 1e-5
+    assert max_rel(l1, l0) < 1e-5
+    worst = max((max_rel(g1[k], g0[k]), k) for k in g0)
+    print(f'batched modulations (mixing={mixing}): {len(layers)} layers, worst parameter gradient max-rel {worst[0]:.2e} ({worst[1]})')
+    assert len(g0) == 2 * len(layers) and worst[0] < 1e-5, worst
+    # whole generator, first-order pass: identical image, one launch instead of one per layer each way
+    noise = [torch.randn(3, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), device=DEV) for i in range(g.num_layers)]
+    imgs, launches = [], []
+    for batched in (False, True):
         saved = M.Generator._precompute_modulations
         if not batched:
             M.Generator._precompute_modulations = lambda self, latent: None
         try:
             with ops.first_order():
-                n0 = __import__('gan_control_b200.kernels', fromlist=['x']).launch_count()
-                img, _ = g(z, noise=noise, inject_index=2)
-                (img * cot).sum().backward()
-                launches = __import__('gan_control_b200.kernels', fromlist=['x']).launch_count() - n0
+                n0 = K.launch_count()
+                img, _ = g([latent.clone().requires_grad_(True)], input_is_latent=True, noise=noise)
+                img.sum().backward()
+                launches.append(K.launch_count() - n0)
         finally:
             M.Generator._precompute_modulations = saved
-        res.append((img.detach().clone(), [t.grad.clone() for t in z], {k: v.grad.clone() for k, v in g.named_parameters()}, launches))
-    (i0, z0, g0, l0), (i1, z1, g1, l1) = res
-    # The two passes differ by fp32 summation order only; gradients are piecewise in the leaky-ReLU gates, so one gate whose
-    # pre-activation rounds to the other side of zero moves them by ~1e-4 of their norm (scripts/determinism_probe.py): a
-    # wrong slice / missing term would show as O(1), the bound is rel-L2 5e-3.
-    assert max_rel(i1, i0) < 1e-5
-    ez = max(rel_err(a, b) for a, b in zip(z1, z0))
-    worst = max((rel_err(g1[k], g0[k]), k) for k in g0 if float(g0[k].abs().max()) > 0)
-    print(f'batched modulations (mixing={mixing}): dL/dz rel-L2 {ez:.2e}, worst parameter gradient rel-L2 {worst[0]:.2e} '
-          f'({worst[1]}); libb200gan launches {l0} -> {l1}')
-    assert ez < 5e-3 and worst[0] < 5e-3, (ez, worst)
-    assert l1 <= l0 - 30         # 14 modulation layers here: a skinny GEMM forward and two GEMMs backward per layer are gone
+        imgs.append(img.detach())
+    assert max_rel(imgs[1], imgs[0]) < 1e-5
+    assert launches[1] <= launches[0] - 30, launches     # a skinny GEMM forward and two GEMMs backward per layer are gone
