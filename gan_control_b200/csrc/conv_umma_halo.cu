@@ -246,8 +246,11 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const uint32_t a_lo0 = desc_lo(smem_u32(a_buf), 16), a_inc = (uint32_t)p.a_stage_bytes >> 4;
         const int nstages = p.a_stages, kchunks = p.kchunks, bn = p.BN, total = p.total_tiles;
         const uint32_t w_tap = w_inc * (uint32_t)kchunks;               // tiles are [tap][chunk]
-        int stage = 0, par = 0, it = 0, key = -1, wpar = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        int stage = 0, par = 0, key = -1, wpar = 0;
+        // this warp's tiles are iterations mine, mine + issuers, ...: their accumulator (iteration % nacc) and barrier parity
+        // ((iteration / nacc) & 1) advance by `issuers` with a wrap -- no integer division in the issuing warp (issuers | nacc)
+        int my_acc = mine, my_par = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int wkey = p.w_per_sample ? (int)p.div_img.quot((uint32_t)tile) : 0;
             if (wkey != key) {
                 mbar_wait(wfull, wpar);
@@ -261,7 +264,9 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     if (++stage == nstages) { stage = 0; par ^= 1; }
                 continue;
             }
-            const int acc = it % p.nacc, acc_par = (it / p.nacc) & 1;
+            const int acc = my_acc, acc_par = my_par;
+            my_acc += p.issuers;
+            if (my_acc >= p.nacc) { my_acc -= p.nacc; my_par ^= 1; }
             mbar_wait(tempty + acc, acc_par ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * bn);
@@ -397,17 +402,19 @@ conv_fwd_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 }
             }
         };
-        int it = group;
+        int my_acc = group, my_par = 0;                  // iterations group, group + 2, ...: (iteration % nacc, parity), 2 | nacc
         const int first = blockIdx.x + group * gridDim.x;
         fetch_noise(first);
         prefetch_side(first);
         prefetch_side(first + 2 * (int)gridDim.x);
-        for (int tile = first; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+        for (int tile = first; tile < p.total_tiles; tile += 2 * gridDim.x) {
             uint32_t n, t, th, tw;
             p.div_img.divmod((uint32_t)tile, n, t);
             p.div_tw.divmod(t, th, tw);
             const int oy = (int)th * kHTH + h_l, ox = (int)tw * kHTW + w_l;
-            const int acc = it % p.nacc, acc_par = (it / p.nacc) & 1;
+            const int acc = my_acc, acc_par = my_par;
+            my_acc += 2;
+            if (my_acc >= p.nacc) { my_acc -= p.nacc; my_par ^= 1; }
             const bool valid = oy < p.OH && ox < p.OW;
             const uint32_t taddr = tmem_base + (uint32_t)(acc * p.BN) + ((uint32_t)(q * 32) << 16);
             if (!p.pack_out) {

@@ -8,6 +8,7 @@
 //                   IC = 32: one MMA group per ky (kx = 0,1,2 + one ignored atom), IC = 64: (kx 0,1) and (kx 2).
 //   N            = output channels of the dense gy tile.
 // All taps accumulate in TMEM (<= 6 groups x 64 columns); one fp32 atomic pass per work unit.
+#include <cstdlib>
 #include <cstring>
 
 #include "conv.cuh"
@@ -27,6 +28,7 @@ struct WhParams {
     int rowb_m, layout_m, rowb_n, layout_n;
     int PW, RH, a_slot_bytes, b_slot_bytes, stages;
     int ngroups, atoms_per_group;                         // MMA groups per tile, kx taps packed per group
+    int issuers;                                          // MMA-issuing warps (1..3): group g is issued by warp 1 + g % issuers
     int tmem_cols;
     // space-to-depth views (ConvGeom::pack_*): the packed operand is read one row phase py at a time through a 5-D
     // map (its (px, c) pair row is contiguous), IC / OC above are then the channels of that HALF of the view and the
@@ -56,8 +58,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         prefetch_tensormap(&map_gy);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tfull, 1);
+        // every issuing warp commits to a stage's `empty` and to `tfull`: the barriers complete when all of them have
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, (uint32_t)p.issuers); }
+        mbar_init(tfull, (uint32_t)p.issuers);
         mbar_init(tempty, 4);
         fence_barrier_init();
     }
@@ -105,7 +108,12 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 if (++stage == p.stages) { stage = 0; par ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp >= 1 && warp <= p.issuers) {
+        // The MMA groups of a tile (one per ky for 32 channels, two per ky for 64) write DISJOINT accumulators, so they are
+        // issued by up to three warps in parallel, each walking every tile: with ONE issuing warp the kernel ran at
+        // 1830 clk per tile for 960 clk of MMA time (24 instructions of 40 clk) -- issue-bound like the forward kernel
+        // before it got several issuers (profiles/r02_headline.md: tensor pipe 18 %, issue slots 7 %).
+        const int mine = warp - 1, n_iss = p.issuers;
         const uint32_t idesc = instr_desc_bf16(128, p.OC, 1, 1, p.f16);
         const uint32_t a_hi = desc_hi((uint32_t)(p.PW * p.rowb_m), (uint32_t)p.layout_m);     // next tile row of pixels
         const uint32_t b_hi = desc_hi(8u * (uint32_t)p.rowb_n, (uint32_t)p.layout_n);
@@ -131,6 +139,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                     int g = 0;
                     for (int ky = 0; ky < kdim; ++ky)
                         for (int kx0 = 0; kx0 < kdim; kx0 += apg, ++g) {
+                            if (g % n_iss != mine) continue;
                             const uint32_t a_g = a_st + ((uint32_t)ky * pw + (uint32_t)kx0) * row_units;
                             const uint32_t d_tmem = tmem_base + (uint32_t)(g * oc);
                             mma_issue_dyn(d_tmem, a_g, a_hi, b_st, b_hi, idesc, acc0);
@@ -236,6 +245,11 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
     p.b_slot_bytes = 128 * p.rowb_n;
     p.atoms_per_group = g.kh == 1 ? 1 : (128 / ic >= 3 ? 3 : 2);
     p.ngroups = g.kh == 1 ? 1 : g.kh * ((g.kw + p.atoms_per_group - 1) / p.atoms_per_group);
+    p.issuers = p.ngroups < 3 ? p.ngroups : 3;
+    if (const char* e = getenv("B200GAN_WGRAD_ISSUERS")) {          // timing experiments: 1 = the single-issuer kernel
+        const int v = atoi(e);
+        if (v >= 1 && v <= 3 && v <= p.ngroups) p.issuers = v;
+    }
     int cols = 32;
     while (cols < p.ngroups * p.OC) cols <<= 1;
     if (cols > 512) return B200GAN_ENOSUP;
