@@ -24,6 +24,7 @@ constexpr int kWhTW = 8, kWhTH = 16;
 struct WhParams {
     int B, H, W, IC, OC, k, pad0, per_sample;
     int tiles_h, tiles_w, tiles_per_img;
+    FastDiv div_tpi, div_tw;                              // pixel tile -> (sample, tile row, tile column) without division
     int units, units_per_wb, kt_per_unit, kt_total;       // split-K over pixel tiles
     int rowb_m, layout_m, rowb_n, layout_n;
     int PW, RH, a_slot_bytes, b_slot_bytes, stages;
@@ -81,10 +82,12 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         kt1 = min(p.kt_total, kt0 + p.kt_per_unit);
     };
     auto tile_coord = [&](int wb, int kt, int& n, int& h0, int& w0) {
-        n = p.per_sample ? wb : kt / p.tiles_per_img;
-        const int t = kt % p.tiles_per_img;
-        h0 = (t / p.tiles_w) * kWhTH;
-        w0 = (t % p.tiles_w) * kWhTW;
+        uint32_t q, t, th, tw;
+        p.div_tpi.divmod((uint32_t)kt, q, t);
+        p.div_tw.divmod(t, th, tw);
+        n = p.per_sample ? wb : (int)q;
+        h0 = (int)th * kWhTH;
+        w0 = (int)tw * kWhTW;
     };
 
     if (warp == 0) {
@@ -231,6 +234,8 @@ int conv_wgrad_halo(const void* x, const void* gy, float* gw, const ConvGeom& g,
     p.tiles_h = (g.out_h + kWhTH - 1) / kWhTH;
     p.tiles_w = (g.out_w + kWhTW - 1) / kWhTW;
     p.tiles_per_img = p.tiles_h * p.tiles_w;
+    p.div_tpi = make_fastdiv((uint32_t)p.tiles_per_img);
+    p.div_tw = make_fastdiv((uint32_t)p.tiles_w);
     const int wbs = g.w_per_sample ? g.b : 1;
     p.kt_total = g.w_per_sample ? p.tiles_per_img : p.tiles_per_img * g.b;
     int splits = (3 * sm_count() + wbs - 1) / wbs;
