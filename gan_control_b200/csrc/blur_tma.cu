@@ -24,6 +24,7 @@ struct BlurParams {
     int n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip;
     float gain;
     int tiles_x, tiles_y, chunks, total_tiles;
+    FastDiv div_chunks, div_tx, div_ty;      // tile decode without integer division (every thread decodes every tile)
     const float* taps;
     __nv_bfloat16* y;
     FirEpilogue ep;
@@ -88,11 +89,11 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_con
     }
 
     auto issue = [&](int tile, int stage) {
-        int t = tile;
-        const int chunk = t % p.chunks; t /= p.chunks;
-        const int bx = t % p.tiles_x; t /= p.tiles_x;
-        const int by = t % p.tiles_y;
-        const int b = t / p.tiles_y;
+        uint32_t t, uchunk, ubx, uby, ub;
+        p.div_chunks.divmod((uint32_t)tile, t, uchunk);
+        p.div_tx.divmod(t, ub, ubx);
+        p.div_ty.divmod(ub, t, uby);
+        const int chunk = (int)uchunk, bx = (int)ubx, by = (int)uby, b = (int)t;
         mbar_arrive_expect_tx(full + stage, (uint32_t)(PITCH * BOXH));
         tma_load_4d(smem + stage * STAGE, &map_x, full + stage, chunk * CH, bx * TW - p.pad0_x, by * kBlurRows - p.pad0_y, b);
     };
@@ -104,11 +105,11 @@ __global__ void __launch_bounds__(kBlurThreads) blur_tma_kernel(const __grid_con
         const int next = tile + gridDim.x;
         if (tid == 0 && next < p.total_tiles) issue(next, stage ^ 1);      // stage^1 was released by the barrier below
         mbar_wait(full + stage, (it >> 1) & 1);
-        int t = tile;
-        const int chunk = t % p.chunks; t /= p.chunks;
-        const int bx = t % p.tiles_x; t /= p.tiles_x;
-        const int by = t % p.tiles_y;
-        const int b = t / p.tiles_y;
+        uint32_t t, uchunk, ubx, uby, ub;
+        p.div_chunks.divmod((uint32_t)tile, t, uchunk);
+        p.div_tx.divmod(t, ub, ubx);
+        p.div_ty.divmod(ub, t, uby);
+        const int chunk = (int)uchunk, bx = (int)ubx, by = (int)uby, b = (int)t;
         const uint8_t* tbase = smem + stage * STAGE + tid * 16;
         const int ox = bx * TW + tx, oy0 = by * kBlurRows;
         float2 acc[4][4];                                   // rolling output rows x channel pairs
@@ -234,6 +235,9 @@ int blur_tma(const void* x, void* y, const float* taps, int n, int in_h, int in_
     p.tiles_y = (out_h + kBlurRows - 1) / kBlurRows;
     p.chunks = c / ch;
     p.total_tiles = n * p.tiles_y * p.tiles_x * p.chunks;
+    p.div_chunks = make_fastdiv((uint32_t)p.chunks);
+    p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
+    p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
     if (p.total_tiles == 0) return 0;
     CUtensorMap map_x;
     uint64_t dims[4] = {(uint64_t)c, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)n};

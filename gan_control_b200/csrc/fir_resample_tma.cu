@@ -22,6 +22,7 @@ struct FirResampleParams {
     int n, in_h, in_w, c, out_h, out_w, kh, kw, pad0_y, pad0_x, flip;
     float gain;
     int tiles_x, tiles_y, chunks, total_tiles;
+    FastDiv div_chunks, div_tx, div_ty;      // tile decode without integer division
     const float* taps;
     __nv_bfloat16* y;
 };
@@ -57,10 +58,11 @@ __device__ __forceinline__ void load_taps(float* taps, const FirResampleParams& 
 }
 
 __device__ __forceinline__ void decode_tile(const FirResampleParams& p, int tile, int& chunk, int& bx, int& by, int& b) {
-    chunk = tile % p.chunks; tile /= p.chunks;
-    bx = tile % p.tiles_x; tile /= p.tiles_x;
-    by = tile % p.tiles_y;
-    b = tile / p.tiles_y;
+    uint32_t t, uchunk, ubx, uby, ub;
+    p.div_chunks.divmod((uint32_t)tile, t, uchunk);
+    p.div_tx.divmod(t, ub, ubx);
+    p.div_ty.divmod(ub, t, uby);
+    chunk = (int)uchunk; bx = (int)ubx; by = (int)uby; b = (int)t;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -288,6 +290,9 @@ int fir_resample_tma(const void* x, void* y, const float* taps, int n, int in_h,
     p.chunks = c / ch;
     p.total_tiles = n * p.tiles_y * p.tiles_x * p.chunks;
     if (p.total_tiles == 0) return 0;
+    p.div_chunks = make_fastdiv((uint32_t)p.chunks);
+    p.div_tx = make_fastdiv((uint32_t)p.tiles_x);
+    p.div_ty = make_fastdiv((uint32_t)p.tiles_y);
     const int box_w = down == 2 ? 2 * tw + 2 : tw / 2 + 2;
     const int box_h = down == 2 ? 2 * rows + 2 : 6;
     CUtensorMap map_x;
