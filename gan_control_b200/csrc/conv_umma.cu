@@ -17,6 +17,7 @@
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each),
 // warp 2 = TMEM allocator, warps 4..7 = epilogue (thread t <-> TMEM lane t <-> pixel t of the tile).
+#include <cstdlib>
 #include <cstring>
 
 #include "conv.cuh"
@@ -48,6 +49,7 @@ struct FwdParams {
     int es, os;
     int BN, n_oc_tiles;
     int kchunks, kc, row_bytes, layout;
+    int sub;                         // 64-channel sub-tiles per pipeline stage (2: K = 128 per barrier round, see conv_fwd_umma)
     int taps_total, w_per_sample;
     int total_tiles;
     FastDiv div_oc;
@@ -140,12 +142,16 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const int wz0 = (p.w_per_sample ? t.n0 : 0) * p.taps_total;
             for (int tp = 0; tp < P.ntaps; ++tp) {
                 const int cx = t.w0 * p.es + P.dx[tp], cy = t.h0 * p.es + P.dy[tp];
-                for (int c = 0; c < p.kchunks; ++c) {
+                for (int c = 0; c < p.kchunks; c += p.sub) {
                     mbar_wait(empty + stage, par ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(full + stage, (uint32_t)p.tx_bytes);
-                        tma_load_4d(a_buf + stage * p.a_stage_bytes, &map_x, full + stage, c * p.kc, cx, cy, t.n0);
-                        tma_load_3d(b_buf + stage * p.b_stage_bytes, &map_w, full + stage, c * p.kc, t.ocb * p.BN, wz0 + P.wtap[tp]);
+                        for (int j = 0; j < p.sub; ++j) {
+                            tma_load_4d(a_buf + stage * p.a_stage_bytes + j * (kTileM * p.row_bytes), &map_x, full + stage,
+                                        (c + j) * p.kc, cx, cy, t.n0);
+                            tma_load_3d(b_buf + stage * p.b_stage_bytes + j * (p.BN * p.row_bytes), &map_w, full + stage,
+                                        (c + j) * p.kc, t.ocb * p.BN, wz0 + P.wtap[tp]);
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; par ^= 1; }
@@ -160,13 +166,14 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const uint32_t a_inc = (uint32_t)p.a_stage_bytes >> 4, b_inc = (uint32_t)p.b_stage_bytes >> 4;
         const int nstages = p.stages, kchunks = p.kchunks, bn = p.BN, total = p.total_tiles;
         const bool k4 = p.kc == 64;
+        const uint32_t a_sub = (uint32_t)(kTileM * p.row_bytes) >> 4, b_sub = (uint32_t)(p.BN * p.row_bytes) >> 4;
         int stage = 0, par = 0, it = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
             const TileCoord t = decode_tile(p, tile);
             const int acc = it & 1, acc_par = (it >> 1) & 1;
             mbar_wait(tempty + acc, acc_par ^ 1);
             tc_fence_after();
-            const int ksteps = p.phase[t.phase].ntaps * kchunks;
+            const int ksteps = p.phase[t.phase].ntaps * (kchunks / p.sub);
             if (ksteps == 0) {           // phase without taps: the epilogue writes zeros
                 if (elect_one()) mbar_arrive(tfull + acc);
                 __syncwarp();
@@ -185,6 +192,13 @@ conv_fwd_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     if (k4) {
                         mma_issue<true>(d_tmem, a_lo + 4, hi, b_lo + 4, hi, idesc);
                         mma_issue<true>(d_tmem, a_lo + 6, hi, b_lo + 6, hi, idesc);
+                    }
+                    if (p.sub == 2) {           // second 64-channel sub-tile of the stage (always 128-byte rows: k4)
+                        const uint32_t a2 = a_lo + a_sub, b2 = b_lo + b_sub;
+                        mma_issue<true>(d_tmem, a2, hi, b2, hi, idesc);
+                        mma_issue<true>(d_tmem, a2 + 2, hi, b2 + 2, hi, idesc);
+                        mma_issue<true>(d_tmem, a2 + 4, hi, b2 + 4, hi, idesc);
+                        mma_issue<true>(d_tmem, a2 + 6, hi, b2 + 6, hi, idesc);
                     }
                     mma_commit(empty + stage);
                     if (ks == ksteps - 1) mma_commit(tfull + acc);
@@ -490,9 +504,17 @@ int conv_fwd_umma(const void* x, const void* w, void* y, const ConvGeom& g, cons
     }
     p.total_tiles = tiles;
     p.div_oc = make_fastdiv((uint32_t)p.n_oc_tiles);
-    p.a_stage_bytes = kTileM * p.row_bytes;
-    p.b_stage_bytes = p.BN * p.row_bytes;
-    p.tx_bytes = p.rows * p.row_bytes + p.BN * p.row_bytes;
+    // K = 128 per pipeline stage where the stage is short: at N <= 128 the four MMAs of a 64-channel stage (<= 256 clk)
+    // take no longer than the issuing warp's barrier round (wait, fence, elect, commit, ring advance), so the general
+    // engine ran issue-bound there (128 -> 128 @256^2: 50 % of the tensor peak, N = 64 transposed-convolution phases
+    // 25 %; profiles/r02_launches_step.md).  Two sub-tiles per stage halve the rounds per tile.
+    p.sub = (g.ic % 128 == 0 && p.row_bytes == 128 && p.BN <= 128) ? 2 : 1;
+    if (const char* e = getenv("B200GAN_UMMA_SUB")) {               // timing experiments: 1 = one sub-tile per stage
+        if (atoi(e) == 1) p.sub = 1;
+    }
+    p.a_stage_bytes = p.sub * kTileM * p.row_bytes;
+    p.b_stage_bytes = p.sub * p.BN * p.row_bytes;
+    p.tx_bytes = p.sub * (p.rows * p.row_bytes + p.BN * p.row_bytes);
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     p.stages = (200 * 1024) / stage_bytes;
     if (p.stages > 12) p.stages = 12;
