@@ -1,4 +1,5 @@
-"""Halo weight-gradient kernel: one MMA-issuing warp vs one per accumulator group (B200GAN_WGRAD_ISSUERS), timed alone
+"""Weight-gradient kernels (halo and general tcgen05 engine): one MMA-issuing warp vs one per accumulator group
+(B200GAN_WGRAD_ISSUERS), timed alone
 (CUDA events, L2 flushed), batch 16, bf16."""
 import os
 import sys
@@ -30,7 +31,8 @@ def timed(fn, reps=8):
     return sorted(ts)[len(ts) // 2]
 
 
-for res, ch, ps in [(1024, 32, True), (1024, 32, False), (512, 64, True), (512, 64, False)]:
+for res, ch, ps in [(1024, 32, True), (1024, 32, False), (512, 64, True), (512, 64, False),
+                    (256, 128, True), (256, 128, False), (128, 256, True), (64, 512, False)]:      # last four: general engine
     x = torch.randn(16, res, res, ch, device=dev).bfloat16()
     gy = torch.randn(16, res, res, ch, device=dev).bfloat16()
     out = {}
