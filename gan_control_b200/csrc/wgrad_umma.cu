@@ -15,7 +15,6 @@
 //   coalesced).
 // Geometry: stride-2 convs read x through TMA element strides; transposed convs (up = 2) are split
 // into their 4 output-parity phases and read gy through element strides.  Out-of-bounds = zeros.
-#include <cstdlib>
 #include <cstring>
 
 #include "conv.cuh"
@@ -56,7 +55,6 @@ struct WgParams {
     int total_units;
     int sa_stages, sb_stages, a_slot_bytes, b_slot_bytes;
     int tmem_cols;
-    int issuers;             // MMA-issuing warps (1..3): accumulator group gl of a unit is issued by warp 1 + gl % issuers
     int f16;                 // operands are IEEE half instead of bfloat16
     float* gw;
 };
@@ -119,10 +117,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
-        // the gy tile of a K step is read by every issuing warp's MMAs, and every one of them finishes a unit: those two
-        // barriers complete when ALL issuers have committed; an x tap tile (`aempty`) is consumed by exactly one of them
-        for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull + s, 1); mbar_init(bempty + s, (uint32_t)p.issuers); }
-        mbar_init(tfull, (uint32_t)p.issuers);
+        for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull + s, 1); mbar_init(bempty + s, 1); }
+        mbar_init(tfull, 1);
         mbar_init(tempty, 4);
         fence_barrier_init();
     }
@@ -166,13 +162,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 }
             }
         }
-    } else if (warp >= 1 && warp <= p.issuers) {
-        // ================= MMA issuers (whole warps, elected lane issues) =================
-        // The accumulator groups of a unit are independent, so up to three warps issue them in parallel (group gl by
-        // warp 1 + gl % issuers); all of them walk both rings.  With one issuer a group stage of 8 MMAs (512 clk at
-        // N = 128) was not much longer than its barrier round: 43 % of the tensor peak at 128 -> 128 @256^2 against a
-        // shared-memory bound of ~62 %.
-        const int mine = warp - 1, n_iss = p.issuers;
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp, elected lane issues) =================
         const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1, p.f16);        // both operands MN-major
         const int ksteps = p.rows / 16;
         const uint32_t a_hi = desc_hi(8u * (uint32_t)p.rowb_m, (uint32_t)p.layout_m);
@@ -190,30 +181,24 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 mbar_wait(bfull + bs, bpar);
                 const uint32_t b_lo = b_lo0 + (uint32_t)bs * b_inc;
                 const uint32_t first = kt != u.kt0;
-                tc_fence_after();
                 for (int gl = 0; gl < u.ng; ++gl) {
-                    if (gl % n_iss == mine) {
-                        mbar_wait(afull + as, apar);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)as * a_inc;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(gl * nn);
-                            mma_issue_dyn(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
-                            for (int ks = 1; ks < ksteps; ++ks)
-                                mma_issue<true>(d_tmem, a_lo + (uint32_t)ks * a_kstep, a_hi, b_lo + (uint32_t)ks * b_kstep, b_hi, idesc);
-                            mma_commit(aempty + as);
+                    mbar_wait(afull + as, apar);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)as * a_inc;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(gl * nn);
+                        mma_issue_dyn(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                        for (int ks = 1; ks < ksteps; ++ks)
+                            mma_issue<true>(d_tmem, a_lo + (uint32_t)ks * a_kstep, a_hi, b_lo + (uint32_t)ks * b_kstep, b_hi, idesc);
+                        mma_commit(aempty + as);
+                        if (gl == u.ng - 1) {
+                            mma_commit(bempty + bs);
+                            if (kt == u.kt1 - 1) mma_commit(tfull);
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                     if (++as == sa_stages) { as = 0; apar ^= 1; }
                 }
-                // every issuer releases the gy tile (a commit with no MMA of its own pending arrives at once) and, after the
-                // last K step, reports its part of the unit
-                if (elect_one()) {
-                    mma_commit(bempty + bs);
-                    if (kt == u.kt1 - 1) mma_commit(tfull);
-                }
-                __syncwarp();
                 if (++bs == sb_stages) { bs = 0; bpar ^= 1; }
             }
             if (u.kt1 <= u.kt0) {
@@ -405,11 +390,6 @@ int conv_wgrad_umma(const void* x, const void* gy, float* gw, const ConvGeom& g,
         max_groups = m > max_groups ? m : max_groups;
     }
     p.tmem_cols = wg_pow2_ge(max_groups * p.N, 32);
-    p.issuers = max_groups < 3 ? (max_groups < 1 ? 1 : max_groups) : 3;
-    if (const char* e = getenv("B200GAN_WGRAD_ISSUERS")) {          // timing experiments: 1 = the single-issuer kernel
-        const int v = atoi(e);
-        if (v >= 1 && v <= 3) p.issuers = v;
-    }
 
     CUtensorMap map_x, map_gy;
     {
