@@ -1,5 +1,6 @@
-"""Weight-gradient kernels (halo and general tcgen05 engine): one MMA-issuing warp vs one per accumulator group
-(B200GAN_WGRAD_ISSUERS), timed alone
+"""Weight-gradient kernels: one MMA-issuing warp vs one per accumulator group (B200GAN_WGRAD_ISSUERS; honoured by the HALO
+kernel -- the multi-issuer build of the general kernel was reverted, see profiles/r02_summary.md, so its rows show no
+difference), timed alone
 (CUDA events, L2 flushed), batch 16, bf16."""
 import os
 import sys
