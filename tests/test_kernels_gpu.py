@@ -517,3 +517,43 @@ def test_conv_epilogue_addend_and_gate(case, dt):
     close(y_gate, R.conv_fwd(xr, wr, oh, ow, up, down, pad0, None, rs.double(), None, None, 0.2, 2 ** 0.5, addend=addr, gate=gater, **kw),
           dt, 'addend + gate')
     close(y_gate2, R.conv_fwd(xr, wr, oh, ow, up, down, pad0, None, None, None, None, 0.2, 2 ** 0.5, gate=gater, **kw), dt, 'gate')
+
+
+def test_protocol_stress_multi_issuer_wgrad_and_sub_tiles():
+    """Barrier-protocol stress of the round-2 pipeline changes over many small shapes (a mismatch shows as a device-side
+    barrier timeout / wrong values): the halo weight gradient with one issuing warp per accumulator group against the
+    CUDA-core engine, and the general forward engine with two 64-channel sub-tiles per stage against one (bit for bit)."""
+    import os
+    torch.manual_seed(0)
+    for b in (1, 3, 8, 17):
+        for h, w in ((16, 8), (48, 40), (64, 24), (130, 70)):
+            for ch in (32, 64):
+                for k in (1, 3):
+                    for ps in (False, True):
+                        x = torch.randn(b, h, w, ch, device='cuda').bfloat16()
+                        gy = torch.randn(b, h, w, ch, device='cuda').bfloat16()
+                        with engines('wgrad_halo'):
+                            gw = K.conv_wgrad(x, gy, k, k, 1, 1, k // 2, ps)
+                        prev = K.set_conv_engine(1)
+                        try:
+                            ref = K.conv_wgrad(x, gy, k, k, 1, 1, k // 2, ps)
+                        finally:
+                            K.set_conv_engine(prev)
+                        assert float((gw - ref).abs().max() / ref.abs().max()) < 2e-3, (b, h, w, ch, k, ps)
+    for b in (1, 8):
+        for h in (16, 33, 64):
+            for ic, oc in ((128, 64), (128, 128), (256, 32), (384, 128)):
+                for up, down, pad0 in ((1, 1, 1), (2, 1, 2), (1, 2, 0)):
+                    hh = h + 1 if (down == 2 and h % 2 == 0) else h
+                    oh = 2 * hh + 1 if up == 2 else (hh + 2 * pad0 - 3) // down + 1
+                    x = torch.randn(b, hh, hh, ic, device='cuda').bfloat16()
+                    wt = (torch.randn(1, 3, 3, oc, ic, device='cuda') / (3 * ic ** 0.5)).bfloat16()
+                    with engines('fwd_umma'):
+                        y = K.conv_fwd(x, wt, oh, oh, up, down, pad0)
+                    os.environ['B200GAN_UMMA_SUB'] = '1'
+                    try:
+                        y1 = K.conv_fwd(x, wt, oh, oh, up, down, pad0)
+                    finally:
+                        os.environ.pop('B200GAN_UMMA_SUB', None)
+                    assert torch.equal(y, y1), (b, hh, ic, oc, up, down)
+    torch.cuda.synchronize()
