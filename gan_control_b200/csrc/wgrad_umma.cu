@@ -15,6 +15,7 @@
 //   coalesced).
 // Geometry: stride-2 convs read x through TMA element strides; transposed convs (up = 2) are split
 // into their 4 output-parity phases and read gy through element strides.  Out-of-bounds = zeros.
+#include <cstdlib>
 #include <cstring>
 
 #include "conv.cuh"
@@ -55,6 +56,7 @@ struct WgParams {
     int total_units;
     int sa_stages, sb_stages, a_slot_bytes, b_slot_bytes;
     int tmem_cols;
+    int issuers;             // MMA-issuing warps (1..3): accumulator group gl of a unit is issued by warp 1 + gl % issuers
     int f16;                 // operands are IEEE half instead of bfloat16
     float* gw;
 };
@@ -116,9 +118,14 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         prefetch_tensormap(&map_gy);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
-        for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull + s, 1); mbar_init(bempty + s, 1); }
-        mbar_init(tfull, 1);
+        // Every issuing warp waits on EVERY full barrier and arrives on EVERY empty one, owner of the stage or not: a parity
+        // wait cannot tell "one phase early" from "done" nor "two phases late" from "pending", so a warp that skipped the
+        // stages of the other warps' groups could pass a wait before the previous fill had landed, or be lapped by the
+        // producer (the first multi-issuer version did skip them and an epilogue wait timed out once; profiles/r02_summary.md).
+        const uint32_t n_iss = (uint32_t)p.issuers;
+        for (int s = 0; s < p.sa_stages; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, n_iss); }
+        for (int s = 0; s < p.sb_stages; ++s) { mbar_init(bfull + s, 1); mbar_init(bempty + s, n_iss); }
+        mbar_init(tfull, n_iss);
         mbar_init(tempty, 4);
         fence_barrier_init();
     }
@@ -162,8 +169,11 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer (whole warp, elected lane issues) =================
+    } else if (warp >= 1 && warp <= p.issuers) {
+        // ================= MMA issuers (whole warps, elected lane issues) =================
+        // The accumulator groups of a unit are independent: group gl is issued by warp 1 + gl % issuers.  All issuers walk
+        // both rings in lockstep with the producer (see the barrier counts above).
+        const int mine = warp - 1, n_iss = p.issuers;
         const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1, p.f16);        // both operands MN-major
         const int ksteps = p.rows / 16;
         const uint32_t a_hi = desc_hi(8u * (uint32_t)p.rowb_m, (uint32_t)p.layout_m);
@@ -172,7 +182,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const uint32_t a_inc = (uint32_t)p.a_slot_bytes >> 4, b_inc = (uint32_t)p.b_slot_bytes >> 4;
         const uint32_t a_kstep = (uint32_t)p.rowb_m, b_kstep = (uint32_t)p.rowb_n;     // 16 rows * row_bytes >> 4
         const int sa_stages = p.sa_stages, sb_stages = p.sb_stages, nn = p.N, total = p.total_units;
-        int as = 0, apar = 0, bs = 0, bpar = 0, it = 0;
+        int as = 0, apar = 0, bs = 0, bpar = 0, it = 0, owner = 0;
         for (int unit = blockIdx.x; unit < total; unit += gridDim.x, ++it) {
             const WgUnit u = wg_decode(p, unit);
             mbar_wait(tempty, (it & 1) ^ 1);
@@ -181,22 +191,29 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 mbar_wait(bfull + bs, bpar);
                 const uint32_t b_lo = b_lo0 + (uint32_t)bs * b_inc;
                 const uint32_t first = kt != u.kt0;
+                owner = 0;
                 for (int gl = 0; gl < u.ng; ++gl) {
                     mbar_wait(afull + as, apar);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_lo = a_lo0 + (uint32_t)as * a_inc;
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(gl * nn);
-                        mma_issue_dyn(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
-                        for (int ks = 1; ks < ksteps; ++ks)
-                            mma_issue<true>(d_tmem, a_lo + (uint32_t)ks * a_kstep, a_hi, b_lo + (uint32_t)ks * b_kstep, b_hi, idesc);
-                        mma_commit(aempty + as);
+                        if (owner == mine) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)as * a_inc;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(gl * nn);
+                            mma_issue_dyn(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+                            for (int ks = 1; ks < ksteps; ++ks)
+                                mma_issue<true>(d_tmem, a_lo + (uint32_t)ks * a_kstep, a_hi, b_lo + (uint32_t)ks * b_kstep, b_hi, idesc);
+                            mma_commit(aempty + as);
+                        } else {
+                            mbar_arrive(aempty + as);        // seen, not read
+                        }
                         if (gl == u.ng - 1) {
+                            // a commit with no MMA of this warp pending arrives at once
                             mma_commit(bempty + bs);
                             if (kt == u.kt1 - 1) mma_commit(tfull);
                         }
                     }
                     __syncwarp();
+                    if (++owner == n_iss) owner = 0;
                     if (++as == sa_stages) { as = 0; apar ^= 1; }
                 }
                 if (++bs == sb_stages) { bs = 0; bpar ^= 1; }
@@ -390,6 +407,13 @@ int conv_wgrad_umma(const void* x, const void* gy, float* gw, const ConvGeom& g,
         max_groups = m > max_groups ? m : max_groups;
     }
     p.tmem_cols = wg_pow2_ge(max_groups * p.N, 32);
+    // One issuer ships.  B200GAN_WGRAD_GENERAL_ISSUERS=2|3 spreads the accumulator groups over that many warps (-9..-13 % on
+    // the 128..512-channel layers); it has passed scripts/stress_wgrad_general.py but not a full round of use.
+    p.issuers = 1;
+    if (const char* e = getenv("B200GAN_WGRAD_GENERAL_ISSUERS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 3) p.issuers = v < max_groups ? v : (max_groups < 1 ? 1 : max_groups);
+    }
 
     CUtensorMap map_x, map_gy;
     {

@@ -557,3 +557,32 @@ def test_protocol_stress_multi_issuer_wgrad_and_sub_tiles():
                         os.environ.pop('B200GAN_UMMA_SUB', None)
                     assert torch.equal(y, y1), (b, hh, ic, oc, up, down)
     torch.cuda.synchronize()
+
+
+def test_general_wgrad_issuer_counts_agree():
+    """The general weight-gradient kernel with two and three MMA-issuing warps (B200GAN_WGRAD_GENERAL_ISSUERS, opt-in)
+    against the shipped single issuer, on the ring geometries where skipped barrier phases once hung a block (oc = 64 with
+    ic >= 128: five x stages, eight groups per K step; the 4 / 2 / 2 / 1-group phases of the transposed conv) --
+    profiles/r02_wgrad_general_issuers.md.  Differences are the order of the split-K fp32 atomics."""
+    import os
+    torch.manual_seed(0)
+    env = 'B200GAN_WGRAD_GENERAL_ISSUERS'
+    for b in (1, 8):
+        for h in (16, 33, 64):
+            for ic, oc in ((128, 64), (256, 64), (128, 128), (64, 128), (512, 512)):
+                for k, up, down, pad0 in ((3, 1, 1, 1), (3, 2, 1, 2), (3, 1, 2, 0), (1, 1, 1, 0)):
+                    hh = h + 1 if (down == 2 and h % 2 == 0) else h
+                    oh = 2 * hh + 1 if up == 2 else (hh + 2 * pad0 - k) // down + 1
+                    for ps in (False, True):
+                        x = torch.randn(b, hh, hh, ic, device='cuda').bfloat16()
+                        gy = torch.randn(b, oh, oh, oc, device='cuda').bfloat16()
+                        with engines('wgrad_umma'):
+                            ref = K.conv_wgrad(x, gy, k, k, up, down, pad0, ps)
+                        for iss in ('2', '3'):
+                            os.environ[env] = iss
+                            try:
+                                got = K.conv_wgrad(x, gy, k, k, up, down, pad0, ps)
+                            finally:
+                                os.environ.pop(env, None)
+                            assert float((got - ref).abs().max() / ref.abs().max()) < 1e-4, (b, hh, ic, oc, k, up, down, ps, iss)
+    torch.cuda.synchronize()
